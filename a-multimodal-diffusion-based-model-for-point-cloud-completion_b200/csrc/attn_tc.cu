@@ -1,0 +1,306 @@
+// bf16 flash attention (head dim 64, non-causal) on tcgen05 tensor cores.
+//
+// One CTA = one 128-query tile of one (batch, head); 192 threads:
+//   warp 0   : TMA producer -- Q once, then a 2-stage ring of K/V tiles (128 keys x 64),
+//              read straight out of the packed projection buffers through 4-D tensor maps
+//              {64, H, L, B} (rows past L are zero-filled by TMA, so tails need no copies)
+//   warp 1   : MMA issuer   -- S = Q K^T (M128 x N128 x K64) and O_j = P_j V_j (M128 x N64 x
+//              K128, V consumed as an MN-major operand), accumulators in TMEM
+//   warps 2-5: softmax      -- thread = query row: tcgen05.ld S, fp32 online softmax in the
+//              exp2 domain (scale folded in), P_j written back as bf16 (to TMEM, or to
+//              swizzled shared memory in the SS variant), running O rescaled in registers
+// TMEM budget 256 columns (S 128 | P 64 | O 64) so two CTAs are co-resident per SM and
+// one CTA's softmax overlaps the other's MMAs.
+#include "common.cuh"
+#include "tc_sm100.cuh"
+
+namespace pcd {
+
+using namespace tc;
+
+constexpr int T_BQ = 128, T_BKV = 128, T_HD = 64;
+constexpr int T_TILE_BYTES = T_BKV * T_HD * 2;  // 16 KB (Q, K and V tiles alike)
+
+template <bool P_TMEM>
+struct AttnCfg {
+  static constexpr int KV_STAGES = 2;
+  static constexpr int P_BYTES = P_TMEM ? 0 : 2 * T_TILE_BYTES;
+  static constexpr int TILE_BYTES = T_TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES;
+  static constexpr int SMEM_BYTES = TILE_BYTES + 1024 + 128;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int S_COL = 0, P_COL = 128, O_COL = 192;
+};
+
+template <bool P_TMEM>
+__global__ void __launch_bounds__(192, P_TMEM ? 2 : 1)
+attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs,
+                    int64_t o_ls, int len_q, int len_kv, float scale_log2) {
+  using Cfg = AttnCfg<P_TMEM>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + T_TILE_BYTES;                        // [KV_STAGES]
+  unsigned char* sV = sK + Cfg::KV_STAGES * T_TILE_BYTES;       // [KV_STAGES]
+  unsigned char* sP = sV + Cfg::KV_STAGES * T_TILE_BYTES;       // SS variant only (2 slabs of 64 keys)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * T_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int num_kv = (len_kv + T_BKV - 1) / T_BKV;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmK);
+    prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // --------------------------- TMA producer ---------------------------
+    if (lane == 0) {
+      mbar_expect_tx(q_full, T_TILE_BYTES);
+      tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+      for (int j = 0; j < num_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * T_TILE_BYTES);
+        tma_load_4d(sK + st * T_TILE_BYTES, &tmK, &kv_full[st], 0, h, j * T_BKV, b);
+        tma_load_4d(sV + st * T_TILE_BYTES, &tmV, &kv_full[st], 0, h, j * T_BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------- MMA issuer ----------------------------
+    const uint32_t s_tmem = tmem_base + Cfg::S_COL;
+    const uint32_t p_tmem = tmem_base + Cfg::P_COL;
+    const uint32_t o_tmem = tmem_base + Cfg::O_COL;
+    constexpr uint32_t idesc_pv = idesc_bf16_f32(T_BQ, T_HD, /*B MN-major*/ 1);
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        int nvalid = min(T_BKV, len_kv - j * T_BKV);
+        int n = max(16, (nvalid + 15) & ~15);
+        const uint32_t idesc_qk = idesc_bf16_f32(T_BQ, n, 0);
+        const uint64_t adesc = smem_desc_sw128(smem_u32(sQ));
+        const uint64_t bdesc = smem_desc_sw128(smem_u32(sK + st * T_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < T_HD / 16; ++k) umma_bf16_ss(s_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(s_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < num_kv; ++j) {
+      mbar_wait(p_ready, j & 1);
+      tcgen05_fence_after();
+      if (j + 1 < num_kv) issue_qk(j + 1);  // S is free: every softmax thread has read S_j
+      if (lane == 0) {
+        const int st = j & 1;
+        int nvalid = min(T_BKV, len_kv - j * T_BKV);
+        int nks = (nvalid + 15) >> 4;  // 16 keys per MMA
+        const uint32_t v_addr = smem_u32(sV + st * T_TILE_BYTES);
+        for (int kk = 0; kk < nks; ++kk) {
+          // V tile: 128 key rows of 128 B; 16 keys = two 8-row swizzle groups (SBO 1024)
+          const uint64_t bdesc = smem_desc_sw128(v_addr + kk * 2048);
+          if (P_TMEM) {
+            umma_bf16_ts(o_tmem, p_tmem + kk * 8, bdesc, idesc_pv, kk != 0);
+          } else {
+            const uint64_t adesc = smem_desc_sw128(smem_u32(sP) + (kk >> 2) * T_TILE_BYTES + (kk & 3) * 32);
+            umma_bf16_ss(o_tmem, adesc, bdesc, idesc_pv, kk != 0);
+          }
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ----------------------------- softmax ------------------------------
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_off + Cfg::S_COL;
+    const uint32_t p_tmem = tmem_base + lane_off + Cfg::P_COL;
+    const uint32_t o_tmem = tmem_base + lane_off + Cfg::O_COL;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    float o_acc[T_HD];
+#pragma unroll
+    for (int c = 0; c < T_HD; ++c) o_acc[c] = 0.f;
+
+    for (int j = 0; j < num_kv; ++j) {
+      const int nvalid = min(T_BKV, len_kv - j * T_BKV);
+      const int nchunks = (nvalid + 31) >> 5;
+      mbar_wait(s_full, j & 1);
+      tcgen05_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(s_tmem + c * 32, r);
+        tmem_ld_wait();
+        const int lim = nvalid - c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(r[i]);
+          mx = fmaxf(mx, (i < lim) ? v : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * scale_log2);
+      const float alpha = ex2_approx(m_run - m_new);
+      // pass 2: P = exp2(S*scale - m), row sum, bf16 pack, hand-off
+      float sum = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(s_tmem + c * 32, r);
+        tmem_ld_wait();
+        const int lim = nvalid - c * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
+          float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
+          if (i >= lim) p0 = 0.f;
+          if (i + 1 >= lim) p1 = 0.f;
+          sum += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        if (P_TMEM) {
+          tmem_st_32x32b_x16(p_tmem + c * 16, pk);
+        } else {
+          // K-major bf16 tile, 128B swizzle: 16-byte chunk index ^= (row & 7)
+          unsigned char* prow = sP + (c >> 1) * T_TILE_BYTES + row_in_tile * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int chunk = ((c & 1) * 4 + i) ^ (row_in_tile & 7);
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+        }
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      // fold the previous tile's O_{j-1} = P_{j-1} V_{j-1} into the running output
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(o_tmem + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
+        }
+      }
+      alpha_prev = alpha;
+      if (P_TMEM) {
+        tmem_st_wait();
+      } else {
+        fence_proxy_async_smem();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // last tile
+    mbar_wait(o_full, (num_kv - 1) & 1);
+    tcgen05_fence_after();
+    const float inv = 1.f / l_run;
+    const int row = q0 + row_in_tile;
+    uint16_t* orow = out + b * o_bs + (int64_t)row * o_ls + h * T_HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(o_tmem + c * 32, r);
+      tmem_ld_wait();
+      if (row < len_q) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = fmaf(o_acc[c * 32 + i + t], alpha_prev, __uint_as_float(r[i + t])) * inv;
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <bool P_TMEM>
+static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                          uint16_t* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
+                          int len_kv, float scale_log2, cudaStream_t st) {
+  using Cfg = AttnCfg<P_TMEM>;
+  auto kern = attn_bf16_tc_kernel<P_TMEM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("attention_bf16: cudaFuncSetAttribute(%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return PCD_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(len_q, T_BQ), heads, batch);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2);
+  PCD_CHECK_LAUNCH("attention_bf16");
+  return PCD_OK;
+}
+
+static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batch, int heads, int len) {
+  uint64_t dims[4] = {T_HD, (uint64_t)heads, (uint64_t)len, (uint64_t)batch};
+  uint64_t strides[3] = {(uint64_t)op->head_stride * 2, (uint64_t)op->row_stride * 2, (uint64_t)op->batch_stride * 2};
+  uint32_t box[4] = {T_HD, 1, T_BKV, 1};
+  return encode_tmap_bf16(m, op->ptr, 4, dims, strides, box);
+}
+
+int g_attn_variant = 1;  // 1: P in TMEM (TS MMA, 2 CTAs/SM); 0: P in shared memory (SS MMA)
+
+int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
+                          const pcd_attn_operand* v, uint16_t* out, int64_t o_bs, int64_t o_ls,
+                          int batch, int heads, int len_q, int len_kv, float q_scale, float k_scale,
+                          cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_operand_map(&tq, q, batch, heads, len_q)) != PCD_OK) return rc;
+  if ((rc = make_operand_map(&tk, k, batch, heads, len_kv)) != PCD_OK) return rc;
+  if ((rc = make_operand_map(&tv, v, batch, heads, len_kv)) != PCD_OK) return rc;
+  const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
+  if (g_attn_variant == 1)
+    return launch_attn_tc<true>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
+  return launch_attn_tc<false>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
+}
+
+}  // namespace pcd

@@ -1,0 +1,297 @@
+// LayerNorm, timestep embedding, token assembly and output projection kernels.
+// All are HBM-bound row kernels: one warp per token row, 128-bit accesses.
+#include "common.cuh"
+
+namespace pcd {
+
+// ---------------------------------------------------------------------------
+// timestep embedding (reference models/util.py:72-89)
+// ---------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
+                                      int batch, int dim, float* __restrict__ out, int ld) {
+  int half = dim / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  int b = i / half, k = i % half;
+  float a = __fmul_rn(t[b], freqs[k]);
+  // accurate cosf/sinf (arguments reach ~1e3 rad; no fast-math here)
+  out[(size_t)b * ld + k] = cosf(a);
+  out[(size_t)b * ld + half + k] = sinf(a);
+  if ((dim & 1) && k == 0) out[(size_t)b * ld + dim - 1] = 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// Row LayerNorm in registers.  MAXV = ceil(dim/128) float4 per lane.
+// mean = sum/d; var = sum((x-mean)^2)/d (two-pass, like ATen); rstd = rsqrt(var+eps).
+// ---------------------------------------------------------------------------
+template <int MAXV>
+struct RowRegs {
+  float4 v[MAXV];
+};
+
+template <int MAXV>
+__device__ __forceinline__ void row_stats(const RowRegs<MAXV>& r, int dim, int lane, float& mean,
+                                          float& rstd, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = (i * 32 + lane) * 4;
+    if (c < dim) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+  }
+  mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      float a = r.v[i].x - mean, b = r.v[i].y - mean, cc = r.v[i].z - mean, d = r.v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
+}
+
+template <int MAXV, bool OUT_BF16>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        void* __restrict__ out, int ldo, int rows,
+                                                        int dim, float eps) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * ldx;
+  RowRegs<MAXV> r;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = (i * 32 + lane) * 4;
+    if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(xr + c);
+  }
+  float mean, rstd;
+  row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      float4 b = *reinterpret_cast<const float4*>(beta + c);
+      float4 y;
+      y.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+      if (OUT_BF16) {
+        uint2 p = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + (size_t)warp * ldo + c) = p;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)warp * ldo + c) = y;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// token assembly + ln_pre (reference models/transformer.py:205-220)
+// ---------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) embed_tokens_kernel(
+    const float* __restrict__ x, int x_seqs, int c_in, int n_points,
+    const float* __restrict__ w_in, const float* __restrict__ b_in,
+    const float* __restrict__ prefix, int n_prefix, const float* __restrict__ add_cond,
+    const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+    float* __restrict__ h, int seqs, int dim) {
+  int L = n_prefix + n_points;
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= (int64_t)seqs * L) return;
+  int s = (int)(row / L), l = (int)(row % L);
+  RowRegs<MAXV> r;
+  if (l < n_prefix) {
+    const float* p = prefix + ((size_t)s * n_prefix + l) * dim;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(p + c);
+    }
+  } else {
+    int n = l - n_prefix;
+    const float* xs = x + (size_t)(s % x_seqs) * c_in * n_points + n;
+    float xv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) xv[k] = (k < c_in) ? xs[(size_t)k * n_points] : 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if (c < dim) {
+        float acc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* w = w_in + (size_t)(c + j) * c_in;
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < c_in) a = fmaf(xv[k], w[k], a);
+          acc[j] = a + b_in[c + j];
+        }
+        if (add_cond != nullptr) {
+          float4 e = *reinterpret_cast<const float4*>(add_cond + (size_t)s * dim + c);
+          acc[0] += e.x; acc[1] += e.y; acc[2] += e.z; acc[3] += e.w;
+        }
+        r.v[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    }
+  }
+  float mean, rstd;
+  row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
+  float* hr = h + (size_t)row * dim;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      float4 g = *reinterpret_cast<const float4*>(ln_g + c);
+      float4 b = *reinterpret_cast<const float4*>(ln_b + c);
+      float4 y;
+      y.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+      *reinterpret_cast<float4*>(hr + c) = y;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// ln_post + slice + output_proj + permute (reference models/transformer.py:222-226)
+// One warp per point token; the c_out dot products are reduced with shuffles and
+// staged through shared memory so that the NCL store is coalesced along n.
+// ---------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) output_proj_kernel(
+    const float* __restrict__ h, int seqs, int n_prefix, int n_points, int dim,
+    const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+    const float* __restrict__ w_out, const float* __restrict__ b_out, int c_out,
+    float* __restrict__ out) {
+  // block = 8 warps = 8 consecutive point tokens of one sequence
+  __shared__ float stage[8][33];
+  int L = n_prefix + n_points;
+  int blocks_per_seq = (n_points + 7) / 8;
+  int s = blockIdx.x / blocks_per_seq;
+  int n0 = (blockIdx.x % blocks_per_seq) * 8;
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int n = n0 + w;
+  if (n < n_points) {
+    const float* hr = h + ((size_t)s * L + n_prefix + n) * dim;
+    RowRegs<MAXV> r;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(hr + c);
+    }
+    float mean, rstd;
+    row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if (c < dim) {
+        float4 g = *reinterpret_cast<const float4*>(ln_g + c);
+        float4 b = *reinterpret_cast<const float4*>(ln_b + c);
+        r.v[i].x = (r.v[i].x - mean) * rstd * g.x + b.x;
+        r.v[i].y = (r.v[i].y - mean) * rstd * g.y + b.y;
+        r.v[i].z = (r.v[i].z - mean) * rstd * g.z + b.z;
+        r.v[i].w = (r.v[i].w - mean) * rstd * g.w + b.w;
+      }
+    }
+    for (int o = 0; o < c_out; ++o) {
+      const float* wr = w_out + (size_t)o * dim;
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        int c = (i * 32 + lane) * 4;
+        if (c < dim) {
+          float4 ww = *reinterpret_cast<const float4*>(wr + c);
+          a = fmaf(r.v[i].x, ww.x, a);
+          a = fmaf(r.v[i].y, ww.y, a);
+          a = fmaf(r.v[i].z, ww.z, a);
+          a = fmaf(r.v[i].w, ww.w, a);
+        }
+      }
+      a = warp_sum(a);
+      if (lane == 0) stage[w][o] = a + b_out[o];
+    }
+  }
+  __syncthreads();
+  // coalesced-ish store: thread (o, j) writes out[s, o, n0 + j]
+  for (int idx = threadIdx.x; idx < c_out * 8; idx += blockDim.x) {
+    int o = idx / 8, j = idx % 8;
+    if (n0 + j < n_points) out[((size_t)s * c_out + o) * n_points + n0 + j] = stage[j][o];
+  }
+}
+
+}  // namespace pcd
+
+using namespace pcd;
+
+#define DISPATCH_MAXV(dim, ...)                              \
+  do {                                                       \
+    int nv__ = ((dim) + 127) / 128;                          \
+    if (nv__ <= 1) { constexpr int MAXV = 1; __VA_ARGS__; }  \
+    else if (nv__ <= 2) { constexpr int MAXV = 2; __VA_ARGS__; } \
+    else if (nv__ <= 4) { constexpr int MAXV = 4; __VA_ARGS__; } \
+    else if (nv__ <= 8) { constexpr int MAXV = 8; __VA_ARGS__; } \
+    else { constexpr int MAXV = 16; __VA_ARGS__; }           \
+  } while (0)
+
+extern "C" int pcd_timestep_embed(const float* t, const float* freqs, int batch, int dim,
+                                  float* out, int ld_out, void* stream) {
+  PCD_CHECK_ARG(batch > 0 && dim >= 2 && ld_out >= dim, "timestep_embed: bad shape");
+  int n = batch * (dim / 2);
+  timestep_embed_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(t, freqs, batch, dim, out, ld_out);
+  PCD_CHECK_LAUNCH("timestep_embed");
+  return PCD_OK;
+}
+
+extern "C" int pcd_layernorm(const float* x, int ldx, const float* gamma, const float* beta,
+                             void* out, int ld_out, int out_precision, int rows, int dim, float eps,
+                             void* stream) {
+  PCD_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 2048, "layernorm: dim must be a multiple of 4 and <= 2048 (got %d)", dim);
+  PCD_CHECK_ARG(ldx % 4 == 0 && ld_out % 4 == 0, "layernorm: leading dims must be multiples of 4");
+  dim3 grid(ceil_div(rows, 8)), block(256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_precision == PCD_BF16) {
+    DISPATCH_MAXV(dim, (layernorm_kernel<MAXV, true><<<grid, block, 0, st>>>(x, ldx, gamma, beta, out, ld_out, rows, dim, eps)));
+  } else {
+    DISPATCH_MAXV(dim, (layernorm_kernel<MAXV, false><<<grid, block, 0, st>>>(x, ldx, gamma, beta, out, ld_out, rows, dim, eps)));
+  }
+  PCD_CHECK_LAUNCH("layernorm");
+  return PCD_OK;
+}
+
+extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_points,
+                                const float* w_in, const float* b_in, const float* prefix,
+                                int n_prefix, const float* add_cond, const float* ln_g,
+                                const float* ln_b, float eps, float* h, int seqs, int dim,
+                                void* stream) {
+  PCD_CHECK_ARG(seqs > 0 && x_seqs > 0 && seqs % x_seqs == 0, "embed_tokens: seqs must be a multiple of x_seqs");
+  PCD_CHECK_ARG(c_in >= 1 && c_in <= 8, "embed_tokens: c_in must be in [1,8] (got %d)", c_in);
+  PCD_CHECK_ARG(dim % 4 == 0 && dim <= 2048, "embed_tokens: bad width %d", dim);
+  PCD_CHECK_ARG(n_prefix >= 0 && (n_prefix == 0 || prefix != nullptr), "embed_tokens: prefix missing");
+  int64_t rows = (int64_t)seqs * (n_prefix + n_points);
+  dim3 grid((unsigned)ceil_div64(rows, 8)), block(256);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_MAXV(dim, (embed_tokens_kernel<MAXV><<<grid, block, 0, st>>>(x, x_seqs, c_in, n_points, w_in, b_in, prefix, n_prefix, add_cond, ln_g, ln_b, eps, h, seqs, dim)));
+  PCD_CHECK_LAUNCH("embed_tokens");
+  return PCD_OK;
+}
+
+extern "C" int pcd_output_proj(const float* h, int seqs, int n_prefix, int n_points, int dim,
+                               const float* ln_g, const float* ln_b, float eps,
+                               const float* w_out, const float* b_out, int c_out, float* out,
+                               void* stream) {
+  PCD_CHECK_ARG(seqs > 0 && n_points > 0 && dim % 4 == 0 && dim <= 2048, "output_proj: bad shape");
+  PCD_CHECK_ARG(c_out >= 1 && c_out <= 32, "output_proj: c_out must be in [1,32] (got %d)", c_out);
+  dim3 grid(seqs * ceil_div(n_points, 8)), block(256);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_MAXV(dim, (output_proj_kernel<MAXV><<<grid, block, 0, st>>>(h, seqs, n_prefix, n_points, dim, ln_g, ln_b, eps, w_out, b_out, c_out, out)));
+  PCD_CHECK_LAUNCH("output_proj");
+  return PCD_OK;
+}

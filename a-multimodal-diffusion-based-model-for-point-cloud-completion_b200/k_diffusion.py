@@ -1,0 +1,294 @@
+"""Karras schedule + Heun solver driven by the fused CUDA sampler kernels.
+
+Drop-in for the reference's ``diffusion/k_diffusion.py`` entry points on the
+GaussianDiffusion + "heun" path (karras_sample_progressive :118-222, sample_heun
+:270-310, GaussianToKarrasDenoiser :79-108, guided_denoiser :182-207).
+
+Every per-step scalar is computed once on the host with the same fp32 / float64
+operations the reference performs per evaluation (including the scipy interp1d
+sigma->t lookup and its integer truncation), then passed by value to the kernels.
+That removes the reference's three host syncs per step and makes the whole loop
+CUDA-graph capturable.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, Iterator, List, Optional
+
+import numpy as np
+import torch as th
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream_ptr
+from .gaussian_diffusion import GaussianDiffusion
+from .ops import step_scalars
+
+
+def append_zero(x):
+    return th.cat([x, x.new_zeros([1])])
+
+
+def append_dims(x, target_dims):
+    dims_to_append = target_dims - x.ndim
+    if dims_to_append < 0:
+        raise ValueError(f"input has {x.ndim} dims but target_dims is {target_dims}, which is less")
+    return x[(...,) + (None,) * dims_to_append]
+
+
+def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
+    """Noise schedule of Karras et al. (2022); computed on the CPU like the reference
+    (k_diffusion.py:225-231) so the fp32 values are identical, then moved."""
+    ramp = th.linspace(0, 1, n)
+    min_inv_rho = sigma_min ** (1 / rho)
+    max_inv_rho = sigma_max ** (1 / rho)
+    sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    return append_zero(sigmas).to(device)
+
+
+class GaussianToKarrasDenoiser:
+    """sigma -> integer timestep lookup (reference k_diffusion.py:79-103)."""
+
+    def __init__(self, model, diffusion: GaussianDiffusion):
+        from scipy import interpolate
+
+        self.model = model
+        self.diffusion = diffusion
+        self.alpha_cumprod_to_t = interpolate.interp1d(diffusion.alphas_cumprod,
+                                                       np.arange(0, diffusion.num_timesteps))
+
+    def sigma_to_t(self, sigma):
+        alpha_cumprod = 1.0 / (sigma ** 2 + 1)
+        if alpha_cumprod > self.diffusion.alphas_cumprod[0]:
+            return 0
+        elif alpha_cumprod <= self.diffusion.alphas_cumprod[-1]:
+            return self.diffusion.num_timesteps - 1
+        else:
+            return float(self.alpha_cumprod_to_t(alpha_cumprod))
+
+    def sigma_to_int_t(self, sigma) -> int:
+        # th.tensor([...], dtype=th.long) truncates toward zero (k_diffusion.py:99-103)
+        return int(self.sigma_to_t(np.float32(sigma)))
+
+
+@dataclass
+class HeunEval:
+    sigma: float      # sigma of this denoiser evaluation (fp32 value)
+    t: int            # truncated integer timestep
+    c_in: float
+    coef_x: float
+    coef_eps: float
+
+
+@dataclass
+class HeunStep:
+    sigma: float          # sigma_i
+    sigma_hat: float      # sigma_i * (1 + gamma)
+    noise_scale: float    # sqrt(sigma_hat^2 - sigma_i^2), 0 when gamma == 0
+    dt: float             # sigma_{i+1} - sigma_hat
+    first: HeunEval
+    second: Optional[HeunEval]   # None on the last (Euler) step
+
+
+class HeunPlan:
+    """All host-side scalars of ``sample_heun`` for one stage."""
+
+    def __init__(self, diffusion: GaussianDiffusion, steps: int, sigma_min: float, sigma_max: float,
+                 rho: float = 7.0, s_churn: float = 0.0, s_tmin: float = 0.0,
+                 s_tmax: float = float("inf"), s_noise: float = 1.0):
+        if s_noise != 1.0:
+            raise NotImplementedError("s_noise != 1 (the reference never changes it)")
+        self.sigmas = get_sigmas_karras(steps, sigma_min, sigma_max, rho)  # CPU fp32 [steps+1]
+        self.sigma_max = sigma_max
+        wrap = GaussianToKarrasDenoiser(None, diffusion)
+        sig = self.sigmas
+        n = len(sig) - 1
+
+        def make_eval(s: th.Tensor) -> HeunEval:
+            t = wrap.sigma_to_int_t(s.numpy())
+            c_in = 1.0 / (s ** 2 + 1) ** 0.5
+            a = np.float32(diffusion.sqrt_recip_alphas_cumprod[t])
+            b = np.float32(diffusion.sqrt_recipm1_alphas_cumprod[t])
+            return HeunEval(float(s), t, float(c_in), float(a), float(b))
+
+        self.steps: List[HeunStep] = []
+        for i in range(n):
+            gamma = min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sig[i] <= s_tmax else 0.0
+            sigma_hat = sig[i] * (gamma + 1)
+            noise = float((sigma_hat ** 2 - sig[i] ** 2) ** 0.5) if gamma > 0 else 0.0
+            dt = sig[i + 1] - sigma_hat
+            second = None if sig[i + 1] == 0 else make_eval(sig[i + 1])
+            self.steps.append(HeunStep(float(sig[i]), float(sigma_hat), noise, float(dt),
+                                       make_eval(sigma_hat), second))
+
+    @property
+    def num_evals(self) -> int:
+        return sum(1 + (s.second is not None) for s in self.steps)
+
+    def eval_timesteps(self) -> List[int]:
+        out = []
+        for s in self.steps:
+            out.append(s.first.t)
+            if s.second is not None:
+                out.append(s.second.t)
+        return out
+
+
+class HeunState:
+    """Device buffers + kernel launches for one Heun trajectory (state fp32 [B, C, N])."""
+
+    def __init__(self, diffusion: GaussianDiffusion, plan: HeunPlan, shape, device, guidance_scale: float,
+                 clip_denoised: bool):
+        require_cuda()
+        self.lib = _lib.load()
+        self.plan = plan
+        self.B, self.Cc, self.N = shape
+        self.guided = guidance_scale != 0 and guidance_scale != 1
+        self.guidance = float(guidance_scale)
+        self.clip = 1.0 if clip_denoised else 0.0
+        self.x = th.empty(shape, device=device, dtype=th.float32)
+        self.d = th.empty(shape, device=device, dtype=th.float32)
+        self.model_in = th.empty(shape, device=device, dtype=th.float32)
+        f32 = dict(device=device, dtype=th.float32)
+        self.ch_scale = None if diffusion.channel_scales is None else th.tensor(diffusion.channel_scales, **f32)
+        self.ch_bias = None if diffusion.channel_biases is None else th.tensor(diffusion.channel_biases, **f32)
+
+    def _scal(self, ev: Optional[HeunEval], dt: float, nxt: Optional[HeunEval], next_noise: float):
+        return step_scalars(c_in=ev.c_in if ev else 0.0, coef_x=ev.coef_x if ev else 0.0,
+                            coef_eps=ev.coef_eps if ev else 0.0, sigma=ev.sigma if ev else 0.0, dt=dt,
+                            guidance=self.guidance, clip=self.clip,
+                            next_c_in=nxt.c_in if nxt else 0.0, next_noise=next_noise)
+
+    def begin(self, noise0: th.Tensor):
+        """x <- x_T (+ churn of step 0); model_in <- x * c_in(sigma_hat_0)."""
+        st = self.plan.steps[0]
+        s = self._scal(None, 0.0, st.first, st.noise_scale)
+        check(self.lib.pcd_sampler_begin(ptr(self.x), ptr(noise0), ptr(self.model_in), C.byref(s),
+                                         self.x.numel(), stream_ptr()), "sampler_begin")
+
+    def predictor(self, i: int, model_out: th.Tensor, pred_out: th.Tensor):
+        st = self.plan.steps[i]
+        last = st.second is None
+        s = self._scal(st.first, st.dt, st.second, 0.0)
+        assert model_out.shape[0] == self.B * (2 if self.guided else 1) and model_out.is_contiguous()
+        check(self.lib.pcd_sampler_predictor(ptr(self.x), ptr(model_out), model_out.shape[1], int(self.guided),
+                                             ptr(self.d), ptr(self.model_in), ptr(pred_out), ptr(self.ch_scale),
+                                             ptr(self.ch_bias), C.byref(s), self.B, self.Cc, self.N, int(last),
+                                             stream_ptr()), "sampler_predictor")
+
+    def corrector(self, i: int, model_out: th.Tensor, next_noise: Optional[th.Tensor]):
+        st = self.plan.steps[i]
+        nxt = self.plan.steps[i + 1]
+        s = self._scal(st.second, st.dt, nxt.first, nxt.noise_scale)
+        assert model_out.is_contiguous()
+        check(self.lib.pcd_sampler_corrector(ptr(self.x), ptr(model_out), model_out.shape[1], int(self.guided),
+                                             ptr(self.d), ptr(next_noise), ptr(self.model_in), C.byref(s),
+                                             self.B, self.Cc, self.N, stream_ptr()), "sampler_corrector")
+
+
+def _native(model) -> bool:
+    return bool(getattr(model, "pcd_native", False))
+
+
+def make_denoiser_eval(model, model_kwargs: Dict[str, Any], B: int, guided: bool, device,
+                       eps_channels: Optional[int] = None) -> Callable:
+    """Returns eval(model_in [B,C,N], t:int) -> model output [B or 2B, C_out, N] (contiguous fp32).
+
+    Native modules evaluate the conditional and unconditional halves as ONE 2B-sequence
+    forward sharing x (per-sample arithmetic is independent, SURVEY.md 7.2 "CFG");
+    arbitrary callables get the reference's two B-sized calls (k_diffusion.py:182-207),
+    with ``prev_latent`` threaded per branch when the model returns a tuple."""
+    model_kwargs = model_kwargs or {}
+    if _native(model):
+        def eval_native(model_in, t):
+            return model.forward_cfg(model_in, t, model_kwargs, doubled=guided, out_channels=eps_channels)
+        return eval_native
+
+    latents = {"cond": None, "uncond": None}
+
+    def call(model_in, tt, kwargs, key):
+        kw = dict(kwargs)
+        if latents[key] is not None:
+            kw["prev_latent"] = latents[key]
+        out = model(model_in, tt, **kw)
+        if isinstance(out, tuple):
+            out, latents[key] = out
+        return out.float()
+
+    def eval_generic(model_in, t):
+        tt = th.full((B,), int(t), dtype=th.long, device=device)
+        if not guided:
+            kw = {k: v for k, v in model_kwargs.items() if k != "prev_latent"}
+            return call(model_in, tt, kw, "cond").contiguous()
+        cond = {k: v[:B] for k, v in model_kwargs.items() if k != "prev_latent"}
+        uncond = {k: v[B:] for k, v in model_kwargs.items() if k != "prev_latent"}
+        return th.cat([call(model_in, tt, cond, "cond"), call(model_in, tt, uncond, "uncond")], dim=0).contiguous()
+
+    return eval_generic
+
+
+def karras_sample_progressive(
+    diffusion,
+    model,
+    shape,
+    steps,
+    clip_denoised=True,
+    progress=False,
+    model_kwargs=None,
+    device=None,
+    sigma_min=0.002,
+    sigma_max=80,
+    rho=7.0,
+    sampler="heun",
+    s_churn=0.0,
+    s_tmin=0.0,
+    s_tmax=float("inf"),
+    s_noise=1.0,
+    guidance_scale=0.0,
+    x_target=None,
+    noise_fn: Optional[Callable] = None,
+) -> Iterator[Dict[str, Any]]:
+    """Same signature and yields as the reference (k_diffusion.py:118-222).  ``noise_fn(shape)``
+    optionally replaces the torch RNG draws (draw #0 for x_T, then one per step, in the
+    reference's order, k_diffusion.py:139,292)."""
+    if sampler != "heun":
+        raise NotImplementedError(f"sampler={sampler!r}: only the Heun solver is fused so far")
+    if not isinstance(diffusion, GaussianDiffusion):
+        raise NotImplementedError("only GaussianDiffusion-wrapped models are supported")
+    device = th.device(device if device is not None else "cuda")
+    require_cuda()
+    if noise_fn is None:
+        noise_fn = lambda shp: th.randn(*shp, device=device)
+    plan = HeunPlan(diffusion, steps, sigma_min, sigma_max, rho, s_churn, s_tmin, s_tmax, s_noise)
+    B = shape[0]
+    state = HeunState(diffusion, plan, tuple(shape), device, guidance_scale, clip_denoised)
+    evaluate = make_denoiser_eval(model, model_kwargs, B, state.guided, device,
+                                  shape[1] if diffusion.eps_channels_doubled else None)
+
+    with th.no_grad():
+        state.x.copy_(noise_fn(tuple(shape)).to(device) * sigma_max)
+        eps = noise_fn(tuple(shape)).to(device)  # always drawn, even when gamma == 0
+        state.begin(eps)
+        indices = range(len(plan.steps))
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        pred = None
+        for i in indices:
+            st = plan.steps[i]
+            out = evaluate(state.model_in, st.first.t)
+            x_hat = state.x.clone()  # the reference yields x after churn, before the update
+            pred = th.empty_like(state.x)
+            state.predictor(i, out, pred)
+            yield {"x": diffusion.unscale_channels(x_hat), "i": i, "sigma": th.tensor(st.sigma),
+                   "sigma_hat": th.tensor(st.sigma_hat), "pred_xstart": pred}
+            if st.second is not None:
+                out2 = evaluate(state.model_in, st.second.t)
+                nxt = noise_fn(tuple(shape)).to(device)
+                state.corrector(i, out2, nxt)
+        yield {"x": diffusion.unscale_channels(state.x.clone()), "pred_xstart": pred}
+
+
+def karras_sample(*args, **kwargs):
+    last = None
+    for x in karras_sample_progressive(*args, **kwargs):
+        last = x["x"]
+    return last

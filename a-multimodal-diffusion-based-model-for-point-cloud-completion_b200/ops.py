@@ -1,0 +1,172 @@
+"""Tensor-level wrappers over the C ABI (one ctypes call per op, current CUDA stream).
+
+PyTorch is used here for device memory and streams only; all arithmetic happens
+in libpcd_b200.so.  Every function raises ``PcdError`` instead of falling back.
+"""
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (AttnOperand, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL, PCD_BF16, PCD_F32,
+                   StepScalars, check, ptr, require_cuda, stream_ptr)
+
+_PREC = {torch.float32: PCD_F32, torch.bfloat16: PCD_BF16}
+
+
+def _rowmajor2d(t: torch.Tensor):
+    assert t.dim() == 2 and t.stride(1) == 1, "expected a row-major 2-D tensor"
+    return t.stride(0)
+
+
+def timestep_freqs(dim: int, max_period: float = 10000.0, device=None) -> torch.Tensor:
+    """Frequency table of ``timestep_embedding`` computed on the CPU exactly like the
+    reference does (models/util.py:81-83) and moved to the device."""
+    half = dim // 2
+    f = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+    return f.to(device) if device is not None else f
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, freqs: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """reference models/util.py:72-89."""
+    require_cuda(t)
+    tf = t.to(torch.float32).contiguous()
+    if freqs is None:
+        freqs = timestep_freqs(dim, device=t.device)
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
+    check(_lib.load().pcd_timestep_embed(ptr(tf), ptr(freqs), t.shape[0], dim, ptr(out), dim, stream_ptr()),
+          "timestep_embed")
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+              out_dtype=torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nn.LayerNorm over the last dim of an fp32 tensor -> fp32 or bf16."""
+    require_cuda(x, weight, bias)
+    assert x.dtype == torch.float32
+    dim = x.shape[-1]
+    x2 = x.reshape(-1, dim)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    if out is None:
+        out = torch.empty(x2.shape, device=x.device, dtype=out_dtype)
+    o2 = out.reshape(-1, dim)
+    check(_lib.load().pcd_layernorm(ptr(x2), x2.stride(0), ptr(weight), ptr(bias), ptr(o2), o2.stride(0),
+                                    _PREC[out.dtype], x2.shape[0], dim, float(eps), stream_ptr()), "layernorm")
+    return out.reshape(*x.shape[:-1], dim)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+           epilogue: int = EPI_BIAS, residual: Optional[torch.Tensor] = None,
+           out_dtype=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = epi(x W^T + b).  fp32 operands -> CUDA-core GEMM; bf16 operands -> tcgen05 GEMM
+    (bias / residual stay fp32, output bf16 or fp32)."""
+    require_cuda(x, weight)
+    assert x.dtype == weight.dtype and x.dtype in _PREC
+    K = x.shape[-1]
+    N = weight.shape[0]
+    assert weight.shape[1] == K
+    x2 = x.reshape(-1, K)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if out_dtype is None:
+        out_dtype = x.dtype
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=out_dtype)
+    o2 = out.reshape(-1, N) if out.dim() != 2 else out
+    r2 = None
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == torch.float32
+        r2 = residual.reshape(-1, N) if residual.dim() != 2 else residual
+        ldr = _rowmajor2d(r2)
+        epilogue = EPI_BIAS_RESIDUAL
+    lib = _lib.load()
+    if x.dtype == torch.float32:
+        assert o2.dtype == torch.float32
+        check(lib.pcd_gemm_f32(ptr(x2), x2.stride(0), ptr(weight), _rowmajor2d(weight), ptr(bias), ptr(r2), ldr,
+                               ptr(o2), _rowmajor2d(o2), M, N, K, epilogue, stream_ptr()), "gemm_f32")
+    else:
+        check(lib.pcd_gemm_bf16(ptr(x2), x2.stride(0), ptr(weight), _rowmajor2d(weight), ptr(bias), ptr(r2), ldr,
+                                ptr(o2), _rowmajor2d(o2), _PREC[o2.dtype], M, N, K, epilogue, stream_ptr()),
+              "gemm_bf16")
+    return out.reshape(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
+
+
+def _operand(t: torch.Tensor, offset: int, batch_stride: int, row_stride: int, head_stride: int):
+    return AttnOperand(C.c_void_p(t.data_ptr() + offset * t.element_size()), batch_stride, row_stride, head_stride)
+
+
+def attention_packed(q_op, k_op, v_op, out: torch.Tensor, batch: int, heads: int, len_q: int, len_kv: int,
+                     q_scale: float, k_scale: float, rope_coords: Optional[torch.Tensor] = None):
+    """Low-level call: operands are ``AttnOperand`` views; ``out`` is [batch, len_q, heads*64]."""
+    require_cuda(out)
+    check(_lib.load().pcd_attention(C.byref(q_op), C.byref(k_op), C.byref(v_op), ptr(out), out.stride(0),
+                                    out.stride(1), batch, heads, len_q, len_kv, float(q_scale), float(k_scale),
+                                    ptr(rope_coords), _PREC[out.dtype], stream_ptr()), "attention")
+    return out
+
+
+def self_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """QKVMultiheadAttention (reference models/transformer.py:65-84): qkv [B, L, H*3*64]
+    laid out [H][q|k|v][64]; q and k each scaled by 64**-0.25."""
+    B, L, W3 = qkv.shape
+    hd = W3 // heads // 3
+    assert hd == 64, "this build supports head dim 64 (all registered configs)"
+    qkv = qkv.contiguous()
+    out = torch.empty(B, L, heads * hd, device=qkv.device, dtype=qkv.dtype)
+    s = 1.0 / math.sqrt(math.sqrt(hd))
+    ops = [_operand(qkv, i * hd, L * W3, W3, 3 * hd) for i in range(3)]
+    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, L, L, s, s)
+
+
+def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int) -> torch.Tensor:
+    """QKVMultiheadCrossAttention (reference models/perceiver.py:46-67): q [B, Lq, H*64],
+    kv [B, Lkv, H*2*64] laid out [H][k|v][64]."""
+    B, Lq, W = q.shape
+    _, Lkv, W2 = kv.shape
+    hd = W2 // heads // 2
+    assert hd == 64 and W == heads * hd
+    q, kv = q.contiguous(), kv.contiguous()
+    out = torch.empty(B, Lq, W, device=q.device, dtype=q.dtype)
+    s = 1.0 / math.sqrt(math.sqrt(hd))
+    qo = _operand(q, 0, Lq * W, W, hd)
+    ko = _operand(kv, 0, Lkv * W2, W2, 2 * hd)
+    vo = _operand(kv, hd, Lkv * W2, W2, 2 * hd)
+    return attention_packed(qo, ko, vo, out, B, heads, Lq, Lkv, s, s)
+
+
+def rotary_attention(qkv: torch.Tensor, coords: torch.Tensor, heads: int) -> torch.Tensor:
+    """RotarySelfAttention core (reference models/rotaryencoderpcd.py:68-84): qkv [B, N, 3*D]
+    laid out [3][H][64]; 3-axis RoPE on head dims 0..5 of q and k; logits * D**-0.5."""
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    assert D // heads == 64
+    assert qkv.dtype == torch.float32, "rotary attention runs in the fp32 kernel (RoPE applied on load)"
+    qkv = qkv.contiguous()
+    coords = coords.to(torch.float32).contiguous()
+    out = torch.empty(B, N, D, device=qkv.device, dtype=qkv.dtype)
+    ops = [_operand(qkv, i * D, N * D3, D3, 64) for i in range(3)]
+    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, N, N, D ** -0.5, 1.0, coords)
+
+
+def chamfer_distance_xyz(p1: torch.Tensor, p2: torch.Tensor) -> torch.Tensor:
+    """reference models/util.py:265-295: squared-L2 Chamfer on channels 0:3 -> [B]."""
+    require_cuda(p1, p2)
+    p1, p2 = p1.float().contiguous(), p2.float().contiguous()
+    B, c1, n1 = p1.shape
+    _, c2, n2 = p2.shape
+    out = torch.empty(B, device=p1.device, dtype=torch.float32)
+    ws = torch.empty(B * (n1 + n2), device=p1.device, dtype=torch.float32)
+    check(_lib.load().pcd_chamfer(ptr(p1), c1, n1, ptr(p2), c2, n2, B, ptr(out), ptr(ws), stream_ptr()), "chamfer")
+    return out
+
+
+def step_scalars(**kw) -> StepScalars:
+    s = StepScalars()
+    for k, v in kw.items():
+        setattr(s, k, float(v))
+    return s

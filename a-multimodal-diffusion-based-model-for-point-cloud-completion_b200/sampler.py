@@ -1,0 +1,326 @@
+"""Multi-stage point-cloud sampler on the fused Heun kernels.
+
+Same constructor, attributes and methods as the reference's
+``diffusion/sampler.py`` ``PointCloudSampler`` (:16-291).  Two execution modes:
+
+* eager (default): ``sample_batch_progressive`` yields after every Heun step, like
+  the reference;
+* ``use_cuda_graph=True``: every stage's 64-step loop (all denoiser evaluations and
+  sampler updates, ~10^4 kernel launches) is captured once per (stage, batch) into a
+  CUDA graph and replayed; the 65 yields of a stage become available when the replay
+  finishes.  Noise is drawn by torch in the reference's order before the replay, so a
+  fixed seed gives the same trajectory as the eager mode.
+"""
+from typing import Any, Callable, Dict, Iterator, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .gaussian_diffusion import GaussianDiffusion
+from .k_diffusion import HeunPlan, HeunState, karras_sample_progressive, make_denoiser_eval
+from ._lib import require_cuda
+
+
+class _GraphedStage:
+    """One stage's whole Heun loop as a CUDA graph over persistent buffers."""
+
+    def __init__(self, model, diffusion: GaussianDiffusion, plan: HeunPlan, shape, device, guidance: float,
+                 clip_denoised: bool):
+        self.model, self.diffusion, self.plan = model, diffusion, plan
+        self.shape, self.device = tuple(shape), device
+        self.state = HeunState(diffusion, plan, self.shape, device, guidance, clip_denoised)
+        n = len(plan.steps)
+        self.noise = torch.empty((n + 1,) + self.shape, device=device, dtype=torch.float32)
+        self.preds = torch.empty((n,) + self.shape, device=device, dtype=torch.float32)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.kwargs: Dict[str, Any] = {}
+        self.eps_channels = self.shape[1] if diffusion.eps_channels_doubled else None
+        self.launches_per_replay = 0
+
+    def _enqueue(self):
+        st, plan = self.state, self.plan
+        B = self.shape[0]
+        torch.mul(self.noise[0], plan.sigma_max, out=st.x)
+        st.begin(self.noise[1])
+        for i, step in enumerate(plan.steps):
+            out = self.model.forward_cfg(st.model_in, step.first.t, self.kwargs, st.guided, self.eps_channels)
+            st.predictor(i, out, self.preds[i])
+            if step.second is not None:
+                out2 = self.model.forward_cfg(st.model_in, step.second.t, self.kwargs, st.guided,
+                                              self.eps_channels)
+                st.corrector(i, out2, self.noise[i + 2])
+
+    def run(self, kwargs: Dict[str, Any], noise_fn: Optional[Callable]) -> torch.Tensor:
+        """Returns preds [steps, B, C, N] (unscaled pred_xstart of every step)."""
+        seqs = self.shape[0] * (2 if self.state.guided else 1)
+        # noise in the reference's draw order: x_T, then one eps per step (k_diffusion.py:139,292)
+        for k in range(self.noise.shape[0]):
+            if noise_fn is None:
+                self.noise[k].normal_()
+            else:
+                self.noise[k].copy_(noise_fn(self.shape))
+        self.kwargs = {k: v for k, v in kwargs.items() if k != "prev_latent"}
+        self.model.prepare_cond(seqs, self.kwargs)
+        if self.graph is None:
+            # warm-up on a side stream (populates every cache), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._enqueue()
+        self.graph.replay()
+        return self.preds
+
+
+class PointCloudSampler:
+    """
+    A wrapper around a model or stack of models that produces conditional or
+    unconditional sample tensors (reference diffusion/sampler.py:16-41).
+    """
+
+    def __init__(
+        self,
+        device: torch.device,
+        models: Sequence[nn.Module],
+        diffusions: Sequence[GaussianDiffusion],
+        num_points: Sequence[int],
+        aux_channels: Sequence[str],
+        model_kwargs_key_filter: Sequence[str] = ("*",),
+        guidance_scale: Sequence[float] = (3.0, 3.0),
+        clip_denoised: bool = True,
+        use_karras: Sequence[bool] = (True, True),
+        karras_steps: Sequence[int] = (64, 64),
+        sigma_min: Sequence[float] = (1e-3, 1e-3),
+        sigma_max: Sequence[float] = (120, 160),
+        s_churn: Sequence[float] = (3, 0),
+        use_cuda_graph: bool = False,
+        noise_fn: Optional[Callable] = None,
+    ):
+        n = len(models)
+        assert n > 0
+
+        if n > 1:
+            if len(guidance_scale) == 1:
+                # Don't guide the upsamplers by default.
+                guidance_scale = list(guidance_scale) + [1.0] * (n - 1)
+            if len(use_karras) == 1:
+                use_karras = use_karras * n
+            if len(karras_steps) == 1:
+                karras_steps = karras_steps * n
+            if len(sigma_min) == 1:
+                sigma_min = sigma_min * n
+            if len(sigma_max) == 1:
+                sigma_max = sigma_max * n
+            if len(s_churn) == 1:
+                s_churn = s_churn * n
+            if len(model_kwargs_key_filter) == 1:
+                model_kwargs_key_filter = model_kwargs_key_filter * n
+        if len(model_kwargs_key_filter) == 0:
+            model_kwargs_key_filter = ["*"] * n
+        assert len(guidance_scale) == n
+        assert len(use_karras) == n
+        assert len(karras_steps) == n
+        assert len(sigma_min) == n
+        assert len(sigma_max) == n
+        assert len(s_churn) == n
+        assert len(model_kwargs_key_filter) == n
+
+        self.device = device
+        self.num_points = num_points
+        self.aux_channels = aux_channels
+        self.model_kwargs_key_filter = model_kwargs_key_filter
+        self.guidance_scale = guidance_scale
+        self.clip_denoised = clip_denoised
+        self.use_karras = use_karras
+        self.karras_steps = karras_steps
+        self.sigma_min = sigma_min
+        self.sigma_max = sigma_max
+        self.s_churn = s_churn
+
+        self.models = models
+        self.diffusions = diffusions
+        self.use_cuda_graph = use_cuda_graph
+        self.noise_fn = noise_fn
+        self._graphs: Dict[Tuple, _GraphedStage] = {}
+
+    @property
+    def num_stages(self) -> int:
+        return len(self.models)
+
+    def sample_batch(self, batch_size: int, model_kwargs: Dict[str, Any]) -> torch.Tensor:
+        samples = None
+        for x in self.sample_batch_progressive(batch_size, model_kwargs):
+            samples = x
+        return samples
+
+    def _graphed_stage(self, idx, model, diffusion, shape, steps, smin, smax, churn, guidance) -> _GraphedStage:
+        key = (idx, tuple(shape), steps, smin, smax, churn, guidance, self.clip_denoised)
+        if key not in self._graphs:
+            plan = HeunPlan(diffusion, steps, smin, smax, 7.0, churn)
+            self._graphs[key] = _GraphedStage(model, diffusion, plan, shape, self.device, guidance,
+                                              self.clip_denoised)
+        return self._graphs[key]
+
+    def sample_batch_progressive(
+        self, batch_size: int, model_kwargs: Dict[str, Any], x_target: torch.Tensor = None,
+    ) -> Iterator[torch.Tensor]:
+        require_cuda()
+        samples = None
+        for idx, (
+            model,
+            diffusion,
+            stage_num_points,
+            stage_guidance_scale,
+            stage_use_karras,
+            stage_karras_steps,
+            stage_sigma_min,
+            stage_sigma_max,
+            stage_s_churn,
+            stage_key_filter,
+        ) in enumerate(zip(
+            self.models,
+            self.diffusions,
+            self.num_points,
+            self.guidance_scale,
+            self.use_karras,
+            self.karras_steps,
+            self.sigma_min,
+            self.sigma_max,
+            self.s_churn,
+            self.model_kwargs_key_filter,
+        )):
+            stage_model_kwargs = model_kwargs.copy()
+            if stage_key_filter != "*":
+                use_keys = set(stage_key_filter.split(","))
+                stage_model_kwargs = {k: v for k, v in stage_model_kwargs.items() if k in use_keys}
+            if samples is not None:
+                stage_model_kwargs["low_res"] = samples
+            if hasattr(model, "cached_model_kwargs"):
+                stage_model_kwargs = model.cached_model_kwargs(batch_size, stage_model_kwargs)
+            sample_shape = (batch_size, 3 + len(self.aux_channels), stage_num_points)
+
+            if stage_guidance_scale != 1 and stage_guidance_scale != 0:
+                for k, v in stage_model_kwargs.copy().items():
+                    if k not in ["prev_latent"]:
+                        stage_model_kwargs[k] = torch.cat([v, torch.zeros_like(v)], dim=0)
+
+            if not stage_use_karras:
+                raise NotImplementedError(
+                    "use_karras=False (ancestral DDPM loop) is outside the accelerated path; the "
+                    "reference's own branch for it is dead code (SURVEY.md appendix B)")
+
+            low_res = stage_model_kwargs.get("low_res")
+            if self.use_cuda_graph and getattr(model, "pcd_native", False):
+                stage = self._graphed_stage(idx, model, diffusion, sample_shape, stage_karras_steps,
+                                            stage_sigma_min, stage_sigma_max, stage_s_churn,
+                                            stage_guidance_scale)
+                preds = stage.run(stage_model_kwargs, self.noise_fn)
+                outs = [preds[i] for i in range(preds.shape[0])] + [preds[-1]]
+            else:
+                outs = (o["pred_xstart"] for o in karras_sample_progressive(
+                    diffusion=diffusion,
+                    model=model,
+                    shape=sample_shape,
+                    steps=stage_karras_steps,
+                    clip_denoised=self.clip_denoised,
+                    model_kwargs=stage_model_kwargs,
+                    device=self.device,
+                    sigma_min=stage_sigma_min,
+                    sigma_max=stage_sigma_max,
+                    s_churn=stage_s_churn,
+                    guidance_scale=stage_guidance_scale,
+                    x_target=x_target,
+                    noise_fn=self.noise_fn,
+                ))
+            for x in outs:
+                samples = x[:batch_size]
+                if low_res is not None:
+                    samples = torch.cat([low_res[: len(samples)], samples], dim=-1)
+                yield samples
+
+    @classmethod
+    def combine(cls, *samplers: "PointCloudSampler") -> "PointCloudSampler":
+        assert all(x.device == samplers[0].device for x in samplers[1:])
+        assert all(x.aux_channels == samplers[0].aux_channels for x in samplers[1:])
+        assert all(x.clip_denoised == samplers[0].clip_denoised for x in samplers[1:])
+        return cls(
+            device=samplers[0].device,
+            models=[x for y in samplers for x in y.models],
+            diffusions=[x for y in samplers for x in y.diffusions],
+            num_points=[x for y in samplers for x in y.num_points],
+            aux_channels=samplers[0].aux_channels,
+            model_kwargs_key_filter=[x for y in samplers for x in y.model_kwargs_key_filter],
+            guidance_scale=[x for y in samplers for x in y.guidance_scale],
+            clip_denoised=samplers[0].clip_denoised,
+            use_karras=[x for y in samplers for x in y.use_karras],
+            karras_steps=[x for y in samplers for x in y.karras_steps],
+            sigma_min=[x for y in samplers for x in y.sigma_min],
+            sigma_max=[x for y in samplers for x in y.sigma_max],
+            s_churn=[x for y in samplers for x in y.s_churn],
+            use_cuda_graph=samplers[0].use_cuda_graph,
+            noise_fn=samplers[0].noise_fn,
+        )
+
+    def split_model_output(
+        self,
+        output: torch.Tensor,
+        rescale_colors: bool = False,
+    ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        assert (
+            len(self.aux_channels) + 3 == output.shape[1]
+        ), "there must be three spatial channels before aux"
+        pos, joined_aux = output[:, :3], output[:, 3:]
+
+        aux = {}
+        for i, name in enumerate(self.aux_channels):
+            v = joined_aux[:, i]
+            if name in {"R", "G", "B", "A"}:
+                v = v.clamp(0, 255).round()
+                if rescale_colors:
+                    v = v / 255.0
+            aux[name] = v
+        return pos, aux
+
+    def output_to_point_clouds(self, output: torch.Tensor) -> List[Dict[str, Any]]:
+        """The reference returns ``point_e.util.point_cloud.PointCloud`` dataclasses
+        (sampler.py:255-265); the IO/visualisation layer is out of scope here, so each
+        cloud is returned as ``dict(coords=[N,3] ndarray, channels={name: [N] ndarray})``
+        with the same field names and values."""
+        res = []
+        for sample in output:
+            xyz, aux = self.split_model_output(sample[None], rescale_colors=True)
+            res.append(dict(coords=xyz[0].t().cpu().numpy(),
+                            channels={k: v[0].cpu().numpy() for k, v in aux.items()}))
+        return res
+
+    def with_options(
+        self,
+        guidance_scale: float,
+        clip_denoised: bool,
+        use_karras: Sequence[bool] = (True, True),
+        karras_steps: Sequence[int] = (64, 64),
+        sigma_min: Sequence[float] = (1e-3, 1e-3),
+        sigma_max: Sequence[float] = (120, 160),
+        s_churn: Sequence[float] = (3, 0),
+    ) -> "PointCloudSampler":
+        return PointCloudSampler(
+            device=self.device,
+            models=self.models,
+            diffusions=self.diffusions,
+            num_points=self.num_points,
+            aux_channels=self.aux_channels,
+            model_kwargs_key_filter=self.model_kwargs_key_filter,
+            guidance_scale=guidance_scale,
+            clip_denoised=clip_denoised,
+            use_karras=use_karras,
+            karras_steps=karras_steps,
+            sigma_min=sigma_min,
+            sigma_max=sigma_max,
+            s_churn=s_churn,
+            use_cuda_graph=self.use_cuda_graph,
+            noise_fn=self.noise_fn,
+        )

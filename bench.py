@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Headline benchmark: completed clouds/s of the full 64-step Karras/Heun sampler.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one complete sampling pass over one batch: 64 Heun steps = 127 denoiser
+evaluations (each a 2B-sequence classifier-free-guidance forward) + the fused sampler
+updates, replayed from one CUDA graph.  Workload at N=1 is BASELINE.json configs[1]:
+base40M-imagevec (width 512, 12 layers, L = 1026), 1024 points, batch 64 per GPU, bf16,
+guidance 3, s_churn 3, synthetic unit-norm CLIP embeddings, reference-init weights.
+Multi-GPU (torchrun): one rank per GPU, batch sharded (weak scaling), no per-step
+collective, one NCCL all-gather of the finished clouds per step.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "completed clouds/sec (64-step Heun, 1024 pts)"
+UNIT = "clouds/s"
+WORKLOADS = {
+    # name: (model config, diffusion config, per-GPU batch, sigma_max, s_churn, guidance)
+    "base40M-imagevec-1024pt-b64": ("base40M-imagevec", "base40M-imagevec", 64, 120.0, 3.0, 3.0),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's path on the host cores
+# ---------------------------------------------------------------------------
+def cpu_sample(workload, heun_steps=4, threads=None):
+    """Time `heun_steps` Heun steps of the ORACLE sampler (reference algorithm, fp32 torch
+    CPU) for ONE cloud of the workload and scale to clouds/s for the 64-step sampler."""
+    import torch
+
+    from oracle import cases, det
+    from oracle import denoiser as D
+    from oracle import sampler as S
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_golden import shapes_of
+
+    mcfg, dcfg, _, smax, churn, guidance = WORKLOADS[workload]
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = dict(cases.MODEL_CONFIGS[mcfg])
+    sd = det.fill_state_dict(shapes_of(cfg), 201, mode="reference", width=cfg["width"])
+    tab = S.Tables(**cases.DIFFUSION_CONFIGS["base"])
+    e = det.normal((1, 768), 77)
+    kw = dict(embeddings=torch.cat([e / e.norm(dim=1, keepdim=True), torch.zeros(1, 768)], 0))
+    gen = S.heun_progressive(S.make_model_fn(sd, cfg), tab, (1, 6, cfg["n_ctx"]), steps=64, sigma_min=1e-3,
+                             sigma_max=smax, s_churn=churn, guidance_scale=guidance, model_kwargs=kw,
+                             noise_fn=cases.DetNoise(5))
+    with torch.no_grad():
+        next(gen)  # first yield comes after the first (cond+uncond) evaluation: start the clock there
+        t0 = time.perf_counter()
+        for _ in range(heun_steps):
+            next(gen)
+        dt = time.perf_counter() - t0
+    per_cloud = dt / heun_steps * 64.0
+    return dict(value=1.0 / per_cloud, unit=UNIT, cores=threads, kind="port",
+                sample=f"oracle (reference algorithm, fp32 torch-CPU) on 1 cloud of {workload}: {heun_steps} of 64 "
+                       f"Heun steps ({4 * heun_steps} B=1 denoiser forwards) in {dt:.1f}s, scaled x{64 // heun_steps}"), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, dt = cpu_sample(args.workload, heun_steps=2)
+        if i >= args.warmup:
+            times.append(dt)
+    per_cloud = (sum(times) / len(times)) / 2 * 64.0
+    v = 1.0 / per_cloud
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "each step = bounded CPU sample (2 of 64 Heun steps, 1 cloud)"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+def time_kernel(fn, iters=10, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3  # seconds per launch
+
+
+def kernel_breakdown(P, model, B2, L, width, heads, layers, Bc, C, N, pk):
+    """Live CUDA-event timing of each hot kernel at the workload's shapes (operands larger
+    than L2: the activation matrices are 134-538 MB) -> roofline fractions."""
+    import torch
+    dev = torch.device("cuda")
+    M = B2 * L
+    bf = torch.bfloat16
+    g = torch.Generator(device=dev).manual_seed(1)
+    a_d = torch.randn(M, width, device=dev, generator=g).to(bf)
+    a_4d = torch.randn(M, 4 * width, device=dev, generator=g).to(bf)
+    h = torch.randn(M, width, device=dev, generator=g)
+    mk = lambda n, k: (torch.randn(n, k, device=dev, generator=g) / math.sqrt(k)).to(bf)
+    w_qkv, w_proj, w_fc, w_fc2 = mk(3 * width, width), mk(width, width), mk(4 * width, width), mk(width, 4 * width)
+    bias = lambda n: torch.zeros(n, device=dev)
+    qkv = torch.empty(M, 3 * width, device=dev, dtype=bf)
+    hid = torch.empty(M, 4 * width, device=dev, dtype=bf)
+    out_h = torch.empty(M, width, device=dev)
+    ops = P.ops
+    res = {}
+
+    def add(name, fn, launches, flops=None, bytes_=None):
+        t = time_kernel(fn)
+        r = {"ms": t * 1e3, "launches_per_step": launches, "ms_per_step": t * 1e3 * launches}
+        if flops is not None:
+            r.update(bound="tensor", achieved=flops / t / 1e12, peak=pk["tf_burst"], unit="TFLOP/s")
+        else:
+            r.update(bound="hbm", achieved=bytes_ / t / 1e9, peak=pk["hbm"], unit="GB/s")
+        r["frac"] = r["achieved"] / r["peak"]
+        res[name] = r
+
+    evals = 127
+    per = evals * layers
+    add("gemm_qkv", lambda: ops.linear(a_d, w_qkv, bias(3 * width), out=qkv), per, flops=2.0 * M * 3 * width * width)
+    add("gemm_attn_proj", lambda: ops.linear(a_d, w_proj, bias(width), residual=h, out_dtype=torch.float32, out=out_h),
+        per, flops=2.0 * M * width * width)
+    add("gemm_fc1_gelu", lambda: ops.linear(a_d, w_fc, bias(4 * width), epilogue=1, out=hid), per,
+        flops=2.0 * M * 4 * width * width)
+    add("gemm_fc2_residual", lambda: ops.linear(a_4d, w_fc2, bias(width), residual=h, out_dtype=torch.float32, out=out_h),
+        per, flops=2.0 * M * 4 * width * width)
+    qkv3 = qkv.view(B2, L, 3 * width)
+    qkv3.normal_()
+    add("flash_attention", lambda: ops.self_attention(qkv3, heads), per, flops=4.0 * L * L * 64 * heads * B2)
+    lnw, lnb = torch.ones(width, device=dev), torch.zeros(width, device=dev)
+    xn = torch.empty(M, width, device=dev, dtype=bf)
+    add("layernorm_bf16", lambda: ops.layernorm(h, lnw, lnb, out_dtype=bf, out=xn), 2 * per, bytes_=M * width * 6.0)
+    # fused sampler update (state is tiny at the configured batch: L2-resident, launch bound)
+    d = P.diffusion_from_config(P.DIFFUSION_CONFIGS["base40M"])
+    plan = P.HeunPlan(d, 64, 1e-3, 120.0, 7.0, 3.0)
+    for label, b in (("sampler_update_cfg_batch", Bc), ("sampler_update_large_batch", 4096)):
+        st = P.k_diffusion.HeunState(d, plan, (b, C, N), dev, 3.0, True)
+        st.x.normal_()
+        mo = torch.randn(2 * b, C, N, device=dev)
+        nz = torch.randn(b, C, N, device=dev)
+        pred = torch.empty(b, C, N, device=dev)
+        st.begin(nz)
+
+        def upd():
+            st.predictor(0, mo, pred)
+            st.corrector(0, mo, nz)
+        n_el = b * C * N * 4.0
+        # algorithmic bytes per Heun step: predictor r(x,out_c,out_u) w(d,model_in,pred) +
+        # corrector r(x,d,out_c,out_u,noise) w(x,model_in) = 13 array passes
+        add(label, upd, 64 if b == Bc else 0, bytes_=13.0 * n_el)
+    return res
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import pcd_b200 as P
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+    lib = P._lib.load()
+    assert lib.pcd_check_device() == 0, lib.pcd_last_error().decode()
+
+    mcfg, dcfg, B, smax, churn, guidance = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    cfg = P.MODEL_CONFIGS[mcfg]
+    torch.manual_seed(1234 + rank)
+    model = P.model_from_config(cfg, dev, dtype=torch.bfloat16)
+    with torch.no_grad():  # reference init + re-randomised output_proj
+        model.output_proj.weight.normal_(std=0.02)
+    diffusion = P.diffusion_from_config(P.DIFFUSION_CONFIGS[dcfg])
+    Cc, N = cfg["input_channels"], cfg["n_ctx"]
+    sampler = P.PointCloudSampler(dev, [model], [diffusion], [N], ["R", "G", "B"], guidance_scale=[guidance],
+                                  use_karras=[True], karras_steps=[64], sigma_min=[1e-3], sigma_max=[smax],
+                                  s_churn=[churn], use_cuda_graph=True)
+    emb_host = torch.randn(B, 768)
+    emb_host = (emb_host / emb_host.norm(dim=1, keepdim=True)).pin_memory()
+    emb_dev = emb_host.to(dev)
+    out_host = torch.empty(B, Cc, N).pin_memory()
+    gathered = torch.empty(world * B, Cc, N, device=dev) if world > 1 else None
+
+    def step_device():
+        y = sampler.sample_batch(B, dict(embeddings=emb_dev))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y.contiguous())
+        return y
+
+    def step_e2e():
+        e = emb_host.to(dev, non_blocking=True)
+        y = sampler.sample_batch(B, dict(embeddings=e))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y.contiguous())
+        out_host.copy_(y, non_blocking=False)  # device -> host read of the step's result
+        return out_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) * 1e-3
+
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    clocks = ClockSampler(local)
+    clocks.start()
+    n0 = lib.pcd_launch_count()
+    t_dev = timed(step_device, args.steps)
+    clk = clocks.stop()
+    # launches: the graph replays the kernels captured once; count them from one eager enqueue
+    stage = next(iter(sampler._graphs.values()))
+    c0 = lib.pcd_launch_count()
+    stage._enqueue()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.pcd_launch_count() - c0)
+    step_e2e()
+    t_e2e = timed(step_e2e, args.steps)
+
+    value = world * B * args.steps / t_dev
+    e2e_value = world * B * args.steps / t_e2e
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": world * B,
+                       "points": N, "heun_steps": 64, "denoiser_evals_per_step": 127,
+                       "sequences_per_eval": 2 * B, "seq_len": N + 2, "guidance": guidance, "s_churn": churn,
+                       "cache": "activations per forward (1.5 GB) exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"batch-sharded x{world}, all-gather of finished clouds"},
+            "denoiser_ms_per_heun_step": 1e3 * t_dev / args.steps / 64,
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": emb_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4},
+            "gpu_launches": launches_per_step * args.steps}
+    if rank == 0:
+        pk = peaks()
+        try:
+            kb = kernel_breakdown(P, model, 2 * B, N + 2, cfg["width"], cfg["heads"], cfg["layers"], B, Cc, N, pk)
+            dom = max((k for k in kb if kb[k]["launches_per_step"]), key=lambda k: kb[k]["ms_per_step"])
+            r = kb[dom]
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get(dom)
+            line["roofline"] = {"kernel": dom, "bound": r["bound"], "achieved": r["achieved"], "peak": r["peak"],
+                                "unit": r["unit"], "frac": r["frac"], "traffic": traffic,
+                                "peak_source": pk["source"] + (", burst (kernel timed alone)" if r["bound"] == "tensor" else "")}
+            line["kernels"] = {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()}
+                               for k, v in kb.items()}
+            line["kernel_ms_sum_per_step"] = sum(v["ms_per_step"] for v in kb.values())
+        except Exception as ex:  # the headline number must still be printed
+            line["roofline"] = {"error": repr(ex)}
+        if world == 1 and not args.no_cpu:
+            base, _ = cpu_sample(args.workload, heun_steps=4)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="base40M-imagevec-1024pt-b64", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,243 @@
+/*
+ * pcd_b200.h -- C ABI of the B200-native denoising-sampler hot path.
+ *
+ * The reference (entheeb/A-Multimodal-Diffusion-Based-Model-for-Point-Cloud-Completion)
+ * is 100 % Python and has no FFI: its boundary for this path is two Python call
+ * signatures, PointCloudSampler(...) (diffusion/sampler.py:26-171) and
+ * model(x, t, **kwargs) (models/transformer.py:195-226).  The Python shim in this
+ * repo keeps those signatures and calls the functions below through ctypes; each
+ * entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative pcd_status otherwise;
+ *    pcd_last_error() returns a thread-local message for the last failure.
+ *  - all data pointers are CALLER-OWNED DEVICE memory (the shim allocates with
+ *    PyTorch); nothing here allocates, synchronises or calls back into the host,
+ *    so every entry point is CUDA-graph capturable.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.
+ *  - matrices are row-major; "ld*" are leading dimensions in ELEMENTS.
+ *  - bf16 values are raw uint16 storage (torch.bfloat16).
+ */
+#ifndef PCD_B200_H_
+#define PCD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PCD_API __attribute__((visibility("default")))
+#else
+#define PCD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PCD_OK = 0,
+  PCD_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  PCD_ERR_CUDA = -2,      /* CUDA runtime or driver error (see pcd_last_error) */
+  PCD_ERR_UNSUPPORTED = -3
+} pcd_status;
+
+typedef enum { PCD_F32 = 0, PCD_BF16 = 1 } pcd_precision;
+
+/* GEMM epilogues: C = epi(A W^T + bias) */
+typedef enum {
+  PCD_EPI_BIAS = 0,          /* nn.Linear                         (transformer.py:45-47,55-56) */
+  PCD_EPI_BIAS_GELU = 1,     /* Linear + exact-erf GELU           (transformer.py:57,62)       */
+  PCD_EPI_BIAS_RESIDUAL = 2  /* residual + Linear                 (transformer.py:113-114)     */
+} pcd_epilogue;
+
+PCD_API int pcd_abi_version(void);
+PCD_API const char* pcd_last_error(void);
+/* Kernels launched through this library since it was loaded (host-side counter). */
+PCD_API unsigned long long pcd_launch_count(void);
+/* Device capability probe: 0 if the current device is sm_100 (B200). */
+PCD_API int pcd_check_device(void);
+
+/* Tuning / testing knob (no reference counterpart): attention P operand placement,
+ * 1 = P kept in TMEM (tcgen05.mma with A from TMEM, two CTAs per SM; default),
+ * 0 = P staged through 128B-swizzled shared memory. */
+PCD_API int pcd_set_attention_variant(int variant);
+
+/* ------------------------------------------------------------------ */
+/* Elementwise / normalisation kernels                                 */
+/* ------------------------------------------------------------------ */
+
+/* timestep_embedding (models/util.py:72-89): out[b, :] = [cos(t_b f) || sin(t_b f)],
+ * f = host-computed frequency table [dim/2] (same fp32 values as the reference's CPU
+ * torch.exp).  t is float (int64 timesteps are exact in fp32 below 2^24). */
+PCD_API int pcd_timestep_embed(const float* t, const float* freqs, int batch, int dim,
+                       float* out, int ld_out, void* stream);
+
+/* nn.LayerNorm(dim, eps) with affine (transformer.py:108,110,176,186): x fp32
+ * [rows, dim] -> out fp32 or bf16 [rows, dim]. */
+PCD_API int pcd_layernorm(const float* x, int ldx, const float* gamma, const float* beta,
+                  void* out, int ld_out, int out_precision, int rows, int dim, float eps,
+                  void* stream);
+
+/* Token assembly + ln_pre (transformer.py:205-220).  For sequence s in [0, seqs)
+ * and position l in [0, n_prefix + n_points):
+ *   l <  n_prefix : row = prefix[s, l, :]                     (conditioning tokens)
+ *   l >= n_prefix : row = W_in x[s % x_seqs, :, l-n_prefix] + b_in (+ add_cond[s, :])
+ * then h[s, l, :] = LayerNorm(row).  x is [x_seqs, c_in, n_points] (NCL, as the
+ * sampler holds it); w_in is [dim, c_in]. */
+PCD_API int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_points,
+                     const float* w_in, const float* b_in,
+                     const float* prefix, int n_prefix, const float* add_cond,
+                     const float* ln_g, const float* ln_b, float eps,
+                     float* h, int seqs, int dim, void* stream);
+
+/* ln_post + token slice + output_proj + NLC->NCL permute (transformer.py:222-226):
+ * out[s, c, n] = W_out[c, :] . LayerNorm(h[s, n_prefix + n, :]) + b_out[c]. */
+PCD_API int pcd_output_proj(const float* h, int seqs, int n_prefix, int n_points, int dim,
+                    const float* ln_g, const float* ln_b, float eps,
+                    const float* w_out, const float* b_out, int c_out,
+                    float* out, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Projections: C[M,N] = epi(A[M,K] W[N,K]^T + bias)                    */
+/* ------------------------------------------------------------------ */
+
+/* fp32 mode: CUDA-core FFMA GEMM (fp32 accumulate), used for the 1e-4 parity mode
+ * and for the tiny per-sequence layers (time MLP, clip_embed). residual/out fp32. */
+PCD_API int pcd_gemm_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                 const float* residual, int ldr, float* C, int ldc,
+                 int M, int N, int K, int epilogue, void* stream);
+
+/* bf16 mode: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM) fed by TMA with
+ * 128B swizzle, persistent over 128 x BN tiles.  A, W bf16; bias/residual fp32;
+ * C is bf16 (out_precision = PCD_BF16) or fp32.  Requires K % 8 == 0, lda % 8 == 0,
+ * ldw % 8 == 0 (16-byte TMA strides). */
+PCD_API int pcd_gemm_bf16(const uint16_t* A, int lda, const uint16_t* W, int ldw, const float* bias,
+                  const float* residual, int ldr, void* C, int ldc, int out_precision,
+                  int M, int N, int K, int epilogue, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Attention (head dim 64), softmax in fp32                             */
+/* ------------------------------------------------------------------ */
+
+/* Strided description of one operand: element (b, l, h, c) lives at
+ * ptr[b*batch_stride + l*row_stride + h*head_stride + c], c in [0, 64). */
+typedef struct {
+  const void* ptr;
+  int64_t batch_stride;
+  int64_t row_stride;
+  int64_t head_stride;
+} pcd_attn_operand;
+
+/* out[b, l, h*64 + c] = sum_s softmax_s((q_scale q[b,l,h]) . (k_scale k[b,s,h])) v[b,s,h,c]
+ *  - self-attention   (transformer.py:65-84):   q,k,v views of qkv [B,L,H,3,64], scales 64^-1/4
+ *  - cross-attention  (perceiver.py:46-67):     q [B,Lq,H,64], k,v views of kv [B,Lkv,H,2,64]
+ *  - rotary attention (rotaryencoderpcd.py:6-27,68-84): rope_coords [B,L,3] != NULL applies
+ *    theta = pi*coords to head dims 0..5 of q and k (requires Lq == Lkv);
+ *    q_scale = width^-1/2, k_scale = 1.
+ * `precision` selects the operand/out dtype: PCD_F32 (CUDA-core kernel) or PCD_BF16
+ * (tcgen05 flash kernel: QK^T and PV on tensor cores, accumulators in TMEM). */
+PCD_API int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
+                  void* out, int64_t out_batch_stride, int64_t out_row_stride,
+                  int batch, int heads, int len_q, int len_kv,
+                  float q_scale, float k_scale, const float* rope_coords,
+                  int precision, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Fused Karras/Heun sampler updates (k_diffusion.py:270-310,79-108,182-207;  */
+/* gaussian_diffusion.py:320-357,949-958).  State fp32 [B, C, N].              */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+  float c_in;         /* 1/sqrt(sigma_eval^2+1) of the evaluation that produced `model_out` */
+  float coef_x;       /* sqrt(1/abar_t)     at the truncated integer t of that evaluation   */
+  float coef_eps;     /* sqrt(1/abar_t - 1)                                                 */
+  float sigma;        /* sigma of that evaluation (sigma_hat_i or sigma_{i+1})              */
+  float dt;           /* sigma_{i+1} - sigma_hat_i                                          */
+  float guidance;     /* classifier-free guidance scale (used iff uncond rows present)      */
+  float clip;         /* 1: clamp x0 to [-1,1] (clip_denoised), 0: no clamp                  */
+  float next_c_in;    /* c_in of the NEXT evaluation (prescale of the next model input)     */
+  float next_noise;   /* sqrt(sigma_hat^2 - sigma^2) of the next step's churn (0: none)     */
+} pcd_step_scalars;
+
+/* Start of the loop: x <- x + noise*s.next_noise (if != 0); model_in <- x*s.next_c_in. */
+PCD_API int pcd_sampler_begin(float* x, const float* noise, float* model_in,
+                      const pcd_step_scalars* s, int64_t numel, void* stream);
+
+/* First (Euler/predictor) evaluation of Heun step i.  model_out is [seqs_out, c_out, N]
+ * with the conditional rows first and, if `guided`, the unconditional rows after them;
+ * only channels [0, C) (epsilon) are read.
+ *   x0 = clamp(coef_x*(x*c_in) - coef_eps*eps)      per branch, then CFG combine
+ *   d  = (x - x0)/sigma;  pred_unscaled = (x0 - ch_bias)/ch_scale
+ *   last == 0: model_in <- (x + d*dt)*next_c_in, d stored for the corrector
+ *   last != 0: x <- x + d*dt                                        (sigma_{i+1} == 0) */
+PCD_API int pcd_sampler_predictor(float* x, const float* model_out, int c_out, int guided,
+                          float* d, float* model_in, float* pred_unscaled,
+                          const float* ch_scale, const float* ch_bias,
+                          const pcd_step_scalars* s, int batch, int channels, int n_points,
+                          int last, void* stream);
+
+/* Second (corrector) evaluation: x2 = x + d*dt; d2 = (x2 - x0_2)/sigma;
+ * x <- x + (d+d2)/2*dt; then the next step's churn + prescale:
+ * x <- x + noise*next_noise; model_in <- x*next_c_in. */
+PCD_API int pcd_sampler_corrector(float* x, const float* model_out, int c_out, int guided,
+                          const float* d, const float* noise, float* model_in,
+                          const pcd_step_scalars* s, int batch, int channels, int n_points,
+                          void* stream);
+
+/* Squared-L2 Chamfer distance on xyz (models/util.py:265-295): p1 [B,C1,N1],
+ * p2 [B,C2,N2] -> out [B].  Tiled nearest-neighbour search, no [B,N1,N2] matrix. */
+PCD_API int pcd_chamfer(const float* p1, int c1, int n1, const float* p2, int c2, int n2,
+                int batch, float* out, float* workspace /* >= batch*(n1+n2) floats */,
+                void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Whole-denoiser forward (transformer.py:118-152,195-226)             */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;          /* ln_1, ln_2                     */
+  const void *w_qkv, *w_proj, *w_fc, *w_fc2;           /* [3d,d] [d,d] [4d,d] [d,4d]; fp32 or bf16 per precision */
+  const float *b_qkv, *b_proj, *b_fc, *b_fc2;
+} pcd_block_weights;
+
+typedef struct {
+  int precision;            /* pcd_precision of the backbone                        */
+  int width, heads, layers; /* width = heads*64                                     */
+  int c_in, c_out;          /* input_proj / output_proj channels                    */
+  int n_points;             /* n_ctx of the point tokens                            */
+  int n_prefix;             /* conditioning tokens in front of the points           */
+  int time_slot;            /* index of the time token in the prefix, or -1 when the
+                               time embedding is ADDED to the point tokens instead  */
+  float ln_eps;
+  /* always fp32: */
+  const float *time_fc_w, *time_fc_b, *time_proj_w, *time_proj_b;   /* time_embed MLP      */
+  const float *freqs;                                                /* [width/2]          */
+  const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+  const float *in_w, *in_b, *out_w, *out_b;                          /* input/output_proj  */
+  const pcd_block_weights* blocks;                                   /* HOST array [layers] */
+} pcd_model_desc;
+
+typedef struct pcd_model pcd_model;
+
+PCD_API int pcd_model_create(const pcd_model_desc* desc, pcd_model** out);
+PCD_API int pcd_model_destroy(pcd_model* m);
+/* Bytes of device workspace pcd_model_forward needs for `seqs` sequences. */
+PCD_API size_t pcd_model_workspace_bytes(const pcd_model* m, int seqs);
+
+/* out[s] = model(x[s % x_seqs], t[s], prefix[s]) for s in [0, seqs).
+ *  x       fp32 [x_seqs, c_in, n_points]  (x_seqs == seqs, or seqs/2 when the cond and
+ *          uncond halves of classifier-free guidance share the same x)
+ *  t       fp32 [seqs]
+ *  prefix  fp32 [seqs, n_prefix, width]; slot `time_slot` is (over)written with the
+ *          time-MLP output; the other slots hold step-invariant conditioning tokens
+ *  add_cond fp32 [seqs, width] or NULL: non-token conditioning added to point tokens
+ *  out     fp32 [seqs, c_out_eff, n_points] where c_out_eff = out_channels (<= c_out:
+ *          the sampler only needs the epsilon half, transformer.py:225) */
+PCD_API int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const float* t,
+                      float* prefix, const float* add_cond, float* out, int out_channels,
+                      void* workspace, size_t workspace_bytes, int seqs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCD_B200_H_ */

@@ -1,0 +1,154 @@
+"""Shared definitions of the parity cases (TEST INFRASTRUCTURE).
+
+Every case is fully described by small integers: shapes, config overrides and
+hash seeds (oracle/det.py).  ``oracle/make_golden.py`` runs the UNMODIFIED
+reference on them in the authoring container and stores only the OUTPUTS under
+tests/golden/; the tests regenerate inputs and weights from the same seeds.
+"""
+import copy
+
+import torch
+
+from . import det
+
+# reference models/configs.py:15-114 restated (shapes only; the oracle and the
+# product each carry their own copy -- this one drives fixtures).
+_BASE = dict(heads=8, init_scale=0.25, input_channels=6, layers=12, n_ctx=1024,
+             output_channels=12, time_token_cond=True, width=512)
+_SCALES = [2.0, 2.0, 2.0, 0.007843137255, 0.007843137255, 0.007843137255]
+_BIASES = [0.0, 0.0, 0.0, -1.0, -1.0, -1.0]
+MODEL_CONFIGS = {
+    "base40M-imagevec": dict(_BASE, name="CLIPImagePointDiffusionTransformer",
+                             cond_drop_prob=0.1, token_cond=True),
+    "base40M-textvec": dict(_BASE, name="CLIPImagePointDiffusionTransformer",
+                            cond_drop_prob=0.1, token_cond=True),
+    "base40M-uncond": dict(_BASE, name="PointDiffusionTransformer"),
+    "base40M": dict(_BASE, name="CLIPImageGridPointDiffusionTransformer", cond_drop_prob=0.1),
+    "base300M": dict(_BASE, name="CLIPImageGridPointDiffusionTransformer", cond_drop_prob=0.1,
+                     heads=16, layers=24, width=1024),
+    "upsample": dict(_BASE, name="CLIPImageGridUpsamplePointDiffusionTransformer",
+                     cond_drop_prob=0.1, cond_ctx=1024, n_ctx=3072,
+                     channel_scales=_SCALES, channel_biases=_BIASES),
+    "upsample-plain": dict(_BASE, name="UpsamplePointDiffusionTransformer",
+                           cond_ctx=1024, n_ctx=3072,
+                           channel_scales=_SCALES, channel_biases=_BIASES),
+}
+DIFFUSION_CONFIGS = {
+    "base": dict(schedule="cosine", timesteps=1024, mean_type="epsilon",
+                 channel_scales=_SCALES, channel_biases=_BIASES),
+    "upsample": dict(schedule="linear", timesteps=1024, mean_type="epsilon",
+                     channel_scales=_SCALES, channel_biases=_BIASES),
+}
+
+SMALL = dict(width=128, layers=2, heads=2, n_ctx=64)
+
+
+def small_cfg(name, **over):
+    cfg = copy.deepcopy(MODEL_CONFIGS[name])
+    cfg.update(SMALL)
+    if "cond_ctx" in cfg:
+        cfg["cond_ctx"] = 32
+    cfg.update(over)
+    return cfg
+
+
+# name -> (config, batch, weight seed, weight mode)
+FORWARD_CASES = {
+    "small_uncond": (small_cfg("base40M-uncond"), 2, 101, "unit"),
+    "small_uncond_addcond": (small_cfg("base40M-uncond", time_token_cond=False), 2, 102, "unit"),
+    "small_imagevec": (small_cfg("base40M-imagevec"), 3, 103, "unit"),
+    "small_imagevec_addcond": (small_cfg("base40M-imagevec", token_cond=False), 2, 104, "unit"),
+    "small_grid": (small_cfg("base40M"), 2, 105, "unit"),
+    "small_upsample_plain": (small_cfg("upsample-plain"), 2, 106, "unit"),
+    "small_upsample_grid": (small_cfg("upsample"), 2, 107, "unit"),
+    "small_xyz_only": (small_cfg("base40M-uncond", input_channels=3, output_channels=6,
+                                 n_ctx=100), 2, 108, "unit"),
+    "full_imagevec": (copy.deepcopy(MODEL_CONFIGS["base40M-imagevec"]), 2, 201, "reference"),
+    "full_upsample": (copy.deepcopy(MODEL_CONFIGS["upsample"]), 1, 202, "reference"),
+    "full_base300M": (copy.deepcopy(MODEL_CONFIGS["base300M"]), 1, 203, "reference"),
+}
+
+
+def forward_inputs(name):
+    """Deterministic (x, t, kwargs) for a forward case."""
+    cfg, B, seed, _ = FORWARD_CASES[name]
+    C, N = cfg["input_channels"], cfg["n_ctx"]
+    x = det.normal((B, C, N), seed * 10 + 1)
+    t = torch.tensor([(1017, 3, 511, 0)[i % 4] for i in range(B)], dtype=torch.long)
+    kw = {}
+    cls = cfg["name"]
+    if cls == "CLIPImagePointDiffusionTransformer":
+        e = det.normal((B, 768), seed * 10 + 2)
+        kw["embeddings"] = e / e.norm(dim=1, keepdim=True)
+    if cls in ("CLIPImageGridPointDiffusionTransformer",
+               "CLIPImageGridUpsamplePointDiffusionTransformer"):
+        kw["embeddings"] = det.normal((B, 1024, 256), seed * 10 + 3)
+    if "Upsample" in cls:
+        P = cfg["cond_ctx"]
+        lr = det.uniform((B, C, P), seed * 10 + 4, std=0.5 / 3 ** 0.5)  # xyz ~ U(-0.5, 0.5)
+        lr[:, 3:] = (lr[:, 3:] + 0.5) * 255.0  # rgb ~ U(0, 255), unscaled units
+        kw["low_res"] = lr
+    return x, t, kw
+
+
+def model_ctor_cfg(cfg):
+    """Config dict as the reference's model_from_config expects it."""
+    c = copy.deepcopy(cfg)
+    if c["name"] == "UpsamplePointDiffusionTransformer":
+        c.pop("cond_drop_prob", None)
+    return c
+
+
+# sampler cases: name -> dict
+SAMPLER_CASES = {
+    # guided, churned, cosine schedule (stage-1 defaults, sampler.py:34-40)
+    "small_imagevec_guided": dict(model="small_imagevec", diffusion="base", B=2, steps=64,
+                                  sigma_min=1e-3, sigma_max=120.0, s_churn=3.0, guidance=3.0,
+                                  noise_seed=9001),
+    # unguided, no churn, linear schedule with low_res conditioning (stage-2 defaults)
+    "small_upsample_unguided": dict(model="small_upsample_grid", diffusion="upsample", B=2,
+                                    steps=64, sigma_min=1e-3, sigma_max=160.0, s_churn=0.0,
+                                    guidance=0.0, noise_seed=9002),
+    # unconditional model, guidance off, few steps
+    "small_uncond_16": dict(model="small_uncond", diffusion="base", B=3, steps=16,
+                            sigma_min=1e-3, sigma_max=120.0, s_churn=3.0, guidance=1.0,
+                            noise_seed=9003),
+    # full-size north-star config 1/2 shape: base40M-imagevec, B=1, 64 steps, guidance 3
+    "full_imagevec_guided": dict(model="full_imagevec", diffusion="base", B=1, steps=64,
+                                 sigma_min=1e-3, sigma_max=120.0, s_churn=3.0, guidance=3.0,
+                                 noise_seed=9004),
+}
+
+
+def sampler_kwargs(case):
+    """Deterministic conditioning kwargs (before CFG doubling) for a sampler case."""
+    sc = SAMPLER_CASES[case]
+    cfg, _, seed, _ = FORWARD_CASES[sc["model"]]
+    B = sc["B"]
+    cls = cfg["name"]
+    kw = {}
+    if cls == "CLIPImagePointDiffusionTransformer":
+        e = det.normal((B, 768), seed * 10 + 7)
+        kw["embeddings"] = e / e.norm(dim=1, keepdim=True)
+    elif "Grid" in cls:
+        kw["embeddings"] = det.normal((B, 1024, 256), seed * 10 + 8)
+    if "Upsample" in cls:
+        C, P = cfg["input_channels"], cfg["cond_ctx"]
+        lr = det.uniform((B, C, P), seed * 10 + 9, std=0.5 / 3 ** 0.5)
+        lr[:, 3:] = (lr[:, 3:] + 0.5) * 255.0
+        kw["low_res"] = lr
+    return kw
+
+
+class DetNoise:
+    """Counter-based replacement for the torch RNG draws of the sampling loop
+    (reference k_diffusion.py:139 draw #0, :292 draw #i+1)."""
+
+    def __init__(self, seed):
+        self.seed = seed
+        self.count = 0
+
+    def __call__(self, shape):
+        out = det.normal(tuple(shape), self.seed * 1000 + self.count)
+        self.count += 1
+        return out

@@ -1,0 +1,234 @@
+"""Oracle restatement of the Karras/Heun sampling stack (CPU, fp32).
+
+Follows reference diffusion/gaussian_diffusion.py, diffusion/k_diffusion.py and
+diffusion/sampler.py.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""
+import math
+from typing import Any, Callable, Dict, Iterator, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import denoiser as D
+
+
+# ---------------------------------------------------------------------------
+# Gaussian diffusion tables (reference diffusion/gaussian_diffusion.py)
+# ---------------------------------------------------------------------------
+def named_beta_schedule(name: str, n: int) -> np.ndarray:
+    """reference gaussian_diffusion.py:26-72 (float64)."""
+    if name == "linear":
+        scale = 1000 / n
+        return np.linspace(scale * 0.0001, scale * 0.02, n, dtype=np.float64)
+    if name == "cosine":
+        f = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2
+        betas = [min(1 - f((i + 1) / n) / f(i / n), 0.999) for i in range(n)]
+        return np.array(betas)
+    raise NotImplementedError(name)
+
+
+class Tables:
+    """The pieces of GaussianDiffusion.__init__ the Karras path touches
+    (reference gaussian_diffusion.py:144-196) plus the channel scaling
+    (:938-965)."""
+
+    def __init__(self, schedule="cosine", timesteps=1024, channel_scales=None,
+                 channel_biases=None, mean_type="epsilon", **_):
+        betas = np.array(named_beta_schedule(schedule, timesteps), dtype=np.float64)
+        self.betas = betas
+        self.num_timesteps = int(betas.shape[0])
+        self.alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.channel_scales = None if channel_scales is None else np.array(channel_scales)
+        self.channel_biases = None if channel_biases is None else np.array(channel_biases)
+        assert mean_type == "epsilon"
+
+    def unscale(self, x: torch.Tensor) -> torch.Tensor:
+        """reference gaussian_diffusion.py:949-958."""
+        shape = [1, -1] + [1] * (x.dim() - 2)
+        if self.channel_biases is not None:
+            x = x - torch.from_numpy(self.channel_biases).to(x).reshape(shape)
+        if self.channel_scales is not None:
+            x = x / torch.from_numpy(self.channel_scales).to(x).reshape(shape)
+        return x
+
+    def pred_xstart(self, model_out: torch.Tensor, x_in: torch.Tensor, t: torch.Tensor,
+                    clip: bool = True) -> torch.Tensor:
+        """reference gaussian_diffusion.py:285-338,352-357 with learned_range output:
+        eps = first C channels; x0 = a_t*x - b_t*eps; clamp to [-1, 1]."""
+        C = x_in.shape[1]
+        eps = model_out[:, :C]
+        a = torch.from_numpy(self.sqrt_recip_alphas_cumprod)[t].float()
+        b = torch.from_numpy(self.sqrt_recipm1_alphas_cumprod)[t].float()
+        while a.dim() < x_in.dim():
+            a, b = a[..., None], b[..., None]
+        x0 = a * x_in - b * eps
+        return x0.clamp(-1, 1) if clip else x0
+
+
+class SigmaToT:
+    """reference k_diffusion.py:79-96 (scipy interp1d over the float64 alpha-bar table;
+    the caller truncates to int64, :99-103)."""
+
+    def __init__(self, tables: Tables):
+        from scipy import interpolate
+
+        self.ac = tables.alphas_cumprod
+        self.T = tables.num_timesteps
+        self.f = interpolate.interp1d(self.ac, np.arange(0, self.T))
+
+    def __call__(self, sigma) -> int:
+        sigma = np.float32(sigma)
+        alpha_cumprod = 1.0 / (sigma ** 2 + 1)
+        if alpha_cumprod > self.ac[0]:
+            return 0
+        if alpha_cumprod <= self.ac[-1]:
+            return self.T - 1
+        return int(float(self.f(alpha_cumprod)))
+
+
+def karras_sigmas(n: int, sigma_min: float, sigma_max: float, rho: float = 7.0) -> torch.Tensor:
+    """reference k_diffusion.py:225-231 (+ append_zero :362)."""
+    ramp = torch.linspace(0, 1, n)
+    min_inv_rho = sigma_min ** (1 / rho)
+    max_inv_rho = sigma_max ** (1 / rho)
+    sigmas = (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** rho
+    return torch.cat([sigmas, sigmas.new_zeros([1])])
+
+
+def heun_progressive(
+    model_fn: Callable[..., torch.Tensor],
+    tables: Tables,
+    shape: Sequence[int],
+    steps: int = 64,
+    sigma_min: float = 1e-3,
+    sigma_max: float = 120.0,
+    rho: float = 7.0,
+    s_churn: float = 0.0,
+    s_tmin: float = 0.0,
+    s_tmax: float = float("inf"),
+    s_noise: float = 1.0,
+    guidance_scale: float = 0.0,
+    clip_denoised: bool = True,
+    model_kwargs: Optional[Dict[str, torch.Tensor]] = None,
+    generator: Optional[torch.Generator] = None,
+    trace: Optional[list] = None,
+    noise_fn: Optional[Callable] = None,
+) -> Iterator[Dict[str, Any]]:
+    """reference k_diffusion.py:118-222 (karras_sample_progressive with a
+    GaussianDiffusion, sampler="heun") + :270-310 (sample_heun) + :79-108
+    (GaussianToKarrasDenoiser) + :182-207 (guided_denoiser).
+
+    ``model_fn(x, t, **kwargs)`` returns [B, 2C, N] (or a tuple whose first item
+    is that).  With guidance the kwargs hold 2B rows: [:B] conditional, [B:]
+    unconditional, evaluated as two separate B-sized calls.  Yields the
+    *unscaled* dicts exactly like the reference.  ``trace`` (optional list)
+    collects per-eval (t, x_in, model_out) tuples for per-step parity checks.
+    """
+    model_kwargs = model_kwargs or {}
+    sigmas = karras_sigmas(steps, sigma_min, sigma_max, rho)
+    if noise_fn is None:
+        noise_fn = lambda shp: torch.randn(*shp, generator=generator)
+    x = noise_fn(tuple(shape)) * sigma_max
+    s2t = SigmaToT(tables)
+    B = shape[0]
+
+    def denoise(x_t, sigma, kwargs):
+        t = torch.tensor([s2t(s) for s in sigma.cpu().numpy()], dtype=torch.long)
+        c_in = (1.0 / (sigma ** 2 + 1) ** 0.5)[(...,) + (None,) * (x_t.dim() - 1)]
+        x_in = x_t * c_in
+        out = model_fn(x_in, t, **kwargs)
+        if isinstance(out, tuple):
+            out = out[0]
+        if trace is not None:
+            trace.append((t.clone(), x_in.clone(), out.clone()))
+        return tables.pred_xstart(out, x_in, t, clip_denoised)
+
+    if guidance_scale != 0 and guidance_scale != 1:
+        def denoiser(x_t, sigma):
+            cond = denoise(x_t, sigma, {k: v[:B] for k, v in model_kwargs.items()})
+            uncond = denoise(x_t, sigma, {k: v[B:] for k, v in model_kwargs.items()})
+            return uncond + guidance_scale * (cond - uncond)
+    else:
+        def denoiser(x_t, sigma):
+            return denoise(x_t, sigma, model_kwargs)
+
+    def to_d(x, sigma, denoised):
+        return (x - denoised) / sigma[(...,) + (None,) * (x.dim() - sigma.dim())]
+
+    s_in = x.new_ones([B])
+    denoised = None
+    for i in range(len(sigmas) - 1):
+        gamma = (min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1)
+                 if s_tmin <= sigmas[i] <= s_tmax else 0.0)
+        eps = noise_fn(tuple(x.shape)) * s_noise  # always drawn (:292)
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        denoised = denoiser(x, sigma_hat * s_in)
+        d = to_d(x, sigma_hat, denoised)
+        yield {"x": tables.unscale(x), "i": i, "pred_xstart": tables.unscale(denoised)}
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            denoised_2 = denoiser(x_2, sigmas[i + 1] * s_in)
+            d_2 = to_d(x_2, sigmas[i + 1], denoised_2)
+            x = x + (d + d_2) / 2 * dt
+    yield {"x": tables.unscale(x), "pred_xstart": tables.unscale(denoised)}
+
+
+def sample_batch_progressive(
+    model_fns: Sequence[Callable],
+    cached_kwargs_fns: Sequence[Optional[Callable]],
+    tables: Sequence[Tables],
+    num_points: Sequence[int],
+    aux_channels: Sequence[str],
+    batch_size: int,
+    model_kwargs: Dict[str, Any],
+    guidance_scale: Sequence[float] = (3.0, 3.0),
+    karras_steps: Sequence[int] = (64, 64),
+    sigma_min: Sequence[float] = (1e-3, 1e-3),
+    sigma_max: Sequence[float] = (120, 160),
+    s_churn: Sequence[float] = (3, 0),
+    key_filter: Sequence[str] = ("*",),
+    clip_denoised: bool = True,
+    generator: Optional[torch.Generator] = None,
+    noise_fn: Optional[Callable] = None,
+) -> Iterator[torch.Tensor]:
+    """reference diffusion/sampler.py:96-171 (Karras branch)."""
+    n = len(model_fns)
+    if len(key_filter) == 1:
+        key_filter = list(key_filter) * n
+    samples = None
+    for s in range(n):
+        kw = dict(model_kwargs)
+        if key_filter[s] != "*":
+            keep = set(key_filter[s].split(","))
+            kw = {k: v for k, v in kw.items() if k in keep}
+        if samples is not None:
+            kw["low_res"] = samples
+        if cached_kwargs_fns[s] is not None:
+            kw = cached_kwargs_fns[s](batch_size, kw)
+        shape = (batch_size, 3 + len(aux_channels), num_points[s])
+        g = guidance_scale[s]
+        if g != 1 and g != 0:
+            kw = {k: torch.cat([v, torch.zeros_like(v)], dim=0) for k, v in kw.items()}
+        for out in heun_progressive(
+            model_fns[s], tables[s], shape, steps=karras_steps[s], sigma_min=sigma_min[s],
+            sigma_max=sigma_max[s], s_churn=s_churn[s], guidance_scale=g,
+            clip_denoised=clip_denoised, model_kwargs=kw, generator=generator, noise_fn=noise_fn,
+        ):
+            samples = out["pred_xstart"][:batch_size]
+            if "low_res" in kw:
+                samples = torch.cat([kw["low_res"][: len(samples)], samples], dim=-1)
+            yield samples
+
+
+def make_model_fn(sd, cfg):
+    """Bind an oracle denoiser to a state dict: model_fn(x, t, **kwargs)."""
+    def fn(x, t, **kw):
+        return D.denoiser_forward(sd, cfg, x, t, **kw)
+    return fn

@@ -1,0 +1,185 @@
+"""Kernel-level parity (through the C ABI) against the CPU oracle / golden vectors."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_util import DEV, describe, rel
+from oracle import denoiser as D
+from oracle import det
+
+import pcd_b200 as P
+ops = P.ops
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def test_device_is_b200():
+    assert P._lib.load().pcd_check_device() == 0, P._lib.load().pcd_last_error()
+
+
+def test_timestep_embedding_matches_reference():
+    g = load_golden("ops")
+    t_int = torch.tensor([0, 1, 17, 511, 1017, 1023], dtype=torch.long, device=DEV)
+    t_flt = torch.tensor([0.5, 250.25, 999.75], dtype=torch.float32, device=DEV)
+    for d in (128, 512):
+        a = ops.timestep_embedding(t_int, d).cpu()
+        assert (a - torch.from_numpy(g[f"temb_int_{d}"])).abs().max() < 2e-6, describe(a, g[f"temb_int_{d}"])
+        b = ops.timestep_embedding(t_flt, d).cpu()
+        assert (b - torch.from_numpy(g[f"temb_flt_{d}"])).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("dim", [128, 192, 512, 768, 1024, 2048])
+def test_layernorm(dim):
+    x = det.normal((37, dim), 401 + dim, std=2.0) + 0.5
+    w = 1.0 + det.uniform((dim,), 402, 0.2)
+    b = det.uniform((dim,), 403, 0.2)
+    want = torch.nn.functional.layer_norm(x, (dim,), w, b, 1e-5)
+    got = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV))
+    assert rel(got, want) < 2e-6, describe(got, want)
+    got16 = ops.layernorm(x.to(DEV), w.to(DEV), b.to(DEV), out_dtype=torch.bfloat16)
+    assert got16.dtype == torch.bfloat16
+    assert rel(got16.float(), want) < 4e-3, describe(got16.float(), want)
+
+
+GEMM_SHAPES = [  # M, N, K
+    (128, 128, 64), (128, 256, 128), (256, 512, 512), (300, 384, 128), (1026, 1536, 512),
+    (77, 256, 192), (5, 2048, 512), (1000, 128, 2048), (640, 72, 64), (129, 520, 72),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_f32(M, N, K, epi):
+    if K % 4:
+        pytest.skip("K % 4")
+    a = det.normal((M, K), 500 + M)
+    w = det.uniform((N, K), 501 + N, 1 / math.sqrt(K))
+    bias = det.uniform((N,), 502, 0.5)
+    res = det.normal((M, N), 503)
+    want = a.double() @ w.double().t() + bias.double()
+    if epi == 1:
+        want = torch.nn.functional.gelu(want)
+    if epi == 2:
+        want = want + res.double()
+    got = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), epilogue=epi, residual=res.to(DEV) if epi == 2 else None)
+    assert got.shape == (M, N)
+    assert rel(got, want) < 2e-6, describe(got, want, f"gemm_f32 {M}x{N}x{K} epi{epi}")
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi,out_dtype", [(0, torch.bfloat16), (0, torch.float32), (1, torch.bfloat16),
+                                           (2, torch.float32)])
+def test_gemm_bf16_tcgen05(M, N, K, epi, out_dtype):
+    a = bf16_round(det.normal((M, K), 600 + M))
+    w = bf16_round(det.uniform((N, K), 601 + N, 1 / math.sqrt(K)))
+    bias = det.uniform((N,), 602, 0.5)
+    res = det.normal((M, N), 603)
+    want = a.double() @ w.double().t() + bias.double()
+    if epi == 1:
+        want = torch.nn.functional.gelu(want)
+    if epi == 2:
+        want = want + res.double()
+    got = ops.linear(a.to(DEV).bfloat16(), w.to(DEV).bfloat16(), bias.to(DEV), epilogue=epi,
+                     residual=res.to(DEV) if epi == 2 else None, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    assert got.dtype == out_dtype and got.shape == (M, N)
+    tol = 3e-3 if out_dtype == torch.bfloat16 else 1e-5  # bf16 output rounding vs fp32 accumulate
+    assert rel(got.float(), want) < tol, describe(got.float(), want, f"gemm_bf16 {M}x{N}x{K} epi{epi}")
+
+
+def test_gemm_bf16_large_persistent():
+    """More tiles than SMs, several accumulator phases per CTA, K > one stage ring."""
+    M, N, K = 128 * 150 + 17, 512, 2048
+    a = bf16_round(det.normal((M, K), 610))
+    w = bf16_round(det.uniform((N, K), 611, 1 / math.sqrt(K)))
+    bias = det.uniform((N,), 612, 0.5)
+    got = ops.linear(a.to(DEV).bfloat16(), w.to(DEV).bfloat16(), bias.to(DEV), out_dtype=torch.float32)
+    want = (a.to(DEV) @ w.to(DEV).t() + bias.to(DEV))
+    assert rel(got, want) < 1e-4, describe(got, want)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("variant", [1, 0])
+def test_self_attention_golden(dtype, tol, variant):
+    if dtype == torch.float32 and variant == 0:
+        pytest.skip("variant only affects the tensor-core kernel")
+    P._lib.load().pcd_set_attention_variant(variant)
+    try:
+        g = load_golden("ops")
+        for name, shape, seed, std, heads in (("self_attn", (2, 70, 384), 301, 1.0, 2),
+                                              ("self_attn_h8", (1, 300, 1536), 302, 2.0, 8)):
+            qkv = det.normal(shape, seed, std=std)
+            want = torch.from_numpy(g[name])
+            if dtype == torch.bfloat16:
+                want = D.qkv_attention(bf16_round(qkv), heads)
+            got = ops.self_attention(qkv.to(DEV).to(dtype), heads)
+            torch.cuda.synchronize()
+            assert rel(got.float(), want) < tol, describe(got.float(), want, f"{name} {dtype} v{variant}")
+    finally:
+        P._lib.load().pcd_set_attention_variant(1)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("L", [1, 16, 127, 128, 129, 256, 1026])
+def test_self_attention_lengths(dtype, tol, L):
+    """Tile tails: L = 1 .. 1026 (the north-star L = 1024 + 2 prefix tokens)."""
+    heads, B = 2, 2
+    qkv = det.normal((B, L, heads * 192), 700 + L, std=1.5)
+    src = bf16_round(qkv) if dtype == torch.bfloat16 else qkv
+    want = D.qkv_attention(src, heads)
+    got = ops.self_attention(qkv.to(DEV).to(dtype), heads)
+    torch.cuda.synchronize()
+    assert rel(got.float(), want) < tol, describe(got.float(), want, f"L={L} {dtype}")
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
+def test_cross_attention_golden(dtype, tol):
+    g = load_golden("ops")
+    q, kv = det.normal((2, 70, 128), 303), det.normal((2, 77, 256), 304)
+    want = torch.from_numpy(g["cross_attn"])
+    if dtype == torch.bfloat16:
+        want = D.qkv_cross_attention(bf16_round(q), bf16_round(kv), 2)
+    got = ops.cross_attention(q.to(DEV).to(dtype), kv.to(DEV).to(dtype), 2)
+    assert rel(got.float(), want) < tol, describe(got.float(), want)
+
+
+def test_rotary_attention_golden():
+    g = load_golden("ops")
+    coords = det.uniform((2, 70, 3), 307, std=0.5 / 3 ** 0.5)
+    from test_oracle_golden import TOL  # noqa: F401
+    sd = det.fill_state_dict({"qkv.weight": torch.zeros(384, 128), "qkv.bias": torch.zeros(384),
+                              "out_proj.weight": torch.zeros(128, 128), "out_proj.bias": torch.zeros(128)}, 308)
+    mod = P.rotaryencoderpcd.RotarySelfAttention(128, heads=2).to(DEV)
+    mod.load_state_dict(sd)
+    got = mod(det.normal((2, 70, 128), 309).to(DEV), coords.to(DEV))
+    assert rel(got, g["rotary_self_attn"]) < 1e-5, describe(got, g["rotary_self_attn"])
+    # q-side rotation alone: attention with V = identity-like probes is indirect; check the
+    # rotation itself through a 1-key problem where softmax == 1 and out == v
+    qkv = det.normal((1, 1, 384), 310)
+    out = ops.rotary_attention(qkv.to(DEV), coords[:1, :1].to(DEV), 2)
+    assert rel(out, qkv[..., 256:]) < 1e-6
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_perceiver_golden(dtype, tol):
+    from test_oracle_golden import perceiver_shapes
+    g = load_golden("ops")
+    sd = det.fill_state_dict(perceiver_shapes(128, 2, 192), 310)
+    per = P.perceiver.SimplePerceiver(device=DEV, dtype=dtype, n_data=77, width=128, layers=2, heads=2,
+                                      data_width=192)
+    per.load_state_dict(sd)
+    got = per(det.normal((2, 70, 128), 311).to(DEV), det.normal((2, 77, 192), 312).to(DEV))
+    assert rel(got, g["perceiver"]) < tol, describe(got, g["perceiver"], f"perceiver {dtype}")
+
+
+def test_chamfer_golden():
+    g = load_golden("ops")
+    got = ops.chamfer_distance_xyz(det.uniform((2, 6, 200), 313, 0.3).to(DEV), det.uniform((2, 3, 150), 314, 0.3).to(DEV))
+    assert rel(got, g["chamfer"]) < 1e-4, describe(got, g["chamfer"])
