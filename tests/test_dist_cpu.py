@@ -29,7 +29,7 @@ def _worker(rank, world, port, batch, q):
         return kw["embeddings"].sum(1)[:, None, None].expand(b, 3, 5).contiguous() + 0.0
 
     out = P.dist.sample_sharded(fake_sampler, batch, dict(embeddings=emb, flag="x"))
-    q.put((rank, out))
+    q.put((rank, out.numpy().copy()))
     dist.destroy_process_group()
 
 
@@ -47,4 +47,4 @@ def test_sharded_sampling_gloo(batch):
     [p.join(60) for p in procs]
     want = torch.arange(batch * 4, dtype=torch.float32).reshape(batch, 4).sum(1)[:, None, None].expand(batch, 3, 5)
     for r in range(world):
-        assert torch.equal(res[r], want)
+        assert torch.equal(torch.from_numpy(res[r]), want)
