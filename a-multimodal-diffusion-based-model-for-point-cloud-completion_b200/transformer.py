@@ -233,7 +233,7 @@ class PointDiffusionTransformer(nn.Module):
             pass
 
     # ---- execution ----
-    def _buffers(self, seqs: int):
+    def _get_buffers(self, seqs: int):
         dev = self.ln_pre.weight.device
         if seqs not in self._ws:
             nbytes = _lib.load().pcd_model_workspace_bytes(self._handle, seqs)
@@ -248,7 +248,7 @@ class PointDiffusionTransformer(nn.Module):
         assert x.dim() == 3 and x.shape[1] == self.input_channels and x.shape[2] == self.n_ctx, \
             f"expected x of shape [B, {self.input_channels}, {self.n_ctx}], got {tuple(x.shape)}"
         self._ensure_handle()
-        ws, prefix = self._buffers(seqs)
+        ws, prefix = self._get_buffers(seqs)
         add_cond = self.prepare_cond(seqs, kw)
         x = x.float().contiguous()
         t = t.to(torch.float32).contiguous()
@@ -266,7 +266,7 @@ class PointDiffusionTransformer(nn.Module):
         in the persistent prefix buffer.  Cached on tensor identity + version; the keyed
         tensors are kept alive so their addresses cannot be recycled under the cache."""
         self._ensure_handle()
-        _, prefix = self._buffers(seqs)
+        _, prefix = self._get_buffers(seqs)
         tensors = {k: v for k, v in kw.items() if torch.is_tensor(v)}
         ckey = tuple(sorted((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in tensors.items()))
         if self._cond_key.get(seqs) != ckey or len(tensors) != len(kw):
