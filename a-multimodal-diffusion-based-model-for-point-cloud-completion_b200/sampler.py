@@ -218,7 +218,8 @@ class PointCloudSampler:
                 stage = self._graphed_stage(idx, model, diffusion, sample_shape, stage_karras_steps,
                                             stage_sigma_min, stage_sigma_max, stage_s_churn,
                                             stage_guidance_scale)
-                preds = stage.run(stage_model_kwargs, self.noise_fn)
+                # fresh tensors like the reference (the stage buffers are overwritten by the next replay)
+                preds = stage.run(stage_model_kwargs, self.noise_fn).clone()
                 outs = [preds[i] for i in range(preds.shape[0])] + [preds[-1]]
             else:
                 outs = (o["pred_xstart"] for o in karras_sample_progressive(
