@@ -148,6 +148,14 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t s_tmem = tmem_base + lane_off + Cfg::S_COL;
     const uint32_t p_tmem = tmem_base + lane_off + Cfg::P_COL;
     const uint32_t o_tmem = tmem_base + lane_off + Cfg::O_COL;
+    if (q0 + quarter * 32 >= len_q) {
+      // every row of this warp is past the end of the sequence (ragged last query tile):
+      // skip the softmax work, only keep the hand-off barrier counts in step
+      for (int j = 0; j < num_kv; ++j) {
+        mbar_arrive(p_ready);
+        mbar_wait(p_ready, j & 1);
+      }
+    } else {
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     float o_acc[T_HD];
 #pragma unroll
@@ -156,6 +164,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < num_kv; ++j) {
       const int nvalid = min(T_BKV, len_kv - j * T_BKV);
       const int nchunks = (nvalid + 31) >> 5;
+      const bool ragged = (nvalid & 31) != 0;  // only the last KV tile can be ragged
       mbar_wait(s_full, j & 1);
       tcgen05_fence_after();
       // pass 1: row maximum
@@ -164,11 +173,13 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32b_x32(s_tmem + c * 32, r);
         tmem_ld_wait();
-        const int lim = nvalid - c * 32;
+        if (ragged && c == nchunks - 1) {
+          const int lim = nvalid - c * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]);
-          mx = fmaxf(mx, (i < lim) ? v : -INFINITY);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < lim) ? __uint_as_float(r[i]) : -INFINITY);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
       const float m_new = fmaxf(m_run, mx * scale_log2);
@@ -179,16 +190,29 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32b_x32(s_tmem + c * 32, r);
         tmem_ld_wait();
-        const int lim = nvalid - c * 32;
         uint32_t pk[16];
+        if (ragged && c == nchunks - 1) {
+          const int lim = nvalid - c * 32;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
-          float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
-          if (i >= lim) p0 = 0.f;
-          if (i + 1 >= lim) p1 = 0.f;
-          sum += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
+            float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
+            if (i >= lim) p0 = 0.f;
+            if (i + 1 >= lim) p1 = 0.f;
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        } else {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
+            float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
+            s0 += p0;
+            s1 += p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          sum += s0 + s1;
         }
         if (P_TMEM) {
           tmem_st_32x32b_x16(p_tmem + c * 16, pk);
@@ -247,6 +271,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
       }
+    }
     }
   }
 

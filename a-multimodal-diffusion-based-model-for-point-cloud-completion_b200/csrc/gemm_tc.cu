@@ -1,12 +1,14 @@
 // bf16 GEMM on the 5th-generation tensor cores:  C[M,N] = epi(A[M,K] W[N,K]^T + bias)
 //
-// Persistent, warp-specialised kernel (one CTA per SM, 192 threads):
+// Persistent, warp-specialised kernel (one CTA per SM, 320 threads):
 //   warp 0  : TMA producer   -- A (128 x 64) and W (BN x 64) bf16 tiles, 128B swizzle,
 //                               STAGES-deep mbarrier ring
 //   warp 1  : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16),
 //                               fp32 accumulators double-buffered in TMEM (2 x BN columns)
-//   warps 2-5: epilogue      -- tcgen05.ld 32x32b (thread = row), bias / exact-erf GELU /
-//                               fp32 residual, bf16 or fp32 stores straight from registers
+//   warps 2-9: epilogue      -- 8 warps: TMEM lane quarter = warp % 4, column half = (warp-2) / 4;
+//                               double-buffered tcgen05.ld 32x32b.x32 (thread = row), bias staged
+//                               in shared memory per tile, GELU / fp32 residual, 16-byte stores
+//                               straight from registers
 // Both operands are K-contiguous (activations [M,K], nn.Linear weights [N,K]) so no
 // transposes are needed.  Tails in M, N, K are handled by TMA zero fill + store predicates.
 #include "common.cuh"
@@ -17,6 +19,7 @@ namespace pcd {
 using namespace tc;
 
 constexpr int G_BM = 128, G_BK = 64;
+constexpr int G_THREADS = 320, G_EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -25,11 +28,12 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * G_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;          // 512 / 256 / 128: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;      // per accumulator stage
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
 };
 
 template <int BN, int EPI, bool OUT_BF16>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const float* __restrict__ bias, const float* residual, int ldr,
                     void* Cout, int ldc, int M, int N, int K) {
@@ -45,6 +49,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + G_BM - 1) / G_BM, num_n = (N + BN - 1) / BN;
@@ -60,7 +65,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[s], G_EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -124,45 +129,66 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // --------------------------- epilogue ----------------------------
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are accessible to this warp
+    const int ew = warp - 2;           // 0..7
+    const int quarter = warp & 3;      // TMEM lanes [32*quarter, +32) are accessible to this warp
+    const int half = ew >> 2;          // which half of the tile's columns this warp drains
+    constexpr int HALF_N = BN / 2;
+    constexpr int NCH = HALF_N / 32;   // 32-column chunks per thread (BN=64 -> one 32-col chunk)
+    static_assert(BN % 64 == 0, "BN must be a multiple of 64");
+    const int etid = threadIdx.x - 64;  // 0..255
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m_blk = t / num_n, n_blk = t % num_n;
       const int row = m_blk * G_BM + quarter * 32 + lane;
+      // stage this tile's bias slice in shared memory (double-buffered by accumulator stage)
+      float* sb = sbias + as * BN;
+      if (etid < BN) {
+        const int n = n_blk * BN + etid;
+        sb[etid] = (bias != nullptr && n < N) ? __ldg(bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[as], aphase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c0, r);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * HALF_N;
+      uint32_t rbuf[2][32];
+      tmem_ld_32x32b_x32(taddr, rbuf[0]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t* r = rbuf[c & 1];
+        const int ccol = half * HALF_N + c * 32;      // column inside the tile
+        const int col0 = n_blk * BN + ccol;           // global column
+        const bool active = row < M && col0 < N;
+        const bool full_cols = (col0 + 32 <= N);
+        float4 res[8];
+        if (EPI == PCD_EPI_BIAS_RESIDUAL && active && full_cols) {
+          // issue the residual loads before waiting on TMEM so both latencies overlap
+          const float4* rp = reinterpret_cast<const float4*>(residual + (size_t)row * ldr + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = rp[j];
+        }
         tmem_ld_wait();
-        const int col0 = n_blk * BN + c0;
-        if (row < M && col0 < N) {
+        if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);
+        if (active) {
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full_cols = (col0 + 32 <= N);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + ccol + j);
+            v[j] = __uint_as_float(r[j]) + b4.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          }
+          if (EPI == PCD_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          }
           if (full_cols) {
-            if (bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            }
-            if (EPI == PCD_EPI_BIAS_GELU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-            }
             if (EPI == PCD_EPI_BIAS_RESIDUAL) {
-              const float* rp = residual + (size_t)row * ldr + col0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 r4 = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+              for (int j = 0; j < 8; ++j) {
+                v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
               }
             }
             if (OUT_BF16) {
@@ -184,8 +210,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (col0 + j < N) {
-                float t2 = v[j] + (bias ? bias[col0 + j] : 0.f);
-                if (EPI == PCD_EPI_BIAS_GELU) t2 = gelu_erf(t2);
+                float t2 = v[j];
                 if (EPI == PCD_EPI_BIAS_RESIDUAL) t2 += residual[(size_t)row * ldr + col0 + j];
                 if (OUT_BF16)
                   reinterpret_cast<__nv_bfloat16*>(Cout)[(size_t)row * ldc + col0 + j] = __float2bfloat16_rn(t2);
@@ -227,7 +252,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const flo
   }
   int tiles = ceil_div(M, G_BM) * ceil_div(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmW, bias, residual, ldr, C, ldc, M, N, K);
+  kern<<<grid, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, bias, residual, ldr, C, ldc, M, N, K);
   PCD_CHECK_LAUNCH("gemm_bf16");
   return PCD_OK;
 }
