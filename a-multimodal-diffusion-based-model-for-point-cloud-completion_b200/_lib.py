@@ -50,11 +50,14 @@ _SIGS = {
     "pcd_launch_count": (C.c_ulonglong, []),
     "pcd_check_device": (C.c_int, []),
     "pcd_set_attention_variant": (C.c_int, [C.c_int]),
+    "pcd_set_debug_flags": (C.c_int, [C.c_int]),
     "pcd_timestep_embed": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "pcd_layernorm": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "pcd_embed_tokens": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
                                    C.c_float, vp, C.c_int, C.c_int, vp]),
-    "pcd_output_proj": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, vp, vp,
+    "pcd_add_layernorm": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_float, vp]),
+    "pcd_output_proj": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, vp, vp,
                                   C.c_int, vp, vp]),
     "pcd_gemm_f32": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, vp]),

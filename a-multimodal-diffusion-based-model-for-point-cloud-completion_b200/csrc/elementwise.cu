@@ -51,8 +51,35 @@ __device__ __forceinline__ void row_stats(const RowRegs<MAXV>& r, int dim, int l
   rstd = rsqrtf(warp_sum(q) / (float)dim + eps);
 }
 
+// Adds y (bf16 or fp32, the previous GEMM's output) to the row held in registers.
+template <int MAXV>
+__device__ __forceinline__ void add_rows(RowRegs<MAXV>& r, const void* y, int y_bf16, size_t row_off,
+                                         int dim, int lane) {
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int c = (i * 32 + lane) * 4;
+    if (c < dim) {
+      if (y_bf16) {
+        uint2 p = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(y) + row_off + c);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&p.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&p.y);
+        float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+        r.v[i].x += fa.x; r.v[i].y += fa.y; r.v[i].z += fb.x; r.v[i].w += fb.y;
+      } else {
+        float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(y) + row_off + c);
+        r.v[i].x += t.x; r.v[i].y += t.y; r.v[i].z += t.z; r.v[i].w += t.w;
+      }
+    }
+  }
+}
+
+// out = LayerNorm(x) -- or, with y != nullptr, the fused residual update of the block
+//   x <- x + y ; out = LayerNorm(x)                     (reference transformer.py:113-114)
+// where y is the output of the preceding c_proj GEMM.  One pass: 4+2 B read, 4+2 B written
+// per element in bf16 mode.
 template <int MAXV, bool OUT_BF16>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, int ldx,
+                                                        const void* __restrict__ y, int ldy, int y_bf16,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
                                                         void* __restrict__ out, int ldo, int rows,
@@ -60,12 +87,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= rows) return;
-  const float* xr = x + (size_t)warp * ldx;
+  float* xr = x + (size_t)warp * ldx;
   RowRegs<MAXV> r;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     int c = (i * 32 + lane) * 4;
     if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(xr + c);
+  }
+  if (y != nullptr) {
+    add_rows<MAXV>(r, y, y_bf16, (size_t)warp * ldy, dim, lane);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if (c < dim) *reinterpret_cast<float4*>(xr + c) = r.v[i];
+    }
   }
   float mean, rstd;
   row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
@@ -75,16 +110,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (c < dim) {
       float4 g = *reinterpret_cast<const float4*>(gamma + c);
       float4 b = *reinterpret_cast<const float4*>(beta + c);
-      float4 y;
-      y.x = (r.v[i].x - mean) * rstd * g.x + b.x;
-      y.y = (r.v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (r.v[i].z - mean) * rstd * g.z + b.z;
-      y.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+      float4 o;
+      o.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (r.v[i].w - mean) * rstd * g.w + b.w;
       if (OUT_BF16) {
-        uint2 p = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        uint2 p = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + (size_t)warp * ldo + c) = p;
       } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)warp * ldo + c) = y;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)warp * ldo + c) = o;
       }
     }
   }
@@ -167,8 +202,8 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
 // ---------------------------------------------------------------------------
 template <int MAXV>
 __global__ void __launch_bounds__(256) output_proj_kernel(
-    const float* __restrict__ h, int seqs, int n_prefix, int n_points, int dim,
-    const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+    const float* __restrict__ h, const void* __restrict__ y, int y_bf16, int seqs, int n_prefix,
+    int n_points, int dim, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
     const float* __restrict__ w_out, const float* __restrict__ b_out, int c_out,
     float* __restrict__ out) {
   // block = 8 warps = 8 consecutive point tokens of one sequence
@@ -187,6 +222,8 @@ __global__ void __launch_bounds__(256) output_proj_kernel(
       int c = (i * 32 + lane) * 4;
       if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(hr + c);
     }
+    // last block's MLP output (residual add folded in; h itself is not needed afterwards)
+    if (y != nullptr) add_rows<MAXV>(r, y, y_bf16, ((size_t)s * L + n_prefix + n) * dim, dim, lane);
     float mean, rstd;
     row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
 #pragma unroll
@@ -250,20 +287,36 @@ extern "C" int pcd_timestep_embed(const float* t, const float* freqs, int batch,
   return PCD_OK;
 }
 
+static int launch_layernorm(float* x, int ldx, const void* y, int ldy, int y_precision, const float* gamma,
+                            const float* beta, void* out, int ld_out, int out_precision, int rows, int dim,
+                            float eps, void* stream, const char* what) {
+  PCD_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 2048, "%s: dim must be a multiple of 4 and <= 2048 (got %d)", what, dim);
+  PCD_CHECK_ARG(ldx % 4 == 0 && ld_out % 4 == 0 && ldy % 4 == 0, "%s: leading dims must be multiples of 4", what);
+  dim3 grid(ceil_div(rows, 8)), block(256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int yb = y_precision == PCD_BF16;
+  if (out_precision == PCD_BF16) {
+    DISPATCH_MAXV(dim, (layernorm_kernel<MAXV, true><<<grid, block, 0, st>>>(x, ldx, y, ldy, yb, gamma, beta, out, ld_out, rows, dim, eps)));
+  } else {
+    DISPATCH_MAXV(dim, (layernorm_kernel<MAXV, false><<<grid, block, 0, st>>>(x, ldx, y, ldy, yb, gamma, beta, out, ld_out, rows, dim, eps)));
+  }
+  PCD_CHECK_LAUNCH(what);
+  return PCD_OK;
+}
+
 extern "C" int pcd_layernorm(const float* x, int ldx, const float* gamma, const float* beta,
                              void* out, int ld_out, int out_precision, int rows, int dim, float eps,
                              void* stream) {
-  PCD_CHECK_ARG(rows > 0 && dim > 0 && dim % 4 == 0 && dim <= 2048, "layernorm: dim must be a multiple of 4 and <= 2048 (got %d)", dim);
-  PCD_CHECK_ARG(ldx % 4 == 0 && ld_out % 4 == 0, "layernorm: leading dims must be multiples of 4");
-  dim3 grid(ceil_div(rows, 8)), block(256);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (out_precision == PCD_BF16) {
-    DISPATCH_MAXV(dim, (layernorm_kernel<MAXV, true><<<grid, block, 0, st>>>(x, ldx, gamma, beta, out, ld_out, rows, dim, eps)));
-  } else {
-    DISPATCH_MAXV(dim, (layernorm_kernel<MAXV, false><<<grid, block, 0, st>>>(x, ldx, gamma, beta, out, ld_out, rows, dim, eps)));
-  }
-  PCD_CHECK_LAUNCH("layernorm");
-  return PCD_OK;
+  return launch_layernorm(const_cast<float*>(x), ldx, nullptr, 0, PCD_F32, gamma, beta, out, ld_out, out_precision,
+                          rows, dim, eps, stream, "layernorm");
+}
+
+extern "C" int pcd_add_layernorm(float* h, int ldh, const void* y, int ldy, int y_precision,
+                                 const float* gamma, const float* beta, void* out, int ld_out,
+                                 int out_precision, int rows, int dim, float eps, void* stream) {
+  PCD_CHECK_ARG(y != nullptr, "add_layernorm: y missing");
+  return launch_layernorm(h, ldh, y, ldy, y_precision, gamma, beta, out, ld_out, out_precision, rows, dim, eps,
+                          stream, "add_layernorm");
 }
 
 extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_points,
@@ -283,15 +336,15 @@ extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_poin
   return PCD_OK;
 }
 
-extern "C" int pcd_output_proj(const float* h, int seqs, int n_prefix, int n_points, int dim,
-                               const float* ln_g, const float* ln_b, float eps,
+extern "C" int pcd_output_proj(const float* h, const void* y, int y_precision, int seqs, int n_prefix,
+                               int n_points, int dim, const float* ln_g, const float* ln_b, float eps,
                                const float* w_out, const float* b_out, int c_out, float* out,
                                void* stream) {
   PCD_CHECK_ARG(seqs > 0 && n_points > 0 && dim % 4 == 0 && dim <= 2048, "output_proj: bad shape");
   PCD_CHECK_ARG(c_out >= 1 && c_out <= 32, "output_proj: c_out must be in [1,32] (got %d)", c_out);
   dim3 grid(seqs * ceil_div(n_points, 8)), block(256);
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_MAXV(dim, (output_proj_kernel<MAXV><<<grid, block, 0, st>>>(h, seqs, n_prefix, n_points, dim, ln_g, ln_b, eps, w_out, b_out, c_out, out)));
+  DISPATCH_MAXV(dim, (output_proj_kernel<MAXV><<<grid, block, 0, st>>>(h, y, y_precision == PCD_BF16, seqs, n_prefix, n_points, dim, ln_g, ln_b, eps, w_out, b_out, c_out, out)));
   PCD_CHECK_LAUNCH("output_proj");
   return PCD_OK;
 }

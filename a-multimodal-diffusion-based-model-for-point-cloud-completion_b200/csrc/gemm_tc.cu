@@ -1,16 +1,22 @@
 // bf16 GEMM on the 5th-generation tensor cores:  C[M,N] = epi(A[M,K] W[N,K]^T + bias)
 //
 // Persistent, warp-specialised kernel (one CTA per SM, 320 threads):
-//   warp 0  : TMA producer   -- A (128 x 64) and W (BN x 64) bf16 tiles, 128B swizzle,
-//                               STAGES-deep mbarrier ring
-//   warp 1  : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16),
-//                               fp32 accumulators double-buffered in TMEM (2 x BN columns)
-//   warps 2-9: epilogue      -- 8 warps: TMEM lane quarter = warp % 4, column half = (warp-2) / 4;
-//                               double-buffered tcgen05.ld 32x32b.x32 (thread = row), bias staged
-//                               in shared memory per tile, GELU / fp32 residual, 16-byte stores
-//                               straight from registers
+//   warp 0   : TMA producer -- A (128 x 64) and W (BN x 64) bf16 tiles, 128B swizzle,
+//              STAGES-deep mbarrier ring
+//   warp 1   : MMA issuer   -- one elected lane issues tcgen05.mma (M=128, N=BN, K=16),
+//              fp32 accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 2-9: epilogue     -- TMEM lane quarter = warp % 4, column half = (warp-2) / 4.
+//              Double-buffered tcgen05.ld 32x32b.x32 (thread = output row), bias from a
+//              per-tile shared-memory slice, GELU / fp32 residual, then the 32-row x 128-byte
+//              chunk is staged in 128B-swizzled shared memory and written with ONE TMA store
+//              (full 128-byte lines; M/N tails are clipped by the tensor map).  A residual
+//              chunk, when requested, is TMA-loaded into the same buffer and updated in place.
+// Measured with tools/gemm_probe.py: the MMA loop alone sustains ~1.7 PFLOP/s and the
+// TMA-fed main loop ~1.4 PFLOP/s; register->global stores from the row-per-thread TMEM layout
+// (32 distinct 128-byte lines per warp instruction) were the bottleneck of the first version,
+// hence the staged TMA-store epilogue.
 // Both operands are K-contiguous (activations [M,K], nn.Linear weights [N,K]) so no
-// transposes are needed.  Tails in M, N, K are handled by TMA zero fill + store predicates.
+// transposes are needed.  Tails in M, N, K are handled by TMA zero fill / clipping.
 #include "common.cuh"
 #include "tc_sm100.cuh"
 
@@ -20,36 +26,46 @@ using namespace tc;
 
 constexpr int G_BM = 128, G_BK = 64;
 constexpr int G_THREADS = 320, G_EPI_WARPS = 8;
+constexpr int G_STAGE_TILE = 32 * 128;  // epilogue staging tile: 32 rows x 128 bytes
 
-template <int BN>
+template <int BN, int EPI>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int NBUF = 1;  // staging tiles per epilogue warp
   static constexpr int A_BYTES = G_BM * G_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * G_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;          // 512 / 256 / 128: powers of two
-  static constexpr int BIAS_BYTES = 2 * BN * 4;      // per accumulator stage
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
+  static constexpr int OUT_BYTES = G_EPI_WARPS * NBUF * G_STAGE_TILE;
+  static constexpr int MISC_BYTES = 512 + 2 * BN * 4;  // barriers + bias slices
+  static constexpr int BUDGET = 232448 - OUT_BYTES - MISC_BYTES;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN;          // 512 / 256: powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + MISC_BYTES;
+  static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
 template <int BN, int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                    const float* __restrict__ bias, const float* residual, int ldr,
-                    void* Cout, int ldc, int M, int N, int K) {
-  using Cfg = GemmCfg<BN>;
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                    const float* __restrict__ bias, int M, int N, int K, int dbg) {
+  using Cfg = GemmCfg<BN, EPI>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ unsigned char smem_raw[];
-  // 1024-byte alignment is required by the 128B swizzle atom (8 rows x 128 B)
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NBUF = Cfg::NBUF;
+  // 1024-byte alignment is required by the 128B swizzle atom (8 rows x 128 B); the dynamic
+  // shared window starts at offset 0 of the CTA (no static __shared__ in this kernel)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   unsigned char* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  unsigned char* stage_out = smem + STAGES * Cfg::STAGE_BYTES;             // [8 warps][NBUF][4 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::OUT_BYTES);
   uint64_t* full = bars;                    // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + STAGES;          // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;   // [2]       MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;       // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* sbias = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // [2][BN]
+  uint64_t* res_bar = acc_empty + 2;        // [8 warps][2] residual chunk landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * G_EPI_WARPS);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);  // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + G_BM - 1) / G_BM, num_n = (N + BN - 1) / BN;
@@ -59,6 +75,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmW);
+    prefetch_tensormap(&tmC);
+    if (EPI == PCD_EPI_BIAS_RESIDUAL) prefetch_tensormap(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -67,6 +85,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], G_EPI_WARPS);  // one arrival per epilogue warp
     }
+    for (int s = 0; s < 2 * G_EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -89,9 +108,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = tiles + stage * Cfg::STAGE_BYTES;
           unsigned char* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full[stage], kb * G_BK, m_blk * G_BM);
-          tma_load_2d(sb, &tmW, &full[stage], kb * G_BK, n_blk * BN);
+          if (dbg & 2) {  // profiling aid: no TMA traffic, the MMAs run on stale shared memory
+            mbar_arrive(&full[stage]);
+          } else {
+            mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full[stage], kb * G_BK, m_blk * G_BM);
+            tma_load_2d(sb, &tmW, &full[stage], kb * G_BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -133,15 +156,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quarter = warp & 3;      // TMEM lanes [32*quarter, +32) are accessible to this warp
     const int half = ew >> 2;          // which half of the tile's columns this warp drains
     constexpr int HALF_N = BN / 2;
-    constexpr int NCH = HALF_N / 32;   // 32-column chunks per thread (BN=64 -> one 32-col chunk)
-    static_assert(BN % 64 == 0, "BN must be a multiple of 64");
+    constexpr int NCH = HALF_N / 32;   // 32-column TMEM chunks per thread
+    // one staged store covers 128 bytes per row: 64 bf16 columns (2 chunks) or 32 fp32 columns
+    constexpr int CH_PER_STORE = OUT_BF16 ? 2 : 1;
+    static_assert(BN % 128 == 0, "BN must be a multiple of 128");
+    static_assert(!(EPI == PCD_EPI_BIAS_RESIDUAL && OUT_BF16), "the residual stream is fp32");
     const int etid = threadIdx.x - 64;  // 0..255
+    unsigned char* my_buf = stage_out + ew * NBUF * G_STAGE_TILE;
+    uint64_t* my_res_bar = res_bar + 2 * ew;
+    const int sw = lane & 7;            // 128B swizzle: 16-byte piece index ^= (row & 7)
+    unsigned char* my_row0 = my_buf + lane * 128;
+    uint32_t res_uses[2] = {0, 0};      // per-buffer residual-load counters (mbarrier parity)
+    int sidx = 0;                       // running store-group index of this warp
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m_blk = t / num_n, n_blk = t % num_n;
-      const int row = m_blk * G_BM + quarter * 32 + lane;
+      const int row0 = m_blk * G_BM + quarter * 32;       // first row of this warp
+      const int colbase = n_blk * BN + half * HALF_N;     // first column of this warp
       // stage this tile's bias slice in shared memory (double-buffered by accumulator stage)
       float* sb = sbias + as * BN;
       if (etid < BN) {
@@ -151,80 +184,91 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[as], aphase);
       tcgen05_fence_after();
+      if (dbg & 1) {  // profiling aid: drain nothing, release the accumulator immediately
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        continue;
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * HALF_N;
       uint32_t rbuf[2][32];
       tmem_ld_32x32b_x32(taddr, rbuf[0]);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         uint32_t* r = rbuf[c & 1];
-        const int ccol = half * HALF_N + c * 32;      // column inside the tile
-        const int col0 = n_blk * BN + ccol;           // global column
-        const bool active = row < M && col0 < N;
-        const bool full_cols = (col0 + 32 <= N);
-        float4 res[8];
-        if (EPI == PCD_EPI_BIAS_RESIDUAL && active && full_cols) {
-          // issue the residual loads before waiting on TMEM so both latencies overlap
-          const float4* rp = reinterpret_cast<const float4*>(residual + (size_t)row * ldr + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res[j] = rp[j];
+        const int b = sidx % NBUF;
+        unsigned char* buf_row = my_row0 + b * G_STAGE_TILE;
+        const bool first_of_store = (c % CH_PER_STORE) == 0;
+        const bool last_of_store = (c % CH_PER_STORE) == CH_PER_STORE - 1;
+        if (first_of_store) {
+          if (lane == 0) {
+            tma_store_wait_read<0>();  // staging buffer free again
+            if (EPI == PCD_EPI_BIAS_RESIDUAL) {
+              // residual chunk -> staging buffer (updated in place below).  Not prefetched: the
+              // hot path adds residuals in the fused add+LayerNorm kernel instead (elementwise.cu).
+              mbar_expect_tx(&my_res_bar[0], G_STAGE_TILE);
+              tma_load_2d(my_buf, &tmR, &my_res_bar[0], colbase + c * 32, row0);
+            }
+          }
+          __syncwarp();
+          if (EPI == PCD_EPI_BIAS_RESIDUAL) {
+            mbar_wait(&my_res_bar[0], res_uses[0] & 1);
+            res_uses[0]++;
+          }
         }
         tmem_ld_wait();
         if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);
-        if (active) {
-          float v[32];
+        const float* sbc = sb + half * HALF_N + c * 32;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + ccol + j);
-            v[j] = __uint_as_float(r[j]) + b4.x;
-            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-          }
-          if (EPI == PCD_EPI_BIAS_GELU) {
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbc + j);
+          v[j] = __uint_as_float(r[j]) + b4.x;
+          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+        }
+        if (EPI == PCD_EPI_BIAS_GELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+        }
+        if (OUT_BF16) {
+          // 32 columns = 64 bytes = pieces [4*(c&1), +4) of the 128-byte staging row
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int piece = ((c % CH_PER_STORE) * 4 + i) ^ sw;
+            *reinterpret_cast<uint4*>(buf_row + piece * 16) =
+                make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                           pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
-          if (full_cols) {
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4* pp = reinterpret_cast<float4*>(buf_row + ((i ^ sw) * 16));
+            float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             if (EPI == PCD_EPI_BIAS_RESIDUAL) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
-              }
+              const float4 rr = *pp;  // residual chunk landed here by TMA; update in place
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
             }
-            if (OUT_BF16) {
-              uint16_t* cp = reinterpret_cast<uint16_t*>(Cout) + (size_t)row * ldc + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 p = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                     pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-                *reinterpret_cast<uint4*>(cp + j) = p;
-              }
-            } else {
-              float* cp = reinterpret_cast<float*>(Cout) + (size_t)row * ldc + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          } else {
-            // ragged N tail: predicated scalar path (fully unrolled: registers only)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < N) {
-                float t2 = v[j];
-                if (EPI == PCD_EPI_BIAS_RESIDUAL) t2 += residual[(size_t)row * ldr + col0 + j];
-                if (OUT_BF16)
-                  reinterpret_cast<__nv_bfloat16*>(Cout)[(size_t)row * ldc + col0 + j] = __float2bfloat16_rn(t2);
-                else
-                  reinterpret_cast<float*>(Cout)[(size_t)row * ldc + col0 + j] = t2;
-              }
-            }
+            *pp = o;
           }
+        }
+        if (last_of_store) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int col = colbase + (c / CH_PER_STORE) * (OUT_BF16 ? 64 : 32);
+            tma_store_2d(&tmC, my_buf + b * G_STAGE_TILE, col, row0);
+            tma_store_commit();
+          }
+          ++sidx;
         }
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    if (lane == 0) tma_store_wait_all<0>();  // all output tiles are globally visible
   }
 
   tcgen05_fence_before();
@@ -235,11 +279,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+int g_gemm_debug = 0;  // profiling aid, see pcd_set_debug_flags
+
 template <int BN, int EPI, bool OUT_BF16>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const float* bias,
-                       const float* residual, int ldr, void* C, int ldc, int M, int N, int K,
-                       cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC,
+                       const CUtensorMap& tmR, const float* bias, int M, int N, int K, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI>;
   auto kern = gemm_bf16_tc_kernel<BN, EPI, OUT_BF16>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -252,26 +297,27 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const flo
   }
   int tiles = ceil_div(M, G_BM) * ceil_div(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, bias, residual, ldr, C, ldc, M, N, K);
+  kern<<<grid, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, bias, M, N, K, g_gemm_debug);
   PCD_CHECK_LAUNCH("gemm_bf16");
   return PCD_OK;
 }
 
 template <int BN>
-static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& w, const float* bias,
-                        const float* residual, int ldr, void* C, int ldc, int out_prec, int M, int N,
-                        int K, int epi, cudaStream_t st) {
-#define PCD_GEMM_CASE(E)                                                                          \
-  case E:                                                                                         \
-    return out_prec == PCD_BF16 ? launch_gemm<BN, E, true>(a, w, bias, residual, ldr, C, ldc, M, N, K, st) \
-                                : launch_gemm<BN, E, false>(a, w, bias, residual, ldr, C, ldc, M, N, K, st);
+static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& c, const CUtensorMap& r,
+                        const float* bias, int out_prec, int M, int N, int K, int epi, cudaStream_t st) {
+  const bool ob = out_prec == PCD_BF16;
   switch (epi) {
-    PCD_GEMM_CASE(PCD_EPI_BIAS)
-    PCD_GEMM_CASE(PCD_EPI_BIAS_GELU)
-    PCD_GEMM_CASE(PCD_EPI_BIAS_RESIDUAL)
+    case PCD_EPI_BIAS:
+      return ob ? launch_gemm<BN, PCD_EPI_BIAS, true>(a, w, c, r, bias, M, N, K, st)
+                : launch_gemm<BN, PCD_EPI_BIAS, false>(a, w, c, r, bias, M, N, K, st);
+    case PCD_EPI_BIAS_GELU:
+      return ob ? launch_gemm<BN, PCD_EPI_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st)
+                : launch_gemm<BN, PCD_EPI_BIAS_GELU, false>(a, w, c, r, bias, M, N, K, st);
+    case PCD_EPI_BIAS_RESIDUAL:
+      if (ob) break;
+      return launch_gemm<BN, PCD_EPI_BIAS_RESIDUAL, false>(a, w, c, r, bias, M, N, K, st);
   }
-#undef PCD_GEMM_CASE
-  set_error("gemm_bf16: unknown epilogue %d", epi);
+  set_error("gemm_bf16: unsupported epilogue %d / output precision %d", epi, out_prec);
   return PCD_ERR_INVALID;
 }
 
@@ -285,20 +331,37 @@ extern "C" int pcd_gemm_bf16(const uint16_t* A, int lda, const uint16_t* W, int 
   PCD_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem");
   PCD_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: K, lda, ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", K, lda, ldw);
   PCD_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm_bf16: operands must be 16-byte aligned");
-  PCD_CHECK_ARG(ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_bf16: C must be 16-byte aligned with ldc %% 8 == 0");
-  PCD_CHECK_ARG(epilogue != PCD_EPI_BIAS_RESIDUAL || (residual != nullptr && ldr % 4 == 0), "gemm_bf16: residual missing or misaligned");
-  const int BN = (N % 256 == 0 || N > 1024) ? 256 : (N > 64 ? 128 : 64);
-  CUtensorMap tmA, tmW;
+  const bool ob = out_precision == PCD_BF16;
+  PCD_CHECK_ARG(out_precision == PCD_BF16 || out_precision == PCD_F32, "gemm_bf16: bad output precision");
+  PCD_CHECK_ARG(ldc % (ob ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_bf16: C must be 16-byte aligned with a 16-byte row pitch (ldc=%d)", ldc);
+  PCD_CHECK_ARG(epilogue != PCD_EPI_BIAS_RESIDUAL || (residual != nullptr && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && !ob),
+                "gemm_bf16: residual epilogue needs an fp32, 16-byte aligned residual and fp32 output");
+  const int BN = (N % 256 == 0 || N > 1024) ? 256 : 128;
+  CUtensorMap tmA, tmW, tmC, tmR;
   uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[1] = {(uint64_t)lda * 2};
   uint32_t boxA[2] = {G_BK, G_BM};
   uint64_t dimsW[2] = {(uint64_t)K, (uint64_t)N}, strW[1] = {(uint64_t)ldw * 2};
   uint32_t boxW[2] = {G_BK, (uint32_t)BN};
-  int rc = encode_tmap_bf16(&tmA, A, 2, dimsA, strA, boxA);
-  if (rc != PCD_OK) return rc;
-  rc = encode_tmap_bf16(&tmW, W, 2, dimsW, strW, boxW);
-  if (rc != PCD_OK) return rc;
+  uint64_t dimsC[2] = {(uint64_t)N, (uint64_t)M};
+  int rc;
+  if ((rc = encode_tmap_bf16(&tmA, A, 2, dimsA, strA, boxA)) != PCD_OK) return rc;
+  if ((rc = encode_tmap_bf16(&tmW, W, 2, dimsW, strW, boxW)) != PCD_OK) return rc;
+  if (ob) {
+    uint64_t strC[1] = {(uint64_t)ldc * 2};
+    uint32_t boxC[2] = {64, 32};
+    if ((rc = encode_tmap_bf16(&tmC, C, 2, dimsC, strC, boxC)) != PCD_OK) return rc;
+  } else {
+    uint64_t strC[1] = {(uint64_t)ldc * 4};
+    uint32_t boxC[2] = {32, 32};
+    if ((rc = encode_tmap_f32(&tmC, C, 2, dimsC, strC, boxC)) != PCD_OK) return rc;
+  }
+  tmR = tmC;
+  if (epilogue == PCD_EPI_BIAS_RESIDUAL) {
+    uint64_t strR[1] = {(uint64_t)ldr * 4};
+    uint32_t boxR[2] = {32, 32};
+    if ((rc = encode_tmap_f32(&tmR, residual, 2, dimsC, strR, boxR)) != PCD_OK) return rc;
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 256) return dispatch_epi<256>(tmA, tmW, bias, residual, ldr, C, ldc, out_precision, M, N, K, epilogue, st);
-  if (BN == 128) return dispatch_epi<128>(tmA, tmW, bias, residual, ldr, C, ldc, out_precision, M, N, K, epilogue, st);
-  return dispatch_epi<64>(tmA, tmW, bias, residual, ldr, C, ldc, out_precision, M, N, K, epilogue, st);
+  if (BN == 256) return dispatch_epi<256>(tmA, tmW, tmC, tmR, bias, out_precision, M, N, K, epilogue, st);
+  return dispatch_epi<128>(tmA, tmW, tmC, tmR, bias, out_precision, M, N, K, epilogue, st);
 }

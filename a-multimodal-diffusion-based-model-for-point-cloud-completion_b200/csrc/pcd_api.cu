@@ -50,8 +50,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank,
+                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+int encode_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
+}
+
+static int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank,
+                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return PCD_ERR_CUDA;
   cuuint64_t gdim[5], gstr[4];
@@ -62,7 +74,7 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
     estr[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
                   bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -80,6 +92,7 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
                           uint16_t* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
                           int len_kv, float q_scale, float k_scale, cudaStream_t st);
 extern int g_attn_variant;
+extern int g_gemm_debug;
 
 }  // namespace pcd
 
@@ -108,6 +121,13 @@ extern "C" int pcd_check_device(void) {
 
 // Tuning/testing knob (not part of the reference-facing surface): 1 = P kept in TMEM
 // (tcgen05.mma A-from-TMEM, 2 CTAs/SM), 0 = P staged in swizzled shared memory.
+// Profiling aid (results are WRONG when set): bit 0 = GEMM epilogue skipped, bit 1 = GEMM TMA
+// loads skipped.  Used by tools/ to separate main-loop from epilogue time.
+extern "C" int pcd_set_debug_flags(int flags) {
+  g_gemm_debug = flags;
+  return PCD_OK;
+}
+
 extern "C" int pcd_set_attention_variant(int v) {
   PCD_CHECK_ARG(v == 0 || v == 1, "attention variant must be 0 or 1");
   g_attn_variant = v;
@@ -157,7 +177,7 @@ struct pcd_model {
 namespace {
 struct Workspace {
   float *temb, *thid, *tcond, *h;
-  void *xn, *qkv, *att, *hid;
+  void *xn, *qkv, *att, *hid, *y;
   size_t total;
 };
 
@@ -181,6 +201,7 @@ Workspace carve(const pcd_model_desc& d, int seqs, unsigned char* base) {
   w.qkv = take(M * d.width * 3 * es);
   w.att = take(M * d.width * es);
   w.hid = take(M * d.width * 4 * es);
+  w.y = take(M * d.width * es);
   w.total = off;
   return w;
 }
@@ -254,37 +275,34 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
 
   const float qk_scale = 1.0f / sqrtf(sqrtf(64.0f));  // hd^-1/4 on q and on k (transformer.py:76)
   const int prec = d.precision;
+  const size_t es = bf ? 2 : 4;
+  // The two residual adds of every block (x = x + attn(..), x = x + mlp(..), transformer.py:113-114)
+  // are folded into the LayerNorm that follows them: the c_proj GEMMs write y = A W^T + b and the
+  // next LayerNorm kernel does h += y before normalising (one HBM pass, plain GEMM epilogues).
+  auto gemm = [&](const void* A, int lda, const void* Wt, const float* bias, void* C, int N, int K, int epi) -> int {
+    if (bf)
+      return pcd_gemm_bf16((const uint16_t*)A, lda, (const uint16_t*)Wt, K, bias, nullptr, 0, C, N, PCD_BF16, M, N, K, epi, stream);
+    return pcd_gemm_f32((const float*)A, lda, (const float*)Wt, K, bias, nullptr, 0, (float*)C, N, M, N, K, epi, stream);
+  };
   for (int l = 0; l < d.layers; ++l) {
     const pcd_block_weights& b = m->blocks[l];
-    // x = x + c_proj(attn(c_qkv(ln_1(x))))           transformer.py:113
-    PCD_TRY(pcd_layernorm(w.h, W, b.ln1_g, b.ln1_b, w.xn, W, prec, M, W, d.ln_eps, stream));
-    if (bf) {
-      PCD_TRY(pcd_gemm_bf16((const uint16_t*)w.xn, W, (const uint16_t*)b.w_qkv, W, b.b_qkv, nullptr, 0, w.qkv, 3 * W, PCD_BF16, M, 3 * W, W, PCD_EPI_BIAS, stream));
-    } else {
-      PCD_TRY(pcd_gemm_f32((const float*)w.xn, W, (const float*)b.w_qkv, W, b.b_qkv, nullptr, 0, (float*)w.qkv, 3 * W, M, 3 * W, W, PCD_EPI_BIAS, stream));
+    if (l == 0) {
+      PCD_TRY(pcd_layernorm(w.h, W, b.ln1_g, b.ln1_b, w.xn, W, prec, M, W, d.ln_eps, stream));
+    } else {  // pending MLP output of the previous block
+      PCD_TRY(pcd_add_layernorm(w.h, W, w.y, W, prec, b.ln1_g, b.ln1_b, w.xn, W, prec, M, W, d.ln_eps, stream));
     }
-    const size_t es = bf ? 2 : 4;
+    PCD_TRY(gemm(w.xn, W, b.w_qkv, b.b_qkv, w.qkv, 3 * W, W, PCD_EPI_BIAS));
     pcd_attn_operand q = {w.qkv, (int64_t)L * 3 * W, 3 * W, 3 * 64};
     pcd_attn_operand k = {(const unsigned char*)w.qkv + 64 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
     pcd_attn_operand v = {(const unsigned char*)w.qkv + 128 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
     PCD_TRY(pcd_attention(&q, &k, &v, w.att, (int64_t)L * W, W, seqs, d.heads, L, L, qk_scale, qk_scale, nullptr, prec, stream));
-    if (bf) {
-      PCD_TRY(pcd_gemm_bf16((const uint16_t*)w.att, W, (const uint16_t*)b.w_proj, W, b.b_proj, w.h, W, w.h, W, PCD_F32, M, W, W, PCD_EPI_BIAS_RESIDUAL, stream));
-    } else {
-      PCD_TRY(pcd_gemm_f32((const float*)w.att, W, (const float*)b.w_proj, W, b.b_proj, w.h, W, w.h, W, M, W, W, PCD_EPI_BIAS_RESIDUAL, stream));
-    }
-    // x = x + c_proj(gelu(c_fc(ln_2(x))))             transformer.py:114
-    PCD_TRY(pcd_layernorm(w.h, W, b.ln2_g, b.ln2_b, w.xn, W, prec, M, W, d.ln_eps, stream));
-    if (bf) {
-      PCD_TRY(pcd_gemm_bf16((const uint16_t*)w.xn, W, (const uint16_t*)b.w_fc, W, b.b_fc, nullptr, 0, w.hid, 4 * W, PCD_BF16, M, 4 * W, W, PCD_EPI_BIAS_GELU, stream));
-      PCD_TRY(pcd_gemm_bf16((const uint16_t*)w.hid, 4 * W, (const uint16_t*)b.w_fc2, 4 * W, b.b_fc2, w.h, W, w.h, W, PCD_F32, M, W, 4 * W, PCD_EPI_BIAS_RESIDUAL, stream));
-    } else {
-      PCD_TRY(pcd_gemm_f32((const float*)w.xn, W, (const float*)b.w_fc, W, b.b_fc, nullptr, 0, (float*)w.hid, 4 * W, M, 4 * W, W, PCD_EPI_BIAS_GELU, stream));
-      PCD_TRY(pcd_gemm_f32((const float*)w.hid, 4 * W, (const float*)b.w_fc2, 4 * W, b.b_fc2, w.h, W, w.h, W, M, W, 4 * W, PCD_EPI_BIAS_RESIDUAL, stream));
-    }
+    PCD_TRY(gemm(w.att, W, b.w_proj, b.b_proj, w.y, W, W, PCD_EPI_BIAS));
+    PCD_TRY(pcd_add_layernorm(w.h, W, w.y, W, prec, b.ln2_g, b.ln2_b, w.xn, W, prec, M, W, d.ln_eps, stream));
+    PCD_TRY(gemm(w.xn, W, b.w_fc, b.b_fc, w.hid, 4 * W, W, PCD_EPI_BIAS_GELU));
+    PCD_TRY(gemm(w.hid, 4 * W, b.w_fc2, b.b_fc2, w.y, W, 4 * W, PCD_EPI_BIAS));
   }
-  // ln_post + slice + output_proj + permute (transformer.py:222-226)
-  PCD_TRY(pcd_output_proj(w.h, seqs, d.n_prefix, d.n_points, W, d.ln_post_g, d.ln_post_b, d.ln_eps, d.out_w, d.out_b,
-                          out_channels, out, stream));
+  // (+ last MLP output) + ln_post + slice + output_proj + permute (transformer.py:222-226)
+  PCD_TRY(pcd_output_proj(w.h, w.y, prec, seqs, d.n_prefix, d.n_points, W, d.ln_post_g, d.ln_post_b, d.ln_eps, d.out_w,
+                          d.out_b, out_channels, out, stream));
   return PCD_OK;
 }

@@ -58,6 +58,20 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
     return out.reshape(*x.shape[:-1], dim)
 
 
+def add_layernorm(h: torch.Tensor, y: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                  eps: float = 1e-5, out_dtype=torch.float32) -> torch.Tensor:
+    """Fused residual update + LayerNorm: h += y IN PLACE (h fp32, y bf16/fp32), returns LN(h)."""
+    require_cuda(h, y, weight, bias)
+    assert h.dtype == torch.float32 and h.is_contiguous() and y.is_contiguous() and y.shape == h.shape
+    dim = h.shape[-1]
+    h2, y2 = h.view(-1, dim), y.view(-1, dim)
+    out = torch.empty(h2.shape, device=h.device, dtype=out_dtype)
+    check(_lib.load().pcd_add_layernorm(ptr(h2), dim, ptr(y2), dim, _PREC[y.dtype], ptr(weight), ptr(bias),
+                                        ptr(out), dim, _PREC[out_dtype], h2.shape[0], dim, float(eps),
+                                        stream_ptr()), "add_layernorm")
+    return out.view(h.shape)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
            epilogue: int = EPI_BIAS, residual: Optional[torch.Tensor] = None,
            out_dtype=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -61,6 +61,9 @@ PCD_API int pcd_check_device(void);
  * 1 = P kept in TMEM (tcgen05.mma with A from TMEM, two CTAs per SM; default),
  * 0 = P staged through 128B-swizzled shared memory. */
 PCD_API int pcd_set_attention_variant(int variant);
+/* Profiling aid -- results are INVALID while non-zero: bit 0 skips the GEMM epilogue, bit 1 skips
+ * the GEMM TMA loads (separates main-loop, load and epilogue time in tools/gemm_probe.py). */
+PCD_API int pcd_set_debug_flags(int flags);
 
 /* ------------------------------------------------------------------ */
 /* Elementwise / normalisation kernels                                 */
@@ -78,6 +81,13 @@ PCD_API int pcd_layernorm(const float* x, int ldx, const float* gamma, const flo
                   void* out, int ld_out, int out_precision, int rows, int dim, float eps,
                   void* stream);
 
+/* Fused residual update + LayerNorm (transformer.py:113-114): h <- h + y, out = LayerNorm(h).
+ * y is the bias-added output of the preceding c_proj GEMM ([rows, dim], bf16 or fp32); the
+ * residual stream h stays fp32.  One HBM pass instead of a GEMM residual epilogue + a LayerNorm. */
+PCD_API int pcd_add_layernorm(float* h, int ldh, const void* y, int ldy, int y_precision,
+                              const float* gamma, const float* beta, void* out, int ld_out,
+                              int out_precision, int rows, int dim, float eps, void* stream);
+
 /* Token assembly + ln_pre (transformer.py:205-220).  For sequence s in [0, seqs)
  * and position l in [0, n_prefix + n_points):
  *   l <  n_prefix : row = prefix[s, l, :]                     (conditioning tokens)
@@ -91,8 +101,10 @@ PCD_API int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_points,
                      float* h, int seqs, int dim, void* stream);
 
 /* ln_post + token slice + output_proj + NLC->NCL permute (transformer.py:222-226):
- * out[s, c, n] = W_out[c, :] . LayerNorm(h[s, n_prefix + n, :]) + b_out[c]. */
-PCD_API int pcd_output_proj(const float* h, int seqs, int n_prefix, int n_points, int dim,
+ * out[s, c, n] = W_out[c, :] . LayerNorm(h[s, n_prefix + n, :] (+ y[...])) + b_out[c];
+ * y (nullable, [seqs*L, dim] bf16/fp32) is the last block's pending MLP output. */
+PCD_API int pcd_output_proj(const float* h, const void* y, int y_precision, int seqs, int n_prefix,
+                            int n_points, int dim,
                     const float* ln_g, const float* ln_b, float eps,
                     const float* w_out, const float* b_out, int c_out,
                     float* out, void* stream);

@@ -48,6 +48,21 @@ def test_layernorm(dim):
     assert rel(got16.float(), want) < 4e-3, describe(got16.float(), want)
 
 
+@pytest.mark.parametrize("ydtype", [torch.float32, torch.bfloat16])
+def test_add_layernorm(ydtype):
+    dim = 512
+    h = det.normal((37, dim), 411, std=2.0)
+    y = det.normal((37, dim), 412).to(ydtype)
+    w = 1.0 + det.uniform((dim,), 413, 0.2)
+    b = det.uniform((dim,), 414, 0.2)
+    hs = h + y.float()
+    want = torch.nn.functional.layer_norm(hs, (dim,), w, b, 1e-5)
+    hd = h.to(DEV).clone()
+    got = ops.add_layernorm(hd, y.to(DEV), w.to(DEV), b.to(DEV))
+    assert rel(hd, hs) < 1e-7, describe(hd, hs, "h += y")
+    assert rel(got, want) < 2e-6, describe(got, want)
+
+
 GEMM_SHAPES = [  # M, N, K
     (128, 128, 64), (128, 256, 128), (256, 512, 512), (300, 384, 128), (1026, 1536, 512),
     (77, 256, 192), (5, 2048, 512), (1000, 128, 2048), (640, 72, 64), (129, 520, 72),
