@@ -1,14 +1,19 @@
 // bf16 flash attention (head dim 64, non-causal) on tcgen05 tensor cores.
 //
-// One CTA = one 128-query tile of one (batch, head); 192 threads:
+// One CTA = one 128-query tile of one (batch, head); 256 threads = 2 warpgroups (warpgroup 0
+// hands its registers to the softmax warpgroup with setmaxnreg: 40 vs 216 per thread):
 //   warp 0   : TMA producer -- Q once, then a 2-stage ring of K/V tiles (128 keys x 64),
 //              read straight out of the packed projection buffers through 4-D tensor maps
 //              {64, H, L, B} (rows past L are zero-filled by TMA, so tails need no copies)
 //   warp 1   : MMA issuer   -- S = Q K^T (M128 x N128 x K64) and O_j = P_j V_j (M128 x N64 x
 //              K128, V consumed as an MN-major operand), accumulators in TMEM
-//   warps 2-5: softmax      -- thread = query row: tcgen05.ld S, fp32 online softmax in the
-//              exp2 domain (scale folded in), P_j written back as bf16 (to TMEM, or to
-//              swizzled shared memory in the SS variant), running O rescaled in registers
+//   warps 4-7: softmax      -- thread = query row: the whole 128-wide S row is pulled into
+//              registers with four back-to-back tcgen05.ld (one wait), fp32 softmax in the exp2
+//              domain (scale folded into one FFMA), P_j written back as bf16 (to TMEM, or to
+//              swizzled shared memory in the SS variant).  O accumulates across KV tiles in TMEM
+//              (PV MMAs with accumulate); the running maximum is only refreshed -- and O / l
+//              rescaled in TMEM -- when a row maximum grows by more than 2^8 (lazy rescaling),
+//              so the common iteration touches O not at all.
 // TMEM budget 256 columns (S 128 | P 64 | O 64) so two CTAs are co-resident per SM and
 // one CTA's softmax overlaps the other's MMAs.
 #include "common.cuh"
@@ -32,7 +37,7 @@ struct AttnCfg {
 };
 
 template <bool P_TMEM>
-__global__ void __launch_bounds__(192, P_TMEM ? 2 : 1)
+__global__ void __launch_bounds__(256, P_TMEM ? 2 : 1)
 attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs,
                     int64_t o_ls, int len_q, int len_kv, float scale_log2) {
@@ -79,6 +84,11 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  // warpgroup 0 (TMA, MMA, two idle warps) keeps 40 registers per thread; the freed ones go to
+  // the softmax warpgroup below (setmaxnreg must sit inside the role branch for ptxas to apply
+  // the per-region budget)
+  setmaxnreg_dec<40>();
   if (warp == 0) {
     // --------------------------- TMA producer ---------------------------
     if (lane == 0) {
@@ -129,10 +139,10 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // V tile: 128 key rows of 128 B; 16 keys = two 8-row swizzle groups (SBO 1024)
           const uint64_t bdesc = smem_desc_sw128(v_addr + kk * 2048);
           if (P_TMEM) {
-            umma_bf16_ts(o_tmem, p_tmem + kk * 8, bdesc, idesc_pv, kk != 0);
+            umma_bf16_ts(o_tmem, p_tmem + kk * 8, bdesc, idesc_pv, (j | kk) != 0);
           } else {
             const uint64_t adesc = smem_desc_sw128(smem_u32(sP) + (kk >> 2) * T_TILE_BYTES + (kk & 3) * 32);
-            umma_bf16_ss(o_tmem, adesc, bdesc, idesc_pv, kk != 0);
+            umma_bf16_ss(o_tmem, adesc, bdesc, idesc_pv, (j | kk) != 0);
           }
         }
         umma_commit(&kv_empty[st]);
@@ -140,7 +150,9 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     }
+  }
   } else {
+    setmaxnreg_inc<216>();
     // ----------------------------- softmax ------------------------------
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
@@ -156,92 +168,81 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(p_ready, j & 1);
       }
     } else {
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float o_acc[T_HD];
-#pragma unroll
-    for (int c = 0; c < T_HD; ++c) o_acc[c] = 0.f;
+    float m_used = 0.f, l_run = 0.f;   // m_used: the maximum currently baked into P, l and O
+    constexpr float kRescaleThreshold = 8.f;  // log2 units: P <= 2^8, safe in bf16 / fp32
 
     for (int j = 0; j < num_kv; ++j) {
       const int nvalid = min(T_BKV, len_kv - j * T_BKV);
-      const int nchunks = (nvalid + 31) >> 5;
-      const bool ragged = (nvalid & 31) != 0;  // only the last KV tile can be ragged
       mbar_wait(s_full, j & 1);
       tcgen05_fence_after();
-      // pass 1: row maximum
+      // the whole S row -> registers (columns past nvalid are stale: masked below)
+      uint32_t sr[T_BKV];
+#pragma unroll
+      for (int c = 0; c < T_BKV / 32; ++c)
+        if (c * 32 < nvalid) tmem_ld_32x32b_x32(s_tmem + c * 32, sr + c * 32);
+      tmem_ld_wait();
+      if (nvalid < T_BKV) {
+#pragma unroll
+        for (int i = 0; i < T_BKV; ++i)
+          if (i >= nvalid) sr[i] = 0xff800000u;  // -inf
+      }
       float mx = -INFINITY;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_tmem + c * 32, r);
-        tmem_ld_wait();
-        if (ragged && c == nchunks - 1) {
-          const int lim = nvalid - c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (i < lim) ? __uint_as_float(r[i]) : -INFINITY);
-        } else {
+      for (int i = 0; i < T_BKV; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      mx *= scale_log2;
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool grow = mx > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grow)) {
+          // rare path: rescale this warp's rows of O (and l) to the new maximum.  PV_{j-1} has
+          // to be complete; PV_j is only issued after this thread arrives on p_ready below.
+          mbar_wait(o_full, (j - 1) & 1);
+          tcgen05_fence_after();
+          const float alpha = grow ? ex2_approx(m_used - mx) : 1.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(o_tmem + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32b_x32(o_tmem + c * 32, r);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          if (grow) m_used = mx;
         }
       }
-      const float m_new = fmaxf(m_run, mx * scale_log2);
-      const float alpha = ex2_approx(m_run - m_new);
-      // pass 2: P = exp2(S*scale - m), row sum, bf16 pack, hand-off
-      float sum = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_tmem + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (ragged && c == nchunks - 1) {
-          const int lim = nvalid - c * 32;
+      // P = exp2(S*scale - m_used), row sum, bf16 pack, hand-off (32 columns at a time so the
+      // S registers retire as the packed P words are produced)
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < T_BKV / 32; ++c) {
+        if (c * 32 < nvalid) {
+          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
-            float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
-            if (i >= lim) p0 = 0.f;
-            if (i + 1 >= lim) p1 = 0.f;
-            sum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-        } else {
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2, -m_new));
-            float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_new));
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + i]), scale_log2, -m_used));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + i + 1]), scale_log2, -m_used));
             s0 += p0;
             s1 += p1;
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
-          sum += s0 + s1;
-        }
-        if (P_TMEM) {
-          tmem_st_32x32b_x16(p_tmem + c * 16, pk);
-        } else {
-          // K-major bf16 tile, 128B swizzle: 16-byte chunk index ^= (row & 7)
-          unsigned char* prow = sP + (c >> 1) * T_TILE_BYTES + row_in_tile * 128;
+          if (P_TMEM) {
+            tmem_st_32x32b_x16(p_tmem + c * 16, pk);
+          } else {
+            // K-major bf16 tile, 128B swizzle: 16-byte chunk index ^= (row & 7)
+            unsigned char* prow = sP + (c >> 1) * T_TILE_BYTES + row_in_tile * 128;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int chunk = ((c & 1) * 4 + i) ^ (row_in_tile & 7);
-            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            for (int i = 0; i < 4; ++i) {
+              const int chunk = ((c & 1) * 4 + i) ^ (row_in_tile & 7);
+              *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            }
           }
         }
       }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-      // fold the previous tile's O_{j-1} = P_{j-1} V_{j-1} into the running output
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(o_tmem + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_prev, __uint_as_float(r[i]));
-        }
-      }
-      alpha_prev = alpha;
+      l_run += s0 + s1;
       if (P_TMEM) {
         tmem_st_wait();
       } else {
@@ -250,7 +251,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tcgen05_fence_before();
       mbar_arrive(p_ready);
     }
-    // last tile
+    // epilogue: O / l
     mbar_wait(o_full, (num_kv - 1) & 1);
     tcgen05_fence_after();
     const float inv = 1.f / l_run;
@@ -266,7 +267,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int i = 0; i < 32; i += 8) {
           float v[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[t] = fmaf(o_acc[c * 32 + i + t], alpha_prev, __uint_as_float(r[i + t])) * inv;
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[i + t]) * inv;
           *reinterpret_cast<uint4*>(orow + c * 32 + i) =
               make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
@@ -299,7 +300,7 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     attr_set = true;
   }
   dim3 grid(ceil_div(len_q, T_BQ), heads, batch);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2);
+  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2);
   PCD_CHECK_LAUNCH("attention_bf16");
   return PCD_OK;
 }
