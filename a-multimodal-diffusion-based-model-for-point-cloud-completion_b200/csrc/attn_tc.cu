@@ -284,6 +284,281 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------
+// Ping-pong variant (default): one CTA per SM owns TWO 128-query tiles of one (batch, head).
+// They share the K/V ring; each has its own softmax warpgroup and its own S / P / O columns in
+// TMEM (S0 S1 | P0 P1 | O0 O1 = 512 columns).  The single MMA thread alternates between the tiles,
+// so while one warpgroup exponentiates its S tile (the MUFU-bound part: 16 ex2/clk/SM) the tensor
+// core computes the other tile's QK^T / PV -- the two independent CTAs of the first design ran in
+// lock-step instead (both in softmax, then both waiting on the tensor core).
+// ---------------------------------------------------------------------------
+struct Attn2Cfg {
+  static constexpr int KV_STAGES = 3;
+  static constexpr int TILE_BYTES = T_TILE_BYTES * (2 + 2 * KV_STAGES);
+  static constexpr int SMEM_BYTES = TILE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int S_COL = 0, P_COL = 256, O_COL = 384;  // + tile*128 / tile*64 / tile*64
+};
+
+__global__ void __launch_bounds__(384, 1)
+attn_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs,
+                     int64_t o_ls, int len_q, int len_kv, float scale_log2) {
+  using Cfg = Attn2Cfg;
+  constexpr int KS = Cfg::KV_STAGES;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;                                   // [2]
+  unsigned char* sK = sQ + 2 * T_TILE_BYTES;                  // [KS]
+  unsigned char* sV = sK + KS * T_TILE_BYTES;                 // [KS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILE_BYTES);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* kv_full = bars + 1;       // [KS]
+  uint64_t* kv_empty = kv_full + KS;  // [KS]
+  uint64_t* s_full = kv_empty + KS;   // [2]
+  uint64_t* p_ready = s_full + 2;     // [2]
+  uint64_t* o_full = p_ready + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * T_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int num_kv = (len_kv + T_BKV - 1) / T_BKV;
+  const int ntq = (q0 + T_BQ < len_q) ? 2 : 1;  // second query tile present?
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmK);
+    prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_ready[t], 128);
+      mbar_init(&o_full[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0) {
+      // --------------------------- TMA producer ---------------------------
+      if (lane == 0) {
+        mbar_expect_tx(q_full, ntq * T_TILE_BYTES);
+        for (int t = 0; t < ntq; ++t) tma_load_4d(sQ + t * T_TILE_BYTES, &tmQ, q_full, 0, h, q0 + t * T_BQ, b);
+        for (int j = 0; j < num_kv; ++j) {
+          const int st = j % KS;
+          mbar_wait(&kv_empty[st], ((j / KS) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * T_TILE_BYTES);
+          tma_load_4d(sK + st * T_TILE_BYTES, &tmK, &kv_full[st], 0, h, j * T_BKV, b);
+          tma_load_4d(sV + st * T_TILE_BYTES, &tmV, &kv_full[st], 0, h, j * T_BKV, b);
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------- MMA issuer ----------------------------
+      constexpr uint32_t idesc_pv = idesc_bf16_f32(T_BQ, T_HD, /*B MN-major*/ 1);
+      auto issue_qk = [&](int t, int j) {
+        if (lane == 0) {
+          const int st = j % KS;
+          const int nvalid = min(T_BKV, len_kv - j * T_BKV);
+          const int n = max(16, (nvalid + 15) & ~15);
+          const uint32_t idesc_qk = idesc_bf16_f32(T_BQ, n, 0);
+          const uint64_t adesc = smem_desc_sw128(smem_u32(sQ + t * T_TILE_BYTES));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(sK + st * T_TILE_BYTES));
+          const uint32_t s_tmem = tmem_base + Cfg::S_COL + t * T_BKV;
+#pragma unroll
+          for (int k = 0; k < T_HD / 16; ++k) umma_bf16_ss(s_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int t, int j, bool release_kv) {
+        if (lane == 0) {
+          const int st = j % KS;
+          const int nvalid = min(T_BKV, len_kv - j * T_BKV);
+          const int nks = (nvalid + 15) >> 4;  // 16 keys per MMA
+          const uint32_t v_addr = smem_u32(sV + st * T_TILE_BYTES);
+          const uint32_t p_tmem = tmem_base + Cfg::P_COL + t * (T_BKV / 2);
+          const uint32_t o_tmem = tmem_base + Cfg::O_COL + t * T_HD;
+          for (int kk = 0; kk < nks; ++kk)
+            umma_bf16_ts(o_tmem, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0);
+          if (release_kv) umma_commit(&kv_empty[st]);
+          umma_commit(&o_full[t]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tcgen05_fence_after();
+      for (int t = 0; t < ntq; ++t) issue_qk(t, 0);
+      for (int j = 0; j < num_kv; ++j) {
+        for (int t = 0; t < ntq; ++t) {
+          mbar_wait(&p_ready[t], j & 1);  // P_t(j) is in TMEM and S_t has been fully read
+          tcgen05_fence_after();
+          if (j + 1 < num_kv) {
+            if (t == 0) {
+              mbar_wait(&kv_full[(j + 1) % KS], ((j + 1) / KS) & 1);
+              tcgen05_fence_after();
+            }
+            issue_qk(t, j + 1);  // next S for this tile first: it is on the softmax critical path
+          }
+          issue_pv(t, j, t == ntq - 1);
+        }
+      }
+    }
+  } else {
+    setmaxnreg_inc<232>();
+    // ----------------------------- softmax ------------------------------
+    const int t = (warp - 4) >> 2;  // query tile of this warpgroup
+    const int quarter = warp & 3;
+    const int tq0 = q0 + t * T_BQ;
+    if (t < ntq) {
+      const int row_in_tile = quarter * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t s_tmem = tmem_base + lane_off + Cfg::S_COL + t * T_BKV;
+      const uint32_t p_tmem = tmem_base + lane_off + Cfg::P_COL + t * (T_BKV / 2);
+      const uint32_t o_tmem = tmem_base + lane_off + Cfg::O_COL + t * T_HD;
+      uint64_t* my_s_full = &s_full[t];
+      uint64_t* my_p_ready = &p_ready[t];
+      uint64_t* my_o_full = &o_full[t];
+      if (tq0 + quarter * 32 >= len_q) {
+        // all rows of this warp lie past the end of the sequence: keep the barrier counts in step
+        for (int j = 0; j < num_kv; ++j) {
+          mbar_arrive(my_p_ready);
+          mbar_wait(my_p_ready, j & 1);
+        }
+      } else {
+        float m_used = 0.f, l_run = 0.f;
+        constexpr float kRescaleThreshold = 8.f;
+        for (int j = 0; j < num_kv; ++j) {
+          const int nvalid = min(T_BKV, len_kv - j * T_BKV);
+          mbar_wait(my_s_full, j & 1);
+          tcgen05_fence_after();
+          uint32_t sr[T_BKV];
+#pragma unroll
+          for (int c = 0; c < T_BKV / 32; ++c)
+            if (c * 32 < nvalid) tmem_ld_32x32b_x32(s_tmem + c * 32, sr + c * 32);
+          tmem_ld_wait();
+          if (nvalid < T_BKV) {
+#pragma unroll
+            for (int i = 0; i < T_BKV; ++i)
+              if (i >= nvalid) sr[i] = 0xff800000u;  // -inf
+          }
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < T_BKV; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+          }
+          const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+          if (j == 0) {
+            m_used = mx;
+          } else {
+            const bool grow = mx > m_used + kRescaleThreshold;
+            if (__any_sync(0xffffffffu, grow)) {
+              mbar_wait(my_o_full, (j - 1) & 1);  // PV_t(j-1) complete; PV_t(j) not yet issued
+              tcgen05_fence_after();
+              const float alpha = grow ? ex2_approx(m_used - mx) : 1.f;
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(o_tmem + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                tmem_st_32x32b_x32(o_tmem + c * 32, r);
+              }
+              tmem_st_wait();
+              l_run *= alpha;
+              if (grow) m_used = mx;
+            }
+          }
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < T_BKV / 32; ++c) {
+            if (c * 32 < nvalid) {
+              uint32_t pk[16];
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + i]), scale_log2, -m_used));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c * 32 + i + 1]), scale_log2, -m_used));
+                s0 += p0;
+                s1 += p1;
+                pk[i >> 1] = pack_bf16x2(p0, p1);
+              }
+              tmem_st_32x32b_x16(p_tmem + c * 16, pk);
+            }
+          }
+          l_run += s0 + s1;
+          tmem_st_wait();
+          tcgen05_fence_before();
+          mbar_arrive(my_p_ready);
+        }
+        // epilogue: O / l
+        mbar_wait(my_o_full, (num_kv - 1) & 1);
+        tcgen05_fence_after();
+        const float inv = 1.f / l_run;
+        const int row = tq0 + row_in_tile;
+        uint16_t* orow = out + b * o_bs + (int64_t)row * o_ls + h * T_HD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(o_tmem + c * 32, r);
+          tmem_ld_wait();
+          if (row < len_q) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              float v[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[i + u]) * inv;
+              *reinterpret_cast<uint4*>(orow + c * 32 + i) =
+                  make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
+                           int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv,
+                           float scale_log2, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bf16_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("attention_bf16: cudaFuncSetAttribute(%d): %s", Attn2Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return PCD_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(ceil_div(len_q, T_BQ), 2), heads, batch);
+  attn_bf16_tc2_kernel<<<grid, 384, Attn2Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2);
+  PCD_CHECK_LAUNCH("attention_bf16");
+  return PCD_OK;
+}
+
 template <bool P_TMEM>
 static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           uint16_t* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
@@ -312,7 +587,8 @@ static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batc
   return encode_tmap_bf16(m, op->ptr, 4, dims, strides, box);
 }
 
-int g_attn_variant = 1;  // 1: P in TMEM (TS MMA, 2 CTAs/SM); 0: P in shared memory (SS MMA)
+int g_attn_variant = 2;  // 2: ping-pong over two query tiles (default); 1: one tile per CTA, P in
+                         // TMEM, 2 CTAs/SM; 0: one tile per CTA, P in shared memory (SS MMA)
 
 int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
                           const pcd_attn_operand* v, uint16_t* out, int64_t o_bs, int64_t o_ls,
@@ -324,6 +600,8 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
   if ((rc = make_operand_map(&tk, k, batch, heads, len_kv)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tv, v, batch, heads, len_kv)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
+  if (g_attn_variant == 2)
+    return launch_attn_tc2(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 1)
     return launch_attn_tc<true>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   return launch_attn_tc<false>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);

@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, i
 // ---------------------------------------------------------------------------
 // token assembly + ln_pre (reference models/transformer.py:205-220)
 // ---------------------------------------------------------------------------
+constexpr int EMB_ROWS_PER_WARP = 16;
+
 template <int MAXV>
 __global__ void __launch_bounds__(256) embed_tokens_kernel(
     const float* __restrict__ x, int x_seqs, int c_in, int n_points,
@@ -135,62 +137,80 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
     const float* __restrict__ prefix, int n_prefix, const float* __restrict__ add_cond,
     const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
     float* __restrict__ h, int seqs, int dim) {
-  int L = n_prefix + n_points;
-  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (row >= (int64_t)seqs * L) return;
-  int s = (int)(row / L), l = (int)(row % L);
-  RowRegs<MAXV> r;
-  if (l < n_prefix) {
-    const float* p = prefix + ((size_t)s * n_prefix + l) * dim;
+  // Each warp owns EMB_ROWS_PER_WARP consecutive token rows; the lane's slice of the input
+  // projection (4*MAXV output features x c_in) is loaded once into shared memory per block and
+  // re-used for every row, so the loop is bound by the 4*dim bytes written per token.
+  extern __shared__ __align__(16) float sw[];  // [c_in + 1][dim]: transposed w_in, then the bias
+  const int L = n_prefix + n_points;
+  for (int i = threadIdx.x; i < dim * (c_in + 1); i += blockDim.x) {
+    int k = i / dim, f = i % dim;
+    sw[i] = (k < c_in) ? w_in[(size_t)f * c_in + k] : b_in[f];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t total = (int64_t)seqs * L;
+  for (int rr = 0; rr < EMB_ROWS_PER_WARP; ++rr) {
+    const int64_t row = warp_global * EMB_ROWS_PER_WARP + rr;
+    if (row >= total) break;
+    const int s = (int)(row / L), l = (int)(row % L);
+    RowRegs<MAXV> r;
+    if (l < n_prefix) {
+      const float* p = prefix + ((size_t)s * n_prefix + l) * dim;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int c = (i * 32 + lane) * 4;
-      if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(p + c);
+      for (int i = 0; i < MAXV; ++i) {
+        int c = (i * 32 + lane) * 4;
+        if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(p + c);
+      }
+    } else {
+      const int n = l - n_prefix;
+      const float* xs = x + (size_t)(s % x_seqs) * c_in * n_points + n;
+      float xv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) xv[k] = (k < c_in) ? xs[(size_t)k * n_points] : 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        int c = (i * 32 + lane) * 4;
+        if (c < dim) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k < c_in) {
+              const float4 w4 = *reinterpret_cast<const float4*>(sw + k * dim + c);  // conflict-free
+              acc[0] = fmaf(xv[k], w4.x, acc[0]);
+              acc[1] = fmaf(xv[k], w4.y, acc[1]);
+              acc[2] = fmaf(xv[k], w4.z, acc[2]);
+              acc[3] = fmaf(xv[k], w4.w, acc[3]);
+            }
+          }
+          {
+            const float4 b4 = *reinterpret_cast<const float4*>(sw + c_in * dim + c);
+            acc[0] += b4.x; acc[1] += b4.y; acc[2] += b4.z; acc[3] += b4.w;
+          }
+          if (add_cond != nullptr) {
+            float4 e = *reinterpret_cast<const float4*>(add_cond + (size_t)s * dim + c);
+            acc[0] += e.x; acc[1] += e.y; acc[2] += e.z; acc[3] += e.w;
+          }
+          r.v[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+      }
     }
-  } else {
-    int n = l - n_prefix;
-    const float* xs = x + (size_t)(s % x_seqs) * c_in * n_points + n;
-    float xv[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) xv[k] = (k < c_in) ? xs[(size_t)k * n_points] : 0.f;
+    float mean, rstd;
+    row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
+    float* hr = h + (size_t)row * dim;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       int c = (i * 32 + lane) * 4;
       if (c < dim) {
-        float acc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float* w = w_in + (size_t)(c + j) * c_in;
-          float a = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (k < c_in) a = fmaf(xv[k], w[k], a);
-          acc[j] = a + b_in[c + j];
-        }
-        if (add_cond != nullptr) {
-          float4 e = *reinterpret_cast<const float4*>(add_cond + (size_t)s * dim + c);
-          acc[0] += e.x; acc[1] += e.y; acc[2] += e.z; acc[3] += e.w;
-        }
-        r.v[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        float4 g = *reinterpret_cast<const float4*>(ln_g + c);
+        float4 b = *reinterpret_cast<const float4*>(ln_b + c);
+        float4 y;
+        y.x = (r.v[i].x - mean) * rstd * g.x + b.x;
+        y.y = (r.v[i].y - mean) * rstd * g.y + b.y;
+        y.z = (r.v[i].z - mean) * rstd * g.z + b.z;
+        y.w = (r.v[i].w - mean) * rstd * g.w + b.w;
+        *reinterpret_cast<float4*>(hr + c) = y;
       }
-    }
-  }
-  float mean, rstd;
-  row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
-  float* hr = h + (size_t)row * dim;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int c = (i * 32 + lane) * 4;
-    if (c < dim) {
-      float4 g = *reinterpret_cast<const float4*>(ln_g + c);
-      float4 b = *reinterpret_cast<const float4*>(ln_b + c);
-      float4 y;
-      y.x = (r.v[i].x - mean) * rstd * g.x + b.x;
-      y.y = (r.v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (r.v[i].z - mean) * rstd * g.z + b.z;
-      y.w = (r.v[i].w - mean) * rstd * g.w + b.w;
-      *reinterpret_cast<float4*>(hr + c) = y;
     }
   }
 }
@@ -329,9 +349,13 @@ extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_poin
   PCD_CHECK_ARG(dim % 4 == 0 && dim <= 2048, "embed_tokens: bad width %d", dim);
   PCD_CHECK_ARG(n_prefix >= 0 && (n_prefix == 0 || prefix != nullptr), "embed_tokens: prefix missing");
   int64_t rows = (int64_t)seqs * (n_prefix + n_points);
-  dim3 grid((unsigned)ceil_div64(rows, 8)), block(256);
+  dim3 grid((unsigned)ceil_div64(rows, 8 * EMB_ROWS_PER_WARP)), block(256);
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_MAXV(dim, (embed_tokens_kernel<MAXV><<<grid, block, 0, st>>>(x, x_seqs, c_in, n_points, w_in, b_in, prefix, n_prefix, add_cond, ln_g, ln_b, eps, h, seqs, dim)));
+  const size_t smem = (size_t)dim * (c_in + 1) * sizeof(float);  // <= 2048 * 9 * 4 = 72 KB
+  if (smem > 48 * 1024) {
+    PCD_CHECK_ARG(false, "embed_tokens: width %d with %d channels needs %zu B of shared memory (> 48 KB)", dim, c_in, smem);
+  }
+  DISPATCH_MAXV(dim, (embed_tokens_kernel<MAXV><<<grid, block, smem, st>>>(x, x_seqs, c_in, n_points, w_in, b_in, prefix, n_prefix, add_cond, ln_g, ln_b, eps, h, seqs, dim)));
   PCD_CHECK_LAUNCH("embed_tokens");
   return PCD_OK;
 }

@@ -129,7 +129,7 @@ extern "C" int pcd_set_debug_flags(int flags) {
 }
 
 extern "C" int pcd_set_attention_variant(int v) {
-  PCD_CHECK_ARG(v == 0 || v == 1, "attention variant must be 0 or 1");
+  PCD_CHECK_ARG(v >= 0 && v <= 2, "attention variant must be 0, 1 or 2");
   g_attn_variant = v;
   return PCD_OK;
 }
@@ -242,7 +242,7 @@ extern "C" size_t pcd_model_workspace_bytes(const pcd_model* m, int seqs) {
 extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const float* t, float* prefix,
                                  const float* add_cond, float* out, int out_channels, void* workspace,
                                  size_t workspace_bytes, int seqs, void* stream) {
-  PCD_CHECK_ARG(m != nullptr && x != nullptr && t != nullptr && out != nullptr, "model_forward: null argument");
+  PCD_CHECK_ARG(m != nullptr && x != nullptr && out != nullptr, "model_forward: null argument");
   const pcd_model_desc& d = m->d;
   PCD_CHECK_ARG(seqs > 0 && x_seqs > 0 && seqs % x_seqs == 0, "model_forward: seqs must be a multiple of x_seqs");
   PCD_CHECK_ARG(out_channels >= 1 && out_channels <= d.c_out, "model_forward: out_channels out of range");
@@ -256,18 +256,23 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
   const int M = (int)M64;
   const bool bf = d.precision == PCD_BF16;
 
-  // time embedding MLP (transformer.py:202; models/util.py:72-89) -- always fp32
-  PCD_TRY(pcd_timestep_embed(t, d.freqs, seqs, W, w.temb, W, stream));
-  PCD_TRY(pcd_gemm_f32(w.temb, W, d.time_fc_w, W, d.time_fc_b, nullptr, 0, w.thid, 4 * W, seqs, 4 * W, W, PCD_EPI_BIAS_GELU, stream));
+  // time embedding MLP (transformer.py:202; models/util.py:72-89) -- always fp32.  With t == NULL
+  // the caller has already placed the time token in the prefix slot (or folded it into add_cond):
+  // the sampler evaluates every sequence at the same timestep, so the shim computes each distinct
+  // time token once per stage instead of once per sequence per evaluation.
   const float* addc = add_cond;
-  if (d.time_slot >= 0) {
-    PCD_TRY(pcd_gemm_f32(w.thid, 4 * W, d.time_proj_w, 4 * W, d.time_proj_b, nullptr, 0,
-                         prefix + (size_t)d.time_slot * W, d.n_prefix * W, seqs, W, 4 * W, PCD_EPI_BIAS, stream));
-  } else {
-    // time embedding is added to every point token (transformer.py:209-211)
-    PCD_TRY(pcd_gemm_f32(w.thid, 4 * W, d.time_proj_w, 4 * W, d.time_proj_b, add_cond, W, w.tcond, W, seqs, W, 4 * W,
-                         add_cond ? PCD_EPI_BIAS_RESIDUAL : PCD_EPI_BIAS, stream));
-    addc = w.tcond;
+  if (t != nullptr) {
+    PCD_TRY(pcd_timestep_embed(t, d.freqs, seqs, W, w.temb, W, stream));
+    PCD_TRY(pcd_gemm_f32(w.temb, W, d.time_fc_w, W, d.time_fc_b, nullptr, 0, w.thid, 4 * W, seqs, 4 * W, W, PCD_EPI_BIAS_GELU, stream));
+    if (d.time_slot >= 0) {
+      PCD_TRY(pcd_gemm_f32(w.thid, 4 * W, d.time_proj_w, 4 * W, d.time_proj_b, nullptr, 0,
+                           prefix + (size_t)d.time_slot * W, d.n_prefix * W, seqs, W, 4 * W, PCD_EPI_BIAS, stream));
+    } else {
+      // time embedding is added to every point token (transformer.py:209-211)
+      PCD_TRY(pcd_gemm_f32(w.thid, 4 * W, d.time_proj_w, 4 * W, d.time_proj_b, add_cond, W, w.tcond, W, seqs, W, 4 * W,
+                           add_cond ? PCD_EPI_BIAS_RESIDUAL : PCD_EPI_BIAS, stream));
+      addc = w.tcond;
+    }
   }
   // input_proj + token concat + ln_pre (transformer.py:208-220)
   PCD_TRY(pcd_embed_tokens(x, x_seqs, d.c_in, d.n_points, d.in_w, d.in_b, prefix, d.n_prefix, addc, d.ln_pre_g,

@@ -61,6 +61,7 @@ class _GraphedStage:
                 self.noise[k].copy_(noise_fn(self.shape))
         self.kwargs = {k: v for k, v in kwargs.items() if k != "prev_latent"}
         self.model.prepare_cond(seqs, self.kwargs)
+        self.model.prepare_time_tokens(self.plan.eval_timesteps())
         if self.graph is None:
             # warm-up on a side stream (populates every cache), then capture
             s = torch.cuda.Stream()

@@ -151,7 +151,8 @@ class PointDiffusionTransformer(nn.Module):
         self._cond_key: Dict[int, Any] = {}
         self._cond_refs: Dict[int, Any] = {}
         self._addc: Dict[int, Optional[torch.Tensor]] = {}
-        self._t_cache: Dict[Tuple[int, float], torch.Tensor] = {}
+        self._time_tok: Dict[float, torch.Tensor] = {}
+        self._tcond: Dict[int, torch.Tensor] = {}
         self._out: Dict[Tuple[int, int], torch.Tensor] = {}
 
     # ---- token layout (subclasses override) ----
@@ -220,6 +221,7 @@ class PointDiffusionTransformer(nn.Module):
         self._handle, self._packed_key, self._keep = handle, key, keep
         self._n_prefix, self._time_slot = n_prefix, time_slot
         self._cond_key.clear()
+        self._time_tok.clear()
 
     def _destroy_handle(self):
         if getattr(self, "_handle", None) is not None:
@@ -242,17 +244,20 @@ class PointDiffusionTransformer(nn.Module):
                                   if self._n_prefix else None)
         return self._ws[seqs], self._prefix[seqs]
 
-    def _run(self, x: torch.Tensor, t: torch.Tensor, kw: Dict[str, Any], seqs: int, out_channels: int,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _run(self, x: torch.Tensor, t: Optional[torch.Tensor], kw: Dict[str, Any], seqs: int, out_channels: int,
+             out: Optional[torch.Tensor] = None, add_cond_override: Optional[torch.Tensor] = None) -> torch.Tensor:
         require_cuda(x, t)
         assert x.dim() == 3 and x.shape[1] == self.input_channels and x.shape[2] == self.n_ctx, \
             f"expected x of shape [B, {self.input_channels}, {self.n_ctx}], got {tuple(x.shape)}"
         self._ensure_handle()
         ws, prefix = self._get_buffers(seqs)
         add_cond = self.prepare_cond(seqs, kw)
+        if add_cond_override is not None:
+            add_cond = add_cond_override
         x = x.float().contiguous()
-        t = t.to(torch.float32).contiguous()
-        assert t.shape == (seqs,)
+        if t is not None:
+            t = t.to(torch.float32).contiguous()
+            assert t.shape == (seqs,)
         if out is None:
             out = torch.empty(seqs, out_channels, self.n_ctx, device=x.device, dtype=torch.float32)
         check(_lib.load().pcd_model_forward(self._handle, ptr(x), x.shape[0], ptr(t), ptr(prefix), ptr(add_cond),
@@ -293,14 +298,50 @@ class PointDiffusionTransformer(nn.Module):
         B = x.shape[0]
         seqs = 2 * B if doubled else B
         oc = out_channels or self.output_channels
-        key = (seqs, float(t))
-        if key not in self._t_cache:
-            self._t_cache[key] = torch.full((seqs,), float(t), device=x.device, dtype=torch.float32)
         okey = (seqs, oc)
         if okey not in self._out:
             self._out[okey] = torch.empty(seqs, oc, self.n_ctx, device=x.device, dtype=torch.float32)
         kw = {k: v for k, v in (model_kwargs or {}).items() if k != "prev_latent"}
-        return self._run(x, self._t_cache[key], kw, seqs, oc, out=self._out[okey])
+        # every sequence shares the timestep: the time token is computed once per distinct t
+        # (time_embed MLP on ONE row) and broadcast into the prefix slot
+        self._ensure_handle()
+        tok = self.time_token(t)
+        _, prefix = self._get_buffers(seqs)
+        if self._time_slot >= 0:
+            prefix[:, self._time_slot].copy_(tok.expand(seqs, -1))
+            return self._run(x, None, kw, seqs, oc, out=self._out[okey])
+        addc = self.prepare_cond(seqs, kw)
+        tcond = self._tcond.setdefault(seqs, torch.empty(seqs, tok.shape[-1], device=x.device))
+        if addc is None:
+            tcond.copy_(tok.expand(seqs, -1))
+        else:
+            torch.add(addc, tok, out=tcond)
+        return self._run(x, None, kw, seqs, oc, out=self._out[okey], add_cond_override=tcond)
+
+    @torch.no_grad()
+    def time_token(self, t) -> torch.Tensor:
+        """time_embed(timestep_embedding(t)) for ONE timestep value -> [1, width], cached."""
+        key = float(t)
+        tok = self._time_tok.get(key)
+        if tok is None:
+            dev = self.ln_pre.weight.device
+            tt = torch.full((1,), key, device=dev, dtype=torch.float32)
+            tok = self.time_embed(ops.timestep_embedding(tt, self.backbone.width))
+            self._time_tok[key] = tok
+        return tok
+
+    @torch.no_grad()
+    def prepare_time_tokens(self, timesteps) -> None:
+        """Batch-compute the time tokens of a whole sampling schedule (distinct values only)."""
+        self._ensure_handle()
+        todo = sorted({float(t) for t in timesteps} - set(self._time_tok))
+        if not todo:
+            return
+        dev = self.ln_pre.weight.device
+        tt = torch.tensor(todo, device=dev, dtype=torch.float32)
+        toks = self.time_embed(ops.timestep_embedding(tt, self.backbone.width))
+        for i, k in enumerate(todo):
+            self._time_tok[k] = toks[i:i + 1].clone()
 
     # helpers for subclasses -------------------------------------------------
     def _embed_grid(self, grid: torch.Tensor) -> torch.Tensor:

@@ -57,9 +57,10 @@ PCD_API unsigned long long pcd_launch_count(void);
 /* Device capability probe: 0 if the current device is sm_100 (B200). */
 PCD_API int pcd_check_device(void);
 
-/* Tuning / testing knob (no reference counterpart): attention P operand placement,
- * 1 = P kept in TMEM (tcgen05.mma with A from TMEM, two CTAs per SM; default),
- * 0 = P staged through 128B-swizzled shared memory. */
+/* Tuning / testing knob (no reference counterpart): tensor-core attention kernel variant,
+ * 2 = ping-pong over two query tiles per CTA, P in TMEM (default),
+ * 1 = one query tile per CTA, P in TMEM (tcgen05.mma with A from TMEM), two CTAs per SM,
+ * 0 = one query tile per CTA, P staged through 128B-swizzled shared memory. */
 PCD_API int pcd_set_attention_variant(int variant);
 /* Profiling aid -- results are INVALID while non-zero: bit 0 skips the GEMM epilogue, bit 1 skips
  * the GEMM TMA loads (separates main-loop, load and epilogue time in tools/gemm_probe.py). */
@@ -239,7 +240,8 @@ PCD_API size_t pcd_model_workspace_bytes(const pcd_model* m, int seqs);
 /* out[s] = model(x[s % x_seqs], t[s], prefix[s]) for s in [0, seqs).
  *  x       fp32 [x_seqs, c_in, n_points]  (x_seqs == seqs, or seqs/2 when the cond and
  *          uncond halves of classifier-free guidance share the same x)
- *  t       fp32 [seqs]
+ *  t       fp32 [seqs], or NULL when the caller has already written the time token into the
+ *          prefix slot / folded it into add_cond (one time-MLP evaluation per distinct t)
  *  prefix  fp32 [seqs, n_prefix, width]; slot `time_slot` is (over)written with the
  *          time-MLP output; the other slots hold step-invariant conditioning tokens
  *  add_cond fp32 [seqs, width] or NULL: non-token conditioning added to point tokens
