@@ -613,7 +613,7 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 128);
+      mbar_init(&p_ready[s], 4);  // one arrival per softmax warp
       mbar_init(&pv_done[s], 1);
     }
     fence_barrier_init();
@@ -695,7 +695,7 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (q0 + quarter * 32 >= len_q) {
       // every row of this warp is past the end of the sequence: only keep the counts in step
       for (int j = 0; j < num_kv; ++j) {
-        mbar_arrive(&p_ready[j & 1]);
+        if (lane == 0) mbar_arrive(&p_ready[j & 1]);
         mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
       }
     } else {
@@ -776,7 +776,8 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         l_run += s0 + s1;
         tmem_st_wait();
         tcgen05_fence_before();
-        mbar_arrive(&p_ready[bf]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[bf]);
       }
       // epilogue: O / l
       mbar_wait(&pv_done[(num_kv - 1) & 1], ((num_kv - 1) >> 1) & 1);
