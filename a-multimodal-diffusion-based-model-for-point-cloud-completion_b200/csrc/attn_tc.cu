@@ -701,19 +701,20 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     } else {
       float m_used = 0.f, l_run = 0.f;
       constexpr float kRescaleThreshold = 8.f;
-      for (int j = 0; j < num_kv; ++j) {
-        const int bf = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int nvalid = min(BKV, len_kv - j * BKV);
-        const uint32_t s_tmem = tmem_base + lane_off + Cfg::S_COL + bf * BKV;
-        const uint32_t p_tmem = tmem_base + lane_off + Cfg::P_COL + bf * (BKV / 2);
-        mbar_wait(&s_full[bf], ph);
+      const uint32_t s_base = tmem_base + lane_off + Cfg::S_COL;
+      const uint32_t p_base = tmem_base + lane_off + Cfg::P_COL;
+      // S_j lives in registers one iteration ahead: while the MUFU-bound exponentials of tile j
+      // run, S_{j+1} is already being pulled out of TMEM and reduced to its row maximum.
+      auto load_s = [&](int j, uint32_t* dst) {
+        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
         tcgen05_fence_after();
-        uint32_t sr[BKV];
+        const int nvalid = min(BKV, len_kv - j * BKV);
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c)
-          if (c * 32 < nvalid) tmem_ld_32x32b_x32(s_tmem + c * 32, sr + c * 32);
-        tmem_ld_wait();
+          if (c * 32 < nvalid) tmem_ld_32x32b_x32(s_base + (j & 1) * BKV + c * 32, dst + c * 32);
+      };
+      auto row_max = [&](int j, uint32_t* sr) -> float {
+        const int nvalid = min(BKV, len_kv - j * BKV);
         if (nvalid < BKV) {
 #pragma unroll
           for (int i = 0; i < BKV; ++i)
@@ -727,29 +728,40 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      };
+      uint32_t sa[BKV], sb[BKV];
+      load_s(0, sa);
+      tmem_ld_wait();
+      float mx_cur = row_max(0, sa);
+      // process one KV tile held in `sr`; `nx` receives the next tile
+      auto step = [&](int j, uint32_t* sr, uint32_t* nx) {
+        const int bf = j & 1;
+        const int nvalid = min(BKV, len_kv - j * BKV);
+        const uint32_t p_tmem = p_base + bf * (BKV / 2);
+        if (j + 1 < num_kv) load_s(j + 1, nx);  // asynchronous: consumed after the exponentials
         if (j == 0) {
-          m_used = mx;
+          m_used = mx_cur;
         } else {
-          const bool grow = mx > m_used + kRescaleThreshold;
+          const bool grow = mx_cur > m_used + kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
             // rare: bring O and l to the new maximum.  PV_{j-1} (and all earlier) must be done;
-            // PV_j is not issued before this thread arrives on p_ready below.
+            // PV_j is not issued before this warp arrives on p_ready below.
             mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
             tcgen05_fence_after();
-            const float alpha = grow ? ex2_approx(m_used - mx) : 1.f;
+            const float alpha = grow ? ex2_approx(m_used - mx_cur) : 1.f;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(o_tmem + c * 32, r);
-              tmem_ld_wait();
+              tmem_ld_wait();  // (also completes the S_{j+1} prefetch)
 #pragma unroll
               for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
               tmem_st_32x32b_x32(o_tmem + c * 32, r);
             }
             tmem_st_wait();
             l_run *= alpha;
-            if (grow) m_used = mx;
+            if (grow) m_used = mx_cur;
           }
         }
         // P buffer bf was last read by PV_{j-2}
@@ -774,10 +786,18 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         l_run += s0 + s1;
+        if (j + 1 < num_kv) {
+          tmem_ld_wait();
+          mx_cur = row_max(j + 1, nx);
+        }
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[bf]);
+      };
+      for (int j = 0; j < num_kv; j += 2) {
+        step(j, sa, sb);
+        if (j + 1 < num_kv) step(j + 1, sb, sa);
       }
       // epilogue: O / l
       mbar_wait(&pv_done[(num_kv - 1) & 1], ((num_kv - 1) >> 1) & 1);
