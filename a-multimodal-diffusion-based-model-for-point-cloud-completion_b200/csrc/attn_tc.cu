@@ -701,20 +701,19 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     } else {
       float m_used = 0.f, l_run = 0.f;
       constexpr float kRescaleThreshold = 8.f;
-      const uint32_t s_base = tmem_base + lane_off + Cfg::S_COL;
-      const uint32_t p_base = tmem_base + lane_off + Cfg::P_COL;
-      // S_j lives in registers one iteration ahead: while the MUFU-bound exponentials of tile j
-      // run, S_{j+1} is already being pulled out of TMEM and reduced to its row maximum.
-      auto load_s = [&](int j, uint32_t* dst) {
-        mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-        tcgen05_fence_after();
+      for (int j = 0; j < num_kv; ++j) {
+        const int bf = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
         const int nvalid = min(BKV, len_kv - j * BKV);
+        const uint32_t s_tmem = tmem_base + lane_off + Cfg::S_COL + bf * BKV;
+        const uint32_t p_tmem = tmem_base + lane_off + Cfg::P_COL + bf * (BKV / 2);
+        mbar_wait(&s_full[bf], ph);
+        tcgen05_fence_after();
+        uint32_t sr[BKV];
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c)
-          if (c * 32 < nvalid) tmem_ld_32x32b_x32(s_base + (j & 1) * BKV + c * 32, dst + c * 32);
-      };
-      auto row_max = [&](int j, uint32_t* sr) -> float {
-        const int nvalid = min(BKV, len_kv - j * BKV);
+          if (c * 32 < nvalid) tmem_ld_32x32b_x32(s_tmem + c * 32, sr + c * 32);
+        tmem_ld_wait();
         if (nvalid < BKV) {
 #pragma unroll
           for (int i = 0; i < BKV; ++i)
@@ -728,40 +727,29 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
           mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
         }
-        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-      };
-      uint32_t sa[BKV], sb[BKV];
-      load_s(0, sa);
-      tmem_ld_wait();
-      float mx_cur = row_max(0, sa);
-      // process one KV tile held in `sr`; `nx` receives the next tile
-      auto step = [&](int j, uint32_t* sr, uint32_t* nx) {
-        const int bf = j & 1;
-        const int nvalid = min(BKV, len_kv - j * BKV);
-        const uint32_t p_tmem = p_base + bf * (BKV / 2);
-        if (j + 1 < num_kv) load_s(j + 1, nx);  // asynchronous: consumed after the exponentials
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
         if (j == 0) {
-          m_used = mx_cur;
+          m_used = mx;
         } else {
-          const bool grow = mx_cur > m_used + kRescaleThreshold;
+          const bool grow = mx > m_used + kRescaleThreshold;
           if (__any_sync(0xffffffffu, grow)) {
             // rare: bring O and l to the new maximum.  PV_{j-1} (and all earlier) must be done;
-            // PV_j is not issued before this warp arrives on p_ready below.
+            // PV_j is not issued before this thread arrives on p_ready below.
             mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
             tcgen05_fence_after();
-            const float alpha = grow ? ex2_approx(m_used - mx_cur) : 1.f;
+            const float alpha = grow ? ex2_approx(m_used - mx) : 1.f;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint32_t r[32];
               tmem_ld_32x32b_x32(o_tmem + c * 32, r);
-              tmem_ld_wait();  // (also completes the S_{j+1} prefetch)
+              tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
               tmem_st_32x32b_x32(o_tmem + c * 32, r);
             }
             tmem_st_wait();
             l_run *= alpha;
-            if (grow) m_used = mx_cur;
+            if (grow) m_used = mx;
           }
         }
         // P buffer bf was last read by PV_{j-2}
@@ -786,18 +774,10 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         l_run += s0 + s1;
-        if (j + 1 < num_kv) {
-          tmem_ld_wait();
-          mx_cur = row_max(j + 1, nx);
-        }
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[bf]);
-      };
-      for (int j = 0; j < num_kv; j += 2) {
-        step(j, sa, sb);
-        if (j + 1 < num_kv) step(j + 1, sb, sa);
       }
       // epilogue: O / l
       mbar_wait(&pv_done[(num_kv - 1) & 1], ((num_kv - 1) >> 1) & 1);
@@ -850,6 +830,297 @@ static int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const C
   return PCD_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Split-row variant (default): like the double-buffered kernel above, but every query row is
+// shared by TWO softmax threads (warps w and w+4 own the same TMEM lane quarter and split the 64
+// keys of a KV tile 32/32).  That doubles the number of softmax warps (16 per SM, 4 per
+// scheduler) so the per-iteration latencies of one warp (barrier wake-up, TMEM load/store
+// round trips) hide behind the exponentials of the others.  The two threads of a row only
+// synchronise through a 64-thread named barrier per iteration (to agree on lazy rescaling) and
+// once at the end (row sum).
+// ---------------------------------------------------------------------------
+// 64-thread named barrier of the warp pair that shares TMEM lane quarter q (literal barrier ids,
+// so that ptxas reserves 5 hardware barriers per CTA instead of all 16)
+__device__ __forceinline__ void pair_sync(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+struct Attn4Cfg {
+  static constexpr int BKV = 64;
+  static constexpr int KV_TILE = BKV * T_HD * 2;   // 8 KB per K or V tile
+  static constexpr int KV_STAGES = 5;
+  static constexpr int TILE_BYTES = T_TILE_BYTES + KV_STAGES * 2 * KV_TILE;  // Q + ring
+  static constexpr int XCH_BYTES = 128 * 2 * 4 + 64;  // per-row exchange floats + pair flags
+  static constexpr int SMEM_BYTES = TILE_BYTES + 1024 + 256 + XCH_BYTES;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int S_COL = 0, P_COL = 128, O_COL = 192;  // S: +buf*64, P: +buf*32
+};
+
+__global__ void __launch_bounds__(384, 2)
+attn_bf16_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs,
+                     int64_t o_ls, int len_q, int len_kv, float scale_log2) {
+  using Cfg = Attn4Cfg;
+  constexpr int KS = Cfg::KV_STAGES;
+  constexpr int BKV = Cfg::BKV;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + T_TILE_BYTES;            // [KS] 8 KB each
+  unsigned char* sV = sK + KS * Cfg::KV_TILE;       // [KS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::TILE_BYTES);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* kv_full = bars + 1;       // [KS]
+  uint64_t* kv_empty = kv_full + KS;  // [KS]
+  uint64_t* s_full = kv_empty + KS;   // [2]  QK_j done            (MMA -> softmax)
+  uint64_t* p_ready = s_full + 2;     // [2]  P_j written, S_j read (softmax -> MMA)
+  uint64_t* pv_done = p_ready + 2;    // [2]  PV_j done: P buffer free, O updated (MMA -> softmax)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::TILE_BYTES + 256);        // [128 rows][2 halves]
+  volatile int* pair_flag = reinterpret_cast<volatile int*>(xch + 256);       // [4 quarters][2 halves]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * T_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int num_kv = (len_kv + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmK);
+    prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 8);  // one arrival per softmax warp
+      mbar_init(&pv_done[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    setmaxnreg_dec<40>();
+    if (warp == 0) {
+      // --------------------------- TMA producer ---------------------------
+      if (lane == 0) {
+        mbar_expect_tx(q_full, T_TILE_BYTES);
+        tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+        for (int j = 0; j < num_kv; ++j) {
+          const int st = j % KS;
+          mbar_wait(&kv_empty[st], ((j / KS) & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * Cfg::KV_TILE);
+          tma_load_4d(sK + st * Cfg::KV_TILE, &tmK, &kv_full[st], 0, h, j * BKV, b);
+          tma_load_4d(sV + st * Cfg::KV_TILE, &tmV, &kv_full[st], 0, h, j * BKV, b);
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------- MMA issuer ----------------------------
+      constexpr uint32_t idesc_pv = idesc_bf16_f32(T_BQ, T_HD, /*B MN-major*/ 1);
+      auto issue_qk = [&](int j) {
+        const int st = j % KS;
+        mbar_wait(&kv_full[st], (j / KS) & 1);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const int nvalid = min(BKV, len_kv - j * BKV);
+          const int n = max(16, (nvalid + 15) & ~15);
+          const uint32_t idesc_qk = idesc_bf16_f32(T_BQ, n, 0);
+          const uint64_t adesc = smem_desc_sw128(smem_u32(sQ));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(sK + st * Cfg::KV_TILE));
+          const uint32_t s_tmem = tmem_base + Cfg::S_COL + (j & 1) * BKV;
+#pragma unroll
+          for (int k = 0; k < T_HD / 16; ++k) umma_bf16_ss(s_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[j & 1]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      if (num_kv > 1) issue_qk(1);
+      for (int j = 0; j < num_kv; ++j) {
+        const int bf = j & 1;
+        mbar_wait(&p_ready[bf], (j >> 1) & 1);  // P_j in TMEM, S buffer bf fully read
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const int st = j % KS;
+          const int nvalid = min(BKV, len_kv - j * BKV);
+          const int nks = (nvalid + 15) >> 4;  // 16 keys per MMA
+          const uint32_t v_addr = smem_u32(sV + st * Cfg::KV_TILE);
+          const uint32_t p_tmem = tmem_base + Cfg::P_COL + bf * (BKV / 2);
+          const uint32_t o_tmem = tmem_base + Cfg::O_COL;
+          for (int kk = 0; kk < nks; ++kk)
+            umma_bf16_ts(o_tmem, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0);
+          umma_commit(&kv_empty[st]);
+          umma_commit(&pv_done[bf]);
+        }
+        __syncwarp();
+        if (j + 2 < num_kv) issue_qk(j + 2);  // refill the S buffer that was just drained
+      }
+    }
+  } else {
+    setmaxnreg_inc<104>();
+    // ----------------------------- softmax ------------------------------
+    const int quarter = warp & 3;            // TMEM lane quarter (rows 32*quarter .. +31)
+    const int half = (warp - 4) >> 2;        // which 32 of the 64 keys / 32 of the 64 O columns
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t o_tmem = tmem_base + lane_off + Cfg::O_COL + half * 32;
+    if (q0 + quarter * 32 >= len_q) {
+      // every row of this warp is past the end of the sequence: only keep the counts in step
+      for (int j = 0; j < num_kv; ++j) {
+        if (lane == 0) mbar_arrive(&p_ready[j & 1]);
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+      }
+    } else {
+      float m_used = 0.f, l_run = 0.f;
+      constexpr float kRescaleThreshold = 8.f;
+      for (int j = 0; j < num_kv; ++j) {
+        const int bf = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        const int nvalid = min(BKV, len_kv - j * BKV) - half * 32;  // valid keys in my 32 columns
+        const uint32_t s_tmem = tmem_base + lane_off + Cfg::S_COL + bf * BKV + half * 32;
+        const uint32_t p_tmem = tmem_base + lane_off + Cfg::P_COL + bf * (BKV / 2) + half * 16;
+        mbar_wait(&s_full[bf], ph);
+        tcgen05_fence_after();
+        uint32_t sr[32];
+        if (nvalid > 0) {
+          tmem_ld_32x32b_x32(s_tmem, sr);
+          tmem_ld_wait();
+        }
+        if (nvalid < 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= nvalid) sr[i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+        // agree with the partner warp on whether any row of this quarter needs a new maximum
+        const bool want = (j == 0) || (mx > m_used + kRescaleThreshold);
+        const int my_any = __any_sync(0xffffffffu, want) ? 1 : 0;
+        if (lane == 0) pair_flag[quarter * 2 + half] = my_any;
+        pair_sync(quarter);
+        const int any = my_any | pair_flag[quarter * 2 + (half ^ 1)];
+        if (any) {
+          // rare (always at j == 0): exchange the per-row maxima so both halves of a row use the
+          // same reference, then bring O and l to it.  PV_{j-1} must be done; PV_j is not issued
+          // before both warps arrive on p_ready below.
+          xch[row_in_tile * 2 + half] = mx;
+          pair_sync(quarter);
+          const float m_row = fmaxf(mx, xch[row_in_tile * 2 + (half ^ 1)]);
+          if (j == 0) {
+            m_used = m_row;
+          } else {
+            const bool grow = m_row > m_used + kRescaleThreshold;
+            mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            tcgen05_fence_after();
+            const float alpha = grow ? ex2_approx(m_used - m_row) : 1.f;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(o_tmem, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32b_x32(o_tmem, r);
+            tmem_st_wait();
+            l_run *= alpha;
+            if (grow) m_used = m_row;
+          }
+          // (the flag / xch slots are rewritten only after the next bar.sync of this pair)
+        }
+        // P buffer bf was last read by PV_{j-2}
+        if (j >= 2) {
+          mbar_wait(&pv_done[bf], ((j - 2) >> 1) & 1);
+          tcgen05_fence_after();
+        }
+        if (nvalid > 0) {
+          float s0 = 0.f, s1 = 0.f;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[i]), scale_log2, -m_used));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[i + 1]), scale_log2, -m_used));
+            s0 += p0;
+            s1 += p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          l_run += s0 + s1;
+          tmem_st_32x32b_x16(p_tmem, pk);
+          tmem_st_wait();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[bf]);
+      }
+      // epilogue: O / (l_mine + l_partner), 32 output columns per thread
+      xch[row_in_tile * 2 + half] = l_run;
+      pair_sync(quarter);
+      const float inv = 1.f / (l_run + xch[row_in_tile * 2 + (half ^ 1)]);
+      mbar_wait(&pv_done[(num_kv - 1) & 1], ((num_kv - 1) >> 1) & 1);
+      tcgen05_fence_after();
+      const int row = q0 + row_in_tile;
+      uint16_t* orow = out + b * o_bs + (int64_t)row * o_ls + h * T_HD + half * 32;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(o_tmem, r);
+      tmem_ld_wait();
+      if (row < len_q) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[i + u]) * inv;
+          *reinterpret_cast<uint4*>(orow + i) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+static int launch_attn_tc4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
+                           int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv,
+                           float scale_log2, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bf16_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn4Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("attention_bf16: cudaFuncSetAttribute(%d): %s", Attn4Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return PCD_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(len_q, T_BQ), heads, batch);
+  attn_bf16_tc4_kernel<<<grid, 384, Attn4Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2);
+  PCD_CHECK_LAUNCH("attention_bf16");
+  return PCD_OK;
+}
+
 template <bool P_TMEM>
 static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                           uint16_t* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
@@ -878,7 +1149,8 @@ static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batc
   return encode_tmap_bf16(m, op->ptr, 4, dims, strides, box);
 }
 
-int g_attn_variant = 3;  // 3: double-buffered S/P, 64-key tiles, 2 CTAs/SM (default); 2: ping-pong
+int g_attn_variant = 4;  // 4: split-row double-buffered (default); 3: double-buffered S/P, 64-key
+                         // tiles, 2 CTAs/SM; 2: ping-pong
                          // over two query tiles; 1: one tile per CTA, P in
                          // TMEM, 2 CTAs/SM; 0: one tile per CTA, P in shared memory (SS MMA)
 
@@ -888,11 +1160,13 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
                           cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   int rc;
-  const int kv_rows = g_attn_variant == 3 ? Attn3Cfg::BKV : T_BKV;
+  const int kv_rows = g_attn_variant >= 3 ? Attn3Cfg::BKV : T_BKV;
   if ((rc = make_operand_map(&tq, q, batch, heads, len_q, T_BQ)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
+  if (g_attn_variant == 4)
+    return launch_attn_tc4(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 3)
     return launch_attn_tc3(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 2)

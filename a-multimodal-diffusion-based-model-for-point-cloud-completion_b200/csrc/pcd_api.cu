@@ -129,7 +129,7 @@ extern "C" int pcd_set_debug_flags(int flags) {
 }
 
 extern "C" int pcd_set_attention_variant(int v) {
-  PCD_CHECK_ARG(v >= 0 && v <= 3, "attention variant must be 0..3");
+  PCD_CHECK_ARG(v >= 0 && v <= 4, "attention variant must be 0..4");
   g_attn_variant = v;
   return PCD_OK;
 }
