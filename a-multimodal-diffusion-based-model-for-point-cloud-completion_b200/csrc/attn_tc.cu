@@ -855,7 +855,7 @@ struct Attn4Cfg {
   static constexpr int KV_TILE = BKV * T_HD * 2;   // 8 KB per K or V tile
   static constexpr int KV_STAGES = 5;
   static constexpr int TILE_BYTES = T_TILE_BYTES + KV_STAGES * 2 * KV_TILE;  // Q + ring
-  static constexpr int XCH_BYTES = 128 * 2 * 4 + 64;  // per-row exchange floats + pair flags
+  static constexpr int XCH_BYTES = 128 * 2 * 4 + 64;  // per-row exchange floats + 16 pair flags
   static constexpr int SMEM_BYTES = TILE_BYTES + 1024 + 256 + XCH_BYTES;
   static constexpr int TMEM_COLS = 256;
   static constexpr int S_COL = 0, P_COL = 128, O_COL = 192;  // S: +buf*64, P: +buf*32
@@ -972,7 +972,9 @@ attn_bf16_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else {
-    setmaxnreg_inc<104>();
+    // register pool of the CTA is fixed at launch: 384 x 80; warpgroup 0 releases 128 x 40, so the
+    // two softmax warpgroups can grow to (384*80 - 128*40) / 256 = 100 -> 96 registers
+    setmaxnreg_inc<96>();
     // ----------------------------- softmax ------------------------------
     const int quarter = warp & 3;            // TMEM lane quarter (rows 32*quarter .. +31)
     const int half = (warp - 4) >> 2;        // which 32 of the 64 keys / 32 of the 64 O columns
@@ -1018,9 +1020,10 @@ attn_bf16_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // agree with the partner warp on whether any row of this quarter needs a new maximum
         const bool want = (j == 0) || (mx > m_used + kRescaleThreshold);
         const int my_any = __any_sync(0xffffffffu, want) ? 1 : 0;
-        if (lane == 0) pair_flag[quarter * 2 + half] = my_any;
+        // (flag slots alternate with the iteration parity: a slot is rewritten two barriers later)
+        if (lane == 0) pair_flag[(j & 1) * 8 + quarter * 2 + half] = my_any;
         pair_sync(quarter);
-        const int any = my_any | pair_flag[quarter * 2 + (half ^ 1)];
+        const int any = my_any | pair_flag[(j & 1) * 8 + quarter * 2 + (half ^ 1)];
         if (any) {
           // rare (always at j == 0): exchange the per-row maxima so both halves of a row use the
           // same reference, then bring O and l to it.  PV_{j-1} must be done; PV_j is not issued
