@@ -91,7 +91,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   setmaxnreg_dec<40>();
   if (warp == 0) {
     // --------------------------- TMA producer ---------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, T_TILE_BYTES);
       tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
       for (int j = 0; j < num_kv; ++j) {
@@ -112,7 +112,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int st = j & 1;
       mbar_wait(&kv_full[st], (j >> 1) & 1);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         int nvalid = min(T_BKV, len_kv - j * T_BKV);
         int n = max(16, (nvalid + 15) & ~15);
         const uint32_t idesc_qk = idesc_bf16_f32(T_BQ, n, 0);
@@ -130,7 +130,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(p_ready, j & 1);
       tcgen05_fence_after();
       if (j + 1 < num_kv) issue_qk(j + 1);  // S is free: every softmax thread has read S_j
-      if (lane == 0) {
+      if (elect_one()) {
         const int st = j & 1;
         int nvalid = min(T_BKV, len_kv - j * T_BKV);
         int nks = (nvalid + 15) >> 4;  // 16 keys per MMA
@@ -354,7 +354,7 @@ attn_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     setmaxnreg_dec<40>();
     if (warp == 0) {
       // --------------------------- TMA producer ---------------------------
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_expect_tx(q_full, ntq * T_TILE_BYTES);
         for (int t = 0; t < ntq; ++t) tma_load_4d(sQ + t * T_TILE_BYTES, &tmQ, q_full, 0, h, q0 + t * T_BQ, b);
         for (int j = 0; j < num_kv; ++j) {
@@ -369,7 +369,7 @@ attn_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // ---------------------------- MMA issuer ----------------------------
       constexpr uint32_t idesc_pv = idesc_bf16_f32(T_BQ, T_HD, /*B MN-major*/ 1);
       auto issue_qk = [&](int t, int j) {
-        if (lane == 0) {
+        if (elect_one()) {
           const int st = j % KS;
           const int nvalid = min(T_BKV, len_kv - j * T_BKV);
           const int n = max(16, (nvalid + 15) & ~15);
@@ -384,7 +384,7 @@ attn_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         __syncwarp();
       };
       auto issue_pv = [&](int t, int j, bool release_kv) {
-        if (lane == 0) {
+        if (elect_one()) {
           const int st = j % KS;
           const int nvalid = min(T_BKV, len_kv - j * T_BKV);
           const int nks = (nvalid + 15) >> 4;  // 16 keys per MMA
@@ -631,7 +631,7 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     setmaxnreg_dec<40>();
     if (warp == 0) {
       // --------------------------- TMA producer ---------------------------
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_expect_tx(q_full, T_TILE_BYTES);
         tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
         for (int j = 0; j < num_kv; ++j) {
@@ -649,7 +649,7 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int st = j % KS;
         mbar_wait(&kv_full[st], (j / KS) & 1);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const int nvalid = min(BKV, len_kv - j * BKV);
           const int n = max(16, (nvalid + 15) & ~15);
           const uint32_t idesc_qk = idesc_bf16_f32(T_BQ, n, 0);
@@ -669,7 +669,7 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int bf = j & 1;
         mbar_wait(&p_ready[bf], (j >> 1) & 1);  // P_j in TMEM, S buffer bf fully read
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const int st = j % KS;
           const int nvalid = min(BKV, len_kv - j * BKV);
           const int nks = (nvalid + 15) >> 4;  // 16 keys per MMA
@@ -917,7 +917,7 @@ attn_bf16_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     setmaxnreg_dec<40>();
     if (warp == 0) {
       // --------------------------- TMA producer ---------------------------
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_expect_tx(q_full, T_TILE_BYTES);
         tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
         for (int j = 0; j < num_kv; ++j) {
@@ -935,7 +935,7 @@ attn_bf16_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int st = j % KS;
         mbar_wait(&kv_full[st], (j / KS) & 1);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const int nvalid = min(BKV, len_kv - j * BKV);
           const int n = max(16, (nvalid + 15) & ~15);
           const uint32_t idesc_qk = idesc_bf16_f32(T_BQ, n, 0);
@@ -955,7 +955,7 @@ attn_bf16_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int bf = j & 1;
         mbar_wait(&p_ready[bf], (j >> 1) & 1);  // P_j in TMEM, S buffer bf fully read
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const int st = j % KS;
           const int nvalid = min(BKV, len_kv - j * BKV);
           const int nks = (nvalid + 15) >> 4;  // 16 keys per MMA

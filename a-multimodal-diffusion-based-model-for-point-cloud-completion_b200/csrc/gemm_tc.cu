@@ -99,7 +99,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------- TMA producer -------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -134,7 +134,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = smem_desc_sw128(sa);
           const uint64_t bdesc = smem_desc_sw128(sa + Cfg::A_BYTES);
@@ -201,7 +201,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool first_of_store = (c % CH_PER_STORE) == 0;
         const bool last_of_store = (c % CH_PER_STORE) == CH_PER_STORE - 1;
         if (first_of_store) {
-          if (lane == 0) {
+          if (elect_one()) {
             tma_store_wait_read<0>();  // staging buffer free again
             if (EPI == PCD_EPI_BIAS_RESIDUAL) {
               // residual chunk -> staging buffer (updated in place below).  Not prefetched: the
@@ -256,7 +256,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (last_of_store) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {
             const int col = colbase + (c / CH_PER_STORE) * (OUT_BF16 ? 64 : 32);
             tma_store_2d(&tmC, my_buf + b * G_STAGE_TILE, col, row0);
             tma_store_commit();
@@ -268,7 +268,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
-    if (lane == 0) tma_store_wait_all<0>();  // all output tiles are globally visible
+    if (elect_one()) tma_store_wait_all<0>();  // all output tiles are globally visible
   }
 
   tcgen05_fence_before();
