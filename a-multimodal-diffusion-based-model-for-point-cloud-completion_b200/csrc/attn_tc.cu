@@ -1152,8 +1152,8 @@ static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batc
   return encode_tmap_bf16(m, op->ptr, 4, dims, strides, box);
 }
 
-int g_attn_variant = 4;  // 4: split-row double-buffered (default); 3: double-buffered S/P, 64-key
-                         // tiles, 2 CTAs/SM; 2: ping-pong
+int g_attn_variant = 3;  // 3: double-buffered S/P, 64-key tiles, 2 CTAs/SM (default, fastest measured);
+                         // 4: as 3 with rows split over two softmax threads; 2: ping-pong
                          // over two query tiles; 1: one tile per CTA, P in
                          // TMEM, 2 CTAs/SM; 0: one tile per CTA, P in shared memory (SS MMA)
 

@@ -58,8 +58,8 @@ PCD_API unsigned long long pcd_launch_count(void);
 PCD_API int pcd_check_device(void);
 
 /* Tuning / testing knob (no reference counterpart): tensor-core attention kernel variant,
- * 4 = as 3, with every query row split over two softmax threads (16 softmax warps per SM; default),
- * 3 = one query tile per CTA, 64-key tiles, S and P double-buffered in TMEM, two CTAs per SM,
+ * 3 = one query tile per CTA, 64-key tiles, S and P double-buffered in TMEM, two CTAs per SM (default),
+ * 4 = as 3, with every query row split over two softmax threads (16 softmax warps per SM),
  * 2 = ping-pong over two query tiles per CTA, P in TMEM,
  * 1 = one query tile per CTA, P in TMEM (tcgen05.mma with A from TMEM), two CTAs per SM,
  * 0 = one query tile per CTA, P staged through 128B-swizzled shared memory. */

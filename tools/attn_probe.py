@@ -33,4 +33,4 @@ for v in variants:
     err = float((out[:2].float() - want).norm() / want.norm())
     ms = t(lambda: P.ops.self_attention(qkv, H))
     print(f"variant {v}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  rel err {err:.2e}")
-lib.pcd_set_attention_variant(4)
+lib.pcd_set_attention_variant(3)
