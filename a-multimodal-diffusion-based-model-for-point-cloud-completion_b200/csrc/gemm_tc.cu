@@ -295,7 +295,10 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = G_BM * G_BK * 2;    // 16 KB
   static constexpr int B_BYTES = (BN / 2) * G_BK * 2;  // 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_BYTES = G_EPI_WARPS * G_STAGE_TILE;
+  // two staging tiles per epilogue warp: a TMA store only has to have finished READING its tile
+  // by the time the warp comes back to it two store groups later (the round trip is ~2k cycles)
+  static constexpr int NBUF = 2;
+  static constexpr int OUT_BYTES = G_EPI_WARPS * NBUF * G_STAGE_TILE;
   static constexpr int MISC_BYTES = 512 + 2 * BN * 4;
   static constexpr int BUDGET = 232448 - OUT_BYTES - MISC_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
@@ -418,10 +421,11 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr int CH_PER_STORE = OUT_BF16 ? 2 : 1;
     static_assert(!(EPI == PCD_EPI_BIAS_RESIDUAL && OUT_BF16), "the residual stream is fp32");
     const int etid = threadIdx.x - 64;
-    unsigned char* my_buf = stage_out + ew * G_STAGE_TILE;
+    constexpr int NBUF = Cfg::NBUF;
+    unsigned char* my_buf0 = stage_out + ew * NBUF * G_STAGE_TILE;
+    int sidx = 0;  // running store-group index of this warp
     uint64_t* my_res_bar = res_bar + 2 * ew;
     const int sw = lane & 7;
-    unsigned char* buf_row = my_buf + lane * 128;
     uint32_t res_uses = 0;
     int it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
@@ -453,9 +457,11 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t* r = rbuf[c & 1];
         const bool first_of_store = (c % CH_PER_STORE) == 0;
         const bool last_of_store = (c % CH_PER_STORE) == CH_PER_STORE - 1;
+        unsigned char* my_buf = my_buf0 + (sidx % NBUF) * G_STAGE_TILE;
+        unsigned char* buf_row = my_buf + lane * 128;
         if (first_of_store) {
           if (elect_one()) {
-            tma_store_wait_read<0>();
+            tma_store_wait_read<NBUF - 1>();  // the store that used this tile two groups ago has read it
             if (EPI == PCD_EPI_BIAS_RESIDUAL) {
               mbar_expect_tx(&my_res_bar[0], G_STAGE_TILE);
               tma_load_2d(my_buf, &tmR, &my_res_bar[0], colbase + c * 32, row0);
@@ -511,6 +517,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tma_store_2d(&tmC, my_buf, col, row0);
             tma_store_commit();
           }
+          ++sidx;
         }
       }
       tcgen05_fence_before();
