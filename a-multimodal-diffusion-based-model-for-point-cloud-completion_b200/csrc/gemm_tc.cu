@@ -400,9 +400,11 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t sa = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
             const uint64_t adesc = smem_desc_sw128(sa);
             const uint64_t bdesc = smem_desc_sw128(sa + Cfg::A_BYTES);
+            if (!(dbg & 8)) {  // profiling aid: bit 3 skips the MMAs (epilogue timed without tensor traffic)
 #pragma unroll
-            for (int k = 0; k < G_BK / 16; ++k)
-              umma_bf16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < G_BK / 16; ++k)
+                umma_bf16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
             umma_commit_2sm(&empty[stage], 3);                       // frees the slot in both CTAs
             if (kb == num_kb - 1) umma_commit_2sm(&acc_full[as], 3); // accumulators ready in both CTAs
           }

@@ -23,10 +23,10 @@ for name, N, K, epi, od in (("qkv", 1536, 512, 0, torch.bfloat16), ("proj", 512,
     out = torch.empty(M, N, device=dev, dtype=od)
     fn = lambda: P.ops.linear(a, w, bias, epilogue=epi, residual=res, out_dtype=od, out=out)
     r = {}
-    for flags in (0, 1, 2, 3):
+    for flags in (0, 1, 2, 3, 10):
         lib.pcd_set_debug_flags(flags)
         r[flags] = t(fn)
     lib.pcd_set_debug_flags(0)
     fl = 2.0 * M * N * K
     print(f"{name:5s} N={N} K={K}: full {r[0]*1e3:7.1f}us ({fl/r[0]/1e9:6.0f} TF) | no-epilogue {r[1]*1e3:7.1f}us ({fl/r[1]/1e9:6.0f} TF) | "
-          f"no-TMA {r[2]*1e3:7.1f}us | MMA-only {r[3]*1e3:7.1f}us ({fl/r[3]/1e9:6.0f} TF)")
+          f"no-TMA {r[2]*1e3:7.1f}us | MMA-only {r[3]*1e3:7.1f}us ({fl/r[3]/1e9:6.0f} TF) | epilogue-only {r[10]*1e3:7.1f}us")
