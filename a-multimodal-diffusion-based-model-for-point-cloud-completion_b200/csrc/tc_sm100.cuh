@@ -283,8 +283,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Remote arrive with the default (.release.cta) semantics: the cluster-scope release form makes
+// ptxas emit MEMBAR.ALL.CTA + ERRBAR in front of every arrive (measured: 45 % of the epilogue
+// warps' time).  Nothing written through the generic proxy has to be published here -- the TMEM
+// reads are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of the pair into ITS OWN shared memory; the transaction bytes are
 // credited to the mbarrier at cluster address `mbar_cluster` (the leader CTA's barrier).
