@@ -1315,7 +1315,8 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
   // ragged query tail (<= 8 rows past the last full 128-row tile) -> CUDA-core kernel
   const int tail_rows = len_q % T_BQ;
-  if (g_attn_variant == 3 && len_q > T_BQ && tail_rows > 0 && tail_rows <= 8) {
+  // (disabled: a second pass over K/V for the leftover rows costs as much as the extra query tile)
+  if (false && g_attn_variant == 3 && len_q > T_BQ && tail_rows > 0 && tail_rows <= 8) {
     const int main_rows = len_q - tail_rows;
     rc = launch_attn_tc3(tq, tk, tv, out, o_bs, o_ls, batch, heads, main_rows, len_kv, scale_log2, st, k, v);
     if (rc != PCD_OK) return rc;
