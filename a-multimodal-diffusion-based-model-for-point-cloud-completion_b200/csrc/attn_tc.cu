@@ -24,8 +24,6 @@ namespace pcd {
 using namespace tc;
 
 constexpr int T_BQ = 128, T_BKV = 128, T_HD = 64;
-
-__device__ __forceinline__ void unpack8(const uint4& u, float* f);
 constexpr int T_TILE_BYTES = T_BKV * T_HD * 2;  // 16 KB (Q, K and V tiles alike)
 
 template <bool P_TMEM>
@@ -582,13 +580,8 @@ struct Attn3Cfg {
 __global__ void __launch_bounds__(256, 2)
 attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs,
-                     int64_t o_ls, int len_q, int len_kv_total, float scale_log2, int kv_tail,
-                     const uint16_t* __restrict__ kg, int64_t k_bs, int64_t k_ls, int64_t k_hs,
-                     const uint16_t* __restrict__ vg, int64_t v_bs, int64_t v_ls, int64_t v_hs) {
+                     int64_t o_ls, int len_q, int len_kv, float scale_log2) {
   using Cfg = Attn3Cfg;
-  // the last `kv_tail` (<= 4) keys are folded in by the softmax threads on the CUDA cores after
-  // the tile loop instead of costing a whole pipeline iteration (L = 16 x 64 + 2 prefix tokens)
-  const int len_kv = len_kv_total - kv_tail;
   constexpr int KS = Cfg::KV_STAGES;
   constexpr int BKV = Cfg::BKV;
   extern __shared__ unsigned char smem_raw[];
@@ -786,43 +779,6 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[bf]);
       }
-      // tail keys: logits and probabilities of this thread's row on the CUDA cores
-      float p_tail[4] = {0.f, 0.f, 0.f, 0.f};
-      float o_scale = 1.f;
-      if (kv_tail > 0) {
-        mbar_wait(q_full, 0);  // (long complete) makes the TMA-written Q tile visible to this thread
-        float qf[T_HD];
-        const unsigned char* qrow = sQ + row_in_tile * 128;  // TMA 128B swizzle: chunk ^= row & 7
-#pragma unroll
-        for (int c = 0; c < T_HD / 8; ++c)
-          unpack8(*reinterpret_cast<const uint4*>(qrow + ((c ^ (row_in_tile & 7)) << 4)), qf + c * 8);
-        const uint16_t* kb = kg + b * k_bs + h * k_hs;
-        for (int t = 0; t < kv_tail; ++t) {
-          const uint16_t* kr = kb + (int64_t)(len_kv + t) * k_ls;
-          float sdot = 0.f;
-#pragma unroll
-          for (int c = 0; c < T_HD / 8; ++c) {
-            float kf[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(kr + c * 8)), kf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sdot = fmaf(qf[c * 8 + i], kf[i], sdot);
-          }
-          const float s2 = sdot * scale_log2;
-          if (s2 > m_used + kRescaleThreshold) {  // keep exp2 arguments bounded
-            const float a = ex2_approx(m_used - s2);
-            l_run *= a;
-            o_scale *= a;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) p_tail[u] *= a;
-            m_used = s2;
-          }
-          const float pt = ex2_approx(s2 - m_used);
-          l_run += pt;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (u == t) p_tail[u] = pt;
-        }
-      }
       // epilogue: O / l
       mbar_wait(&pv_done[(num_kv - 1) & 1], ((num_kv - 1) >> 1) & 1);
       tcgen05_fence_after();
@@ -839,19 +795,7 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int i = 0; i < 32; i += 8) {
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[i + u]) * o_scale;
-            for (int t = 0; t < kv_tail; ++t) {
-              float vf[8];
-              unpack8(__ldg(reinterpret_cast<const uint4*>(vg + b * v_bs + h * v_hs + (int64_t)(len_kv + t) * v_ls + c * 32 + i)), vf);
-              float pt = p_tail[0];
-              if (t == 1) pt = p_tail[1];
-              if (t == 2) pt = p_tail[2];
-              if (t == 3) pt = p_tail[3];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] = fmaf(pt, vf[u], v[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] *= inv;
+            for (int u = 0; u < 8; ++u) v[u] = __uint_as_float(r[i + u]) * inv;
             *reinterpret_cast<uint4*>(orow + c * 32 + i) =
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           }
@@ -870,11 +814,7 @@ attn_bf16_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 static int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
                            int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv,
-                           float scale_log2, cudaStream_t st, const pcd_attn_operand* k = nullptr,
-                           const pcd_attn_operand* v = nullptr) {
-  // <= 4 keys past the last full 64-key tile are handled on the CUDA cores inside the kernel
-  int kv_tail = len_kv % Attn3Cfg::BKV;
-  if (k == nullptr || kv_tail > 4 || len_kv <= Attn3Cfg::BKV) kv_tail = 0;
+                           float scale_log2, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bf16_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg::SMEM_BYTES);
@@ -885,10 +825,7 @@ static int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const C
     attr_set = true;
   }
   dim3 grid(ceil_div(len_q, T_BQ), heads, batch);
-  attn_bf16_tc3_kernel<<<grid, 256, Attn3Cfg::SMEM_BYTES, st>>>(
-      tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2, kv_tail,
-      k ? (const uint16_t*)k->ptr : nullptr, k ? k->batch_stride : 0, k ? k->row_stride : 0, k ? k->head_stride : 0,
-      v ? (const uint16_t*)v->ptr : nullptr, v ? v->batch_stride : 0, v ? v->row_stride : 0, v ? v->head_stride : 0);
+  attn_bf16_tc3_kernel<<<grid, 256, Attn3Cfg::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2);
   PCD_CHECK_LAUNCH("attention_bf16");
   return PCD_OK;
 }
@@ -1208,88 +1145,6 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   return PCD_OK;
 }
 
-// ---------------------------------------------------------------------------
-// Ragged query tail.  L = 1026 = 8 x 128 + 2 (time + CLIP token in front of 1024 points): a 9th
-// tensor-core query tile would run the whole KV pipeline for two rows (11 % of the CTAs).  The
-// few leftover rows are instead computed by one warp each on the CUDA cores: lanes stride over
-// the keys with a private online softmax (fp32), then the 32 partial (m, l, o[64]) states are
-// merged with shuffles.  Same bf16 inputs, fp32 accumulation.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-
-__global__ void __launch_bounds__(32) attn_tail_rows_kernel(
-    const uint16_t* __restrict__ q, int64_t q_bs, int64_t q_ls, int64_t q_hs,
-    const uint16_t* __restrict__ k, int64_t k_bs, int64_t k_ls, int64_t k_hs,
-    const uint16_t* __restrict__ v, int64_t v_bs, int64_t v_ls, int64_t v_hs,
-    uint16_t* __restrict__ out, int64_t o_bs, int64_t o_ls, int row0, int len_kv, float scale_log2) {
-  const int lane = threadIdx.x;
-  const int row = row0 + blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const uint16_t* qr = q + b * q_bs + (int64_t)row * q_ls + h * q_hs;
-  float qf[T_HD];
-#pragma unroll
-  for (int c = 0; c < T_HD / 8; ++c) {
-    unpack8(*reinterpret_cast<const uint4*>(qr + c * 8), qf + c * 8);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qf[c * 8 + i] *= scale_log2;
-  }
-  float m = -INFINITY, l = 0.f, o[T_HD];
-#pragma unroll
-  for (int c = 0; c < T_HD; ++c) o[c] = 0.f;
-  const uint16_t* kb = k + b * k_bs + h * k_hs;
-  const uint16_t* vb = v + b * v_bs + h * v_hs;
-  for (int key = lane; key < len_kv; key += 32) {
-    const uint16_t* kr = kb + (int64_t)key * k_ls;
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < T_HD / 8; ++c) {
-      float kf[8];
-      unpack8(*reinterpret_cast<const uint4*>(kr + c * 8), kf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s = fmaf(qf[c * 8 + i], kf[i], s);
-    }
-    if (s > m) {  // rescale only when the running maximum moves
-      const float a = ex2_approx(m - s);
-      l *= a;
-#pragma unroll
-      for (int c = 0; c < T_HD; ++c) o[c] *= a;
-      m = s;
-    }
-    const float p = ex2_approx(s - m);
-    l += p;
-    const uint16_t* vr = vb + (int64_t)key * v_ls;
-#pragma unroll
-    for (int c = 0; c < T_HD / 8; ++c) {
-      float vf[8];
-      unpack8(*reinterpret_cast<const uint4*>(vr + c * 8), vf);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[c * 8 + i] = fmaf(p, vf[i], o[c * 8 + i]);
-    }
-  }
-  // merge the 32 partial states
-  const float mg = warp_max(m);
-  const float a = (m == -INFINITY) ? 0.f : ex2_approx(m - mg);
-  l = warp_sum(l * a);
-  const float inv = 1.f / l;
-  float mine0 = 0.f, mine1 = 0.f;
-#pragma unroll
-  for (int c = 0; c < T_HD; ++c) {
-    const float t = warp_sum(o[c] * a);
-    if ((c >> 1) == lane) {
-      if (c & 1) mine1 = t; else mine0 = t;
-    }
-  }
-  uint32_t* orow = reinterpret_cast<uint32_t*>(out + b * o_bs + (int64_t)row * o_ls + h * T_HD);
-  orow[lane] = pack_bf16x2(mine0 * inv, mine1 * inv);
-}
-
 static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batch, int heads, int len, int box_rows) {
   uint64_t dims[4] = {T_HD, (uint64_t)heads, (uint64_t)len, (uint64_t)batch};
   uint64_t strides[3] = {(uint64_t)op->head_stride * 2, (uint64_t)op->row_stride * 2, (uint64_t)op->batch_stride * 2};
@@ -1313,25 +1168,10 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
   if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
-  // ragged query tail (<= 8 rows past the last full 128-row tile) -> CUDA-core kernel
-  const int tail_rows = len_q % T_BQ;
-  // (disabled: a second pass over K/V for the leftover rows costs as much as the extra query tile)
-  if (false && g_attn_variant == 3 && len_q > T_BQ && tail_rows > 0 && tail_rows <= 8) {
-    const int main_rows = len_q - tail_rows;
-    rc = launch_attn_tc3(tq, tk, tv, out, o_bs, o_ls, batch, heads, main_rows, len_kv, scale_log2, st, k, v);
-    if (rc != PCD_OK) return rc;
-    attn_tail_rows_kernel<<<dim3(tail_rows, heads, batch), 32, 0, st>>>(
-        (const uint16_t*)q->ptr, q->batch_stride, q->row_stride, q->head_stride,
-        (const uint16_t*)k->ptr, k->batch_stride, k->row_stride, k->head_stride,
-        (const uint16_t*)v->ptr, v->batch_stride, v->row_stride, v->head_stride, out, o_bs, o_ls, main_rows,
-        len_kv, scale_log2);
-    PCD_CHECK_LAUNCH("attention_bf16(tail rows)");
-    return PCD_OK;
-  }
   if (g_attn_variant == 4)
     return launch_attn_tc4(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 3)
-    return launch_attn_tc3(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st, k, v);
+    return launch_attn_tc3(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 2)
     return launch_attn_tc2(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 1)
