@@ -27,7 +27,14 @@ METRIC = "completed clouds/sec (64-step Heun, 1024 pts)"
 UNIT = "clouds/s"
 WORKLOADS = {
     # name: (model config, diffusion config, per-GPU batch, sigma_max, s_churn, guidance)
+    # BASELINE.json configs[1] -- the configuration the headline metric is quoted on:
     "base40M-imagevec-1024pt-b64": ("base40M-imagevec", "base40M-imagevec", 64, 120.0, 3.0, 3.0),
+    # configs[2] (i): text-conditioned = same network fed a CLIP text vector (base40M-textvec)
+    "base40M-textvec-1024pt-b32": ("base40M-textvec", "base40M-textvec", 32, 120.0, 3.0, 3.0),
+    # configs[3]: upsampler 1024 -> 4096 points (L = 4353), unguided like the reference's text2pc stage 2
+    "upsample-4096pt-b16": ("upsample", "upsample", 16, 160.0, 0.0, 0.0),
+    # configs[4]: 300M denoiser (width 1024, 24 layers) with image grid + partial-cloud conditioning
+    "base300M-upsample-4096pt-b8": ("base300M-upsample", "upsample", 8, 160.0, 0.0, 3.0),
 }
 
 
@@ -98,6 +105,7 @@ def cpu_sample(workload, heun_steps=4, threads=None):
     from test_oracle_golden import shapes_of
 
     mcfg, dcfg, _, smax, churn, guidance = WORKLOADS[workload]
+    assert mcfg.startswith("base40M-"), "the CPU leg covers the base40M vector-conditioned workloads"
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     cfg = dict(cases.MODEL_CONFIGS[mcfg])
@@ -244,9 +252,14 @@ def run_b200(args):
     mcfg, dcfg, B, smax, churn, guidance = WORKLOADS[args.workload]
     if args.batch:
         B = args.batch
-    cfg = P.MODEL_CONFIGS[mcfg]
+    if mcfg == "base300M-upsample":  # grid-upsample class with base300M dims
+        cfg = dict(P.MODEL_CONFIGS["upsample"], width=1024, layers=24, heads=16)
+    else:
+        cfg = P.MODEL_CONFIGS[mcfg]
     torch.manual_seed(1234 + rank)
     model = P.model_from_config(cfg, dev, dtype=torch.bfloat16)
+    if hasattr(model, "accept_grid_embeddings"):
+        model.accept_grid_embeddings = True
     with torch.no_grad():  # reference init + re-randomised output_proj
         model.output_proj.weight.normal_(std=0.02)
     diffusion = P.diffusion_from_config(P.DIFFUSION_CONFIGS[dcfg])
@@ -254,23 +267,42 @@ def run_b200(args):
     sampler = P.PointCloudSampler(dev, [model], [diffusion], [N], ["R", "G", "B"], guidance_scale=[guidance],
                                   use_karras=[True], karras_steps=[64], sigma_min=[1e-3], sigma_max=[smax],
                                   s_churn=[churn], use_cuda_graph=True)
-    emb_host = torch.randn(B, 768)
-    emb_host = (emb_host / emb_host.norm(dim=1, keepdim=True)).pin_memory()
-    emb_dev = emb_host.to(dev)
-    out_host = torch.empty(B, Cc, N).pin_memory()
-    gathered = torch.empty(world * B, Cc, N, device=dev) if world > 1 else None
+    # synthetic conditioning: unit-norm CLIP vectors, N(0,1) CLIP grids, U(-0.5,0.5) xyz +
+    # U(0,255) rgb partial clouds
+    cls = cfg["name"]
+    host_kw = {}
+    if cls == "CLIPImagePointDiffusionTransformer":
+        e = torch.randn(B, 768)
+        host_kw["embeddings"] = e / e.norm(dim=1, keepdim=True)
+    if "Grid" in cls:
+        host_kw["embeddings"] = torch.randn(B, 1024, 256)
+    if "Upsample" in cls:
+        lr = torch.rand(B, Cc, cfg["cond_ctx"]) - 0.5
+        lr[:, 3:] = (lr[:, 3:] + 0.5) * 255.0
+        host_kw["low_res"] = lr
+    host_kw = {k: v.pin_memory() for k, v in host_kw.items()}
+    dev_kw = {k: v.to(dev) for k, v in host_kw.items()}
+    n_out = N + (cfg["cond_ctx"] if "Upsample" in cls else 0)
+    out_host = torch.empty(B, Cc, n_out).pin_memory()
+    gathered = None
 
     def step_device():
-        y = sampler.sample_batch(B, dict(embeddings=emb_dev))
+        y = sampler.sample_batch(B, dict(dev_kw))
         if world > 1:
-            dist.all_gather_into_tensor(gathered, y.contiguous())
+            gather(y)
         return y
 
+    def gather(y):
+        nonlocal gathered
+        if gathered is None:
+            gathered = torch.empty((world * y.shape[0],) + tuple(y.shape[1:]), device=dev)
+        dist.all_gather_into_tensor(gathered, y.contiguous())
+
     def step_e2e():
-        e = emb_host.to(dev, non_blocking=True)
-        y = sampler.sample_batch(B, dict(embeddings=e))
+        kw = {k: v.to(dev, non_blocking=True) for k, v in host_kw.items()}
+        y = sampler.sample_batch(B, kw)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, y.contiguous())
+            gather(y)
         out_host.copy_(y, non_blocking=False)  # device -> host read of the step's result
         return out_host
 
@@ -310,24 +342,28 @@ def run_b200(args):
 
     value = world * B * args.steps / t_dev
     e2e_value = world * B * args.steps / t_e2e
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    metric = METRIC if n_out == 1024 else METRIC.replace("1024 pts", f"{n_out} pts")
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "per_gpu_batch": B, "global_batch": world * B,
-                       "points": N, "heun_steps": 64, "denoiser_evals_per_step": 127,
-                       "sequences_per_eval": 2 * B, "seq_len": N + 2, "guidance": guidance, "s_churn": churn,
+                       "points": n_out, "heun_steps": 64, "denoiser_evals_per_step": 127,
+                       "sequences_per_eval": (2 if guidance not in (0.0, 1.0) else 1) * B,
+                       "seq_len": model._prefix_layout()[0] + N, "guidance": guidance, "s_churn": churn,
                        "cache": "activations per forward (1.5 GB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"batch-sharded x{world}, all-gather of finished clouds"},
             "denoiser_ms_per_heun_step": 1e3 * t_dev / args.steps / 64,
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": emb_host.numel() * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sum(v.numel() * 4 for v in host_kw.values()),
                     "d2h_bytes_per_step": out_host.numel() * 4},
             "gpu_launches": launches_per_step * args.steps}
     if rank == 0:
         pk = peaks()
         clk_mhz = clk.get("sm_mhz")
         try:
-            kb = kernel_breakdown(P, model, 2 * B, N + 2, cfg["width"], cfg["heads"], cfg["layers"], B, Cc, N, pk)
+            seqs_eval = (2 if guidance not in (0.0, 1.0) else 1) * B
+            kb = kernel_breakdown(P, model, seqs_eval, model._prefix_layout()[0] + N, cfg["width"], cfg["heads"],
+                                  cfg["layers"], B, Cc, N, pk)
             dom = max((k for k in kb if kb[k]["launches_per_step"]), key=lambda k: kb[k]["ms_per_step"])
             if dom == "flash_attention":
                 # hd = 64 attention is bound by the 16 ex2/clk/SM special-function rate (tools/ubench),
@@ -350,8 +386,13 @@ def run_b200(args):
         except Exception as ex:  # the headline number must still be printed
             line["roofline"] = {"error": repr(ex)}
         if world == 1 and not args.no_cpu:
-            base, _ = cpu_sample(args.workload, heun_steps=4)
-            line["cpu_baseline"] = base
+            if args.workload.startswith("base40M"):
+                base, _ = cpu_sample(args.workload, heun_steps=4)
+                line["cpu_baseline"] = base
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "not timed for this workload (CPU leg implemented for the "
+                                                  "headline base40M workloads only)"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
