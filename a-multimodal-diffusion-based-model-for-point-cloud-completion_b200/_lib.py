@@ -26,7 +26,7 @@ class AttnOperand(C.Structure):
 
 class StepScalars(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("c_in", "coef_x", "coef_eps", "sigma", "dt", "guidance",
-                                          "clip", "next_c_in", "next_noise")]
+                                          "clip", "next_c_in", "next_noise", "dt2", "mode")]
 
 
 class BlockWeights(C.Structure):

@@ -144,8 +144,13 @@ __global__ void __launch_bounds__(256) sampler_corrector_kernel(
     float x2 = __fadd_rn(xv[j], __fmul_rn(dv[j], s.dt));
     float x0 = denoised(x2, ec[j], guided ? eu[j] : 0.f, guided != 0, s);
     float d2 = __fdiv_rn(__fsub_rn(x2, x0), s.sigma);
-    float dp = __fmul_rn(__fadd_rn(dv[j], d2), 0.5f);  // (d + d_2) / 2
-    float xn = __fadd_rn(xv[j], __fmul_rn(dp, s.dt));
+    float xn;
+    if (s.mode != 0.f) {
+      xn = __fadd_rn(xv[j], __fmul_rn(d2, s.dt2));        // DPM-2: x + d_2 * dt_2
+    } else {
+      float dp = __fmul_rn(__fadd_rn(dv[j], d2), 0.5f);   // Heun: (d + d_2) / 2
+      xn = __fadd_rn(xv[j], __fmul_rn(dp, s.dt));
+    }
     if (s.next_noise != 0.f) xn = __fadd_rn(xn, __fmul_rn(nz[j], s.next_noise));
     xv[j] = xn;
     mv[j] = __fmul_rn(xn, s.next_c_in);

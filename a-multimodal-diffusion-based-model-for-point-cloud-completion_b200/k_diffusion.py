@@ -44,6 +44,33 @@ def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
     return append_zero(sigmas).to(device)
 
 
+class KarrasDenoiser:
+    """EDM preconditioning (reference k_diffusion.py:31-76).  ``get_scalings`` feeds the fused
+    sampler kernels (coef_x = c_skip/c_in, coef_eps = -c_out); ``denoise`` is the plain call."""
+
+    def __init__(self, sigma_data: float = 0.5):
+        self.sigma_data = sigma_data
+
+    def get_snr(self, sigmas):
+        return sigmas ** -2
+
+    def get_sigmas(self, sigmas):
+        return sigmas
+
+    def get_scalings(self, sigma):
+        c_skip = self.sigma_data ** 2 / (sigma ** 2 + self.sigma_data ** 2)
+        c_out = sigma * self.sigma_data / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        c_in = 1 / (sigma ** 2 + self.sigma_data ** 2) ** 0.5
+        return c_skip, c_out, c_in
+
+    def denoise(self, model, x_t, sigmas, **model_kwargs):
+        c_skip, c_out, c_in = [append_dims(x, x_t.ndim) for x in self.get_scalings(sigmas)]
+        rescaled_t = 1000 * 0.25 * th.log(sigmas + 1e-44)
+        model_output = model(c_in * x_t, rescaled_t, **model_kwargs)
+        denoised = c_out * model_output + c_skip * x_t
+        return model_output, denoised
+
+
 class GaussianToKarrasDenoiser:
     """sigma -> integer timestep lookup (reference k_diffusion.py:79-103)."""
 
@@ -72,7 +99,7 @@ class GaussianToKarrasDenoiser:
 @dataclass
 class HeunEval:
     sigma: float      # sigma of this denoiser evaluation (fp32 value)
-    t: int            # truncated integer timestep
+    t: float          # truncated integer timestep (GaussianDiffusion) or 250*ln(sigma) (KarrasDenoiser)
     c_in: float
     coef_x: float
     coef_eps: float
@@ -88,21 +115,38 @@ class HeunStep:
     second: Optional[HeunEval]   # None on the last (Euler) step
 
 
-class HeunPlan:
-    """All host-side scalars of ``sample_heun`` for one stage."""
+def get_ancestral_step(sigma_from, sigma_to):
+    """reference k_diffusion.py:239-245."""
+    sigma_up = (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
 
-    def __init__(self, diffusion: GaussianDiffusion, steps: int, sigma_min: float, sigma_max: float,
+
+class HeunPlan:
+    """All host-side scalars of one stage for ``sampler`` in {"heun", "dpm", "ancestral"}
+    (reference sample_heun :270-310, sample_dpm :313-351, sample_euler_ancestral :248-266)."""
+
+    def __init__(self, diffusion, steps: int, sigma_min: float, sigma_max: float,
                  rho: float = 7.0, s_churn: float = 0.0, s_tmin: float = 0.0,
-                 s_tmax: float = float("inf"), s_noise: float = 1.0):
+                 s_tmax: float = float("inf"), s_noise: float = 1.0, sampler: str = "heun"):
         if s_noise != 1.0:
             raise NotImplementedError("s_noise != 1 (the reference never changes it)")
+        if sampler not in ("heun", "dpm", "ancestral"):
+            raise KeyError(sampler)
+        self.sampler = sampler
         self.sigmas = get_sigmas_karras(steps, sigma_min, sigma_max, rho)  # CPU fp32 [steps+1]
         self.sigma_max = sigma_max
-        wrap = GaussianToKarrasDenoiser(None, diffusion)
+        self.karras = isinstance(diffusion, KarrasDenoiser)
+        wrap = None if self.karras else GaussianToKarrasDenoiser(None, diffusion)
         sig = self.sigmas
         n = len(sig) - 1
 
         def make_eval(s: th.Tensor) -> HeunEval:
+            if self.karras:
+                # x0 = c_out*F + c_skip*x = (c_skip/c_in)*(x*c_in) - (-c_out)*F   (k_diffusion.py:71-76)
+                c_skip, c_out, c_in = diffusion.get_scalings(s)
+                t = float(1000 * 0.25 * th.log(s + 1e-44))
+                return HeunEval(float(s), t, float(c_in), float(c_skip / c_in), float(-c_out))
             t = wrap.sigma_to_int_t(s.numpy())
             c_in = 1.0 / (s ** 2 + 1) ** 0.5
             a = np.float32(diffusion.sqrt_recip_alphas_cumprod[t])
@@ -111,9 +155,23 @@ class HeunPlan:
 
         self.steps: List[HeunStep] = []
         for i in range(n):
+            if sampler == "ancestral":
+                sigma_down, sigma_up = get_ancestral_step(sig[i], sig[i + 1])
+                st = HeunStep(float(sig[i]), float(sig[i]), 0.0, float(sigma_down - sig[i]), make_eval(sig[i]), None)
+                st.sigma_up = float(sigma_up)
+                self.steps.append(st)
+                continue
             gamma = min(s_churn / n, 2 ** 0.5 - 1) if s_tmin <= sig[i] <= s_tmax else 0.0
             sigma_hat = sig[i] * (gamma + 1)
             noise = float((sigma_hat ** 2 - sig[i] ** 2) ** 0.5) if gamma > 0 else 0.0
+            if sampler == "dpm":
+                # midpoint chosen on a rho=3 Karras schedule; the second evaluation always happens
+                sigma_mid = ((sigma_hat ** (1 / 3) + sig[i + 1] ** (1 / 3)) / 2) ** 3
+                st = HeunStep(float(sig[i]), float(sigma_hat), noise, float(sigma_mid - sigma_hat),
+                              make_eval(sigma_hat), make_eval(sigma_mid))
+                st.dt2 = float(sig[i + 1] - sigma_hat)
+                self.steps.append(st)
+                continue
             dt = sig[i + 1] - sigma_hat
             second = None if sig[i + 1] == 0 else make_eval(sig[i + 1])
             self.steps.append(HeunStep(float(sig[i]), float(sigma_hat), noise, float(dt),
@@ -123,7 +181,7 @@ class HeunPlan:
     def num_evals(self) -> int:
         return sum(1 + (s.second is not None) for s in self.steps)
 
-    def eval_timesteps(self) -> List[int]:
+    def eval_timesteps(self) -> List[float]:
         out = []
         for s in self.steps:
             out.append(s.first.t)
@@ -148,20 +206,31 @@ class HeunState:
         self.d = th.empty(shape, device=device, dtype=th.float32)
         self.model_in = th.empty(shape, device=device, dtype=th.float32)
         f32 = dict(device=device, dtype=th.float32)
-        self.ch_scale = None if diffusion.channel_scales is None else th.tensor(diffusion.channel_scales, **f32)
-        self.ch_bias = None if diffusion.channel_biases is None else th.tensor(diffusion.channel_biases, **f32)
+        scales = getattr(diffusion, "channel_scales", None)
+        biases = getattr(diffusion, "channel_biases", None)
+        self.ch_scale = None if scales is None else th.tensor(scales, **f32)
+        self.ch_bias = None if biases is None else th.tensor(biases, **f32)
 
-    def _scal(self, ev: Optional[HeunEval], dt: float, nxt: Optional[HeunEval], next_noise: float):
+    def _scal(self, ev: Optional[HeunEval], dt: float, nxt: Optional[HeunEval], next_noise: float,
+              dt2: float = 0.0, mode: float = 0.0):
         return step_scalars(c_in=ev.c_in if ev else 0.0, coef_x=ev.coef_x if ev else 0.0,
                             coef_eps=ev.coef_eps if ev else 0.0, sigma=ev.sigma if ev else 0.0, dt=dt,
                             guidance=self.guidance, clip=self.clip,
-                            next_c_in=nxt.c_in if nxt else 0.0, next_noise=next_noise)
+                            next_c_in=nxt.c_in if nxt else 0.0, next_noise=next_noise, dt2=dt2, mode=mode)
 
     def begin(self, noise0: th.Tensor):
         """x <- x_T (+ churn of step 0); model_in <- x * c_in(sigma_hat_0)."""
         st = self.plan.steps[0]
         s = self._scal(None, 0.0, st.first, st.noise_scale)
         check(self.lib.pcd_sampler_begin(ptr(self.x), ptr(noise0), ptr(self.model_in), C.byref(s),
+                                         self.x.numel(), stream_ptr()), "sampler_begin")
+
+    def renoise(self, noise: th.Tensor, sigma_up: float, nxt: Optional[HeunEval]):
+        """Euler-ancestral: x <- x + noise*sigma_up; model_in <- x*c_in(next sigma)."""
+        s = self._scal(None, 0.0, nxt, sigma_up)
+        if nxt is None and sigma_up == 0.0:
+            return
+        check(self.lib.pcd_sampler_begin(ptr(self.x), ptr(noise), ptr(self.model_in), C.byref(s),
                                          self.x.numel(), stream_ptr()), "sampler_begin")
 
     def predictor(self, i: int, model_out: th.Tensor, pred_out: th.Tensor):
@@ -176,8 +245,10 @@ class HeunState:
 
     def corrector(self, i: int, model_out: th.Tensor, next_noise: Optional[th.Tensor]):
         st = self.plan.steps[i]
-        nxt = self.plan.steps[i + 1]
-        s = self._scal(st.second, st.dt, nxt.first, nxt.noise_scale)
+        nxt = self.plan.steps[i + 1] if i + 1 < len(self.plan.steps) else None
+        dpm = self.plan.sampler == "dpm"
+        s = self._scal(st.second, st.dt, nxt.first if nxt else None, nxt.noise_scale if nxt else 0.0,
+                       dt2=getattr(st, "dt2", 0.0), mode=1.0 if dpm else 0.0)
         assert model_out.is_contiguous()
         check(self.lib.pcd_sampler_corrector(ptr(self.x), ptr(model_out), model_out.shape[1], int(self.guided),
                                              ptr(self.d), ptr(next_noise), ptr(self.model_in), C.byref(s),
@@ -189,7 +260,7 @@ def _native(model) -> bool:
 
 
 def make_denoiser_eval(model, model_kwargs: Dict[str, Any], B: int, guided: bool, device,
-                       eps_channels: Optional[int] = None) -> Callable:
+                       eps_channels: Optional[int] = None, karras: bool = False) -> Callable:
     """Returns eval(model_in [B,C,N], t:int) -> model output [B or 2B, C_out, N] (contiguous fp32).
 
     Native modules evaluate the conditional and unconditional halves as ONE 2B-sequence
@@ -214,7 +285,8 @@ def make_denoiser_eval(model, model_kwargs: Dict[str, Any], B: int, guided: bool
         return out.float()
 
     def eval_generic(model_in, t):
-        tt = th.full((B,), int(t), dtype=th.long, device=device)
+        tt = (th.full((B,), int(t), dtype=th.long, device=device) if float(t).is_integer() and not karras
+              else th.full((B,), float(t), dtype=th.float32, device=device))
         if not guided:
             kw = {k: v for k, v in model_kwargs.items() if k != "prev_latent"}
             return call(model_in, tt, kw, "cond").contiguous()
@@ -249,42 +321,68 @@ def karras_sample_progressive(
     """Same signature and yields as the reference (k_diffusion.py:118-222).  ``noise_fn(shape)``
     optionally replaces the torch RNG draws (draw #0 for x_T, then one per step, in the
     reference's order, k_diffusion.py:139,292)."""
-    if sampler != "heun":
-        raise NotImplementedError(f"sampler={sampler!r}: only the Heun solver is fused so far")
-    if not isinstance(diffusion, GaussianDiffusion):
-        raise NotImplementedError("only GaussianDiffusion-wrapped models are supported")
+    if sampler not in ("heun", "dpm", "ancestral"):
+        raise KeyError(sampler)
+    karras = isinstance(diffusion, KarrasDenoiser)
+    if not karras and not isinstance(diffusion, GaussianDiffusion):
+        raise NotImplementedError
+    guided = guidance_scale != 0 and guidance_scale != 1
+    if karras and guided:
+        raise NotImplementedError("classifier-free guidance needs a GaussianDiffusion-wrapped model "
+                                  "(the reference's guided path calls model.denoise, k_diffusion.py:194)")
     device = th.device(device if device is not None else "cuda")
     require_cuda()
     if noise_fn is None:
         noise_fn = lambda shp: th.randn(*shp, device=device)
-    plan = HeunPlan(diffusion, steps, sigma_min, sigma_max, rho, s_churn, s_tmin, s_tmax, s_noise)
+    if sampler == "ancestral":
+        plan = HeunPlan(diffusion, steps, sigma_min, sigma_max, rho, sampler=sampler)
+    else:
+        plan = HeunPlan(diffusion, steps, sigma_min, sigma_max, rho, s_churn, s_tmin, s_tmax, s_noise, sampler)
     B = shape[0]
     state = HeunState(diffusion, plan, tuple(shape), device, guidance_scale, clip_denoised)
-    evaluate = make_denoiser_eval(model, model_kwargs, B, state.guided, device,
-                                  shape[1] if diffusion.eps_channels_doubled else None)
+    eps_ch = shape[1] if (karras or diffusion.eps_channels_doubled) else None
+    evaluate = make_denoiser_eval(model, model_kwargs, B, state.guided, device, eps_ch, karras)
+    unscale = (lambda v: v) if karras else diffusion.unscale_channels
+    f32 = lambda v: th.tensor(v)
 
     with th.no_grad():
         state.x.copy_(noise_fn(tuple(shape)).to(device) * sigma_max)
-        eps = noise_fn(tuple(shape)).to(device)  # always drawn, even when gamma == 0
-        state.begin(eps)
         indices = range(len(plan.steps))
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
         pred = None
+        if sampler == "ancestral":
+            # reference k_diffusion.py:248-266: no churn, one evaluation per step, fresh noise after it
+            state.renoise(state.x, 0.0, plan.steps[0].first)  # model_in <- x * c_in(sigma_0)
+            for i in indices:
+                st = plan.steps[i]
+                out = evaluate(state.model_in, st.first.t)
+                x_before = state.x.clone()
+                pred = th.empty_like(state.x)
+                last_flag = st.second  # always None: the predictor applies the Euler step in place
+                state.predictor(i, out, pred)
+                yield {"x": unscale(x_before), "i": i, "sigma": f32(st.sigma), "sigma_hat": f32(st.sigma),
+                       "pred_xstart": pred}
+                nxt = plan.steps[i + 1].first if i + 1 < len(plan.steps) else None
+                state.renoise(noise_fn(tuple(shape)).to(device), st.sigma_up, nxt)
+            yield {"x": unscale(state.x.clone()), "pred_xstart": unscale(state.x.clone())}
+            return
+        eps = noise_fn(tuple(shape)).to(device)  # always drawn, even when gamma == 0
+        state.begin(eps)
+        key = "denoised" if sampler == "dpm" else "pred_xstart"
         for i in indices:
             st = plan.steps[i]
             out = evaluate(state.model_in, st.first.t)
             x_hat = state.x.clone()  # the reference yields x after churn, before the update
             pred = th.empty_like(state.x)
             state.predictor(i, out, pred)
-            yield {"x": diffusion.unscale_channels(x_hat), "i": i, "sigma": th.tensor(st.sigma),
-                   "sigma_hat": th.tensor(st.sigma_hat), "pred_xstart": pred}
+            yield {"x": unscale(x_hat), "i": i, "sigma": f32(st.sigma), "sigma_hat": f32(st.sigma_hat), key: pred}
             if st.second is not None:
                 out2 = evaluate(state.model_in, st.second.t)
-                nxt = noise_fn(tuple(shape)).to(device)
+                nxt = noise_fn(tuple(shape)).to(device) if i + 1 < len(plan.steps) else None
                 state.corrector(i, out2, nxt)
-        yield {"x": diffusion.unscale_channels(state.x.clone()), "pred_xstart": pred}
+        yield {"x": unscale(state.x.clone()), "pred_xstart": pred}
 
 
 def karras_sample(*args, **kwargs):

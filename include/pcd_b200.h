@@ -172,6 +172,9 @@ typedef struct {
   float clip;         /* 1: clamp x0 to [-1,1] (clip_denoised), 0: no clamp                  */
   float next_c_in;    /* c_in of the NEXT evaluation (prescale of the next model input)     */
   float next_noise;   /* sqrt(sigma_hat^2 - sigma^2) of the next step's churn (0: none)     */
+  float dt2;          /* DPM-2 only: sigma_{i+1} - sigma_hat_i (dt is then sigma_mid - sigma_hat_i) */
+  float mode;         /* corrector: 0 = Heun average (k_diffusion.py:305-309), 1 = DPM-2 midpoint
+                         update x <- x + d_2*dt2 (k_diffusion.py:343-350)                    */
 } pcd_step_scalars;
 
 /* Start of the loop: x <- x + noise*s.next_noise (if != 0); model_in <- x*s.next_c_in. */

@@ -63,6 +63,7 @@ FORWARD_CASES = {
     "small_upsample_grid": (small_cfg("upsample"), 2, 107, "unit"),
     "small_xyz_only": (small_cfg("base40M-uncond", input_channels=3, output_channels=6,
                                  n_ctx=100), 2, 108, "unit"),
+    "small_uncond_c6": (small_cfg("base40M-uncond", output_channels=6), 2, 110, "unit"),
     "full_imagevec": (copy.deepcopy(MODEL_CONFIGS["base40M-imagevec"]), 2, 201, "reference"),
     "full_upsample": (copy.deepcopy(MODEL_CONFIGS["upsample"]), 1, 202, "reference"),
     "full_base300M": (copy.deepcopy(MODEL_CONFIGS["base300M"]), 1, 203, "reference"),
@@ -152,3 +153,15 @@ class DetNoise:
         out = det.normal(tuple(shape), self.seed * 1000 + self.count)
         self.count += 1
         return out
+
+
+# solver cases through the reference's karras_sample_progressive (no PointCloudSampler):
+# name -> dict(model, diffusion ("base" | "karras"), sampler, steps, s_churn)
+SOLVER_CASES = {
+    "dpm_gaussian": dict(model="small_uncond", diffusion="base", sampler="dpm", steps=12, s_churn=3.0,
+                         sigma_max=120.0, B=2, noise_seed=9101),
+    "ancestral_gaussian": dict(model="small_uncond", diffusion="base", sampler="ancestral", steps=12, s_churn=0.0,
+                               sigma_max=120.0, B=2, noise_seed=9102),
+    "heun_karras": dict(model="small_uncond_c6", diffusion="karras", sampler="heun", steps=12, s_churn=3.0,
+                        sigma_max=80.0, B=2, noise_seed=9103),
+}

@@ -190,6 +190,28 @@ def gen_two_stage(m):
     save("sampler_two_stage", first_stage=torch.stack(yields[:17]), second_stage=torch.stack(yields[17:]))
 
 
+def gen_solver(m, case):
+    """DPM-2 / Euler-ancestral / KarrasDenoiser through the reference's karras_sample_progressive."""
+    print("solver", case)
+    sc = cases.SOLVER_CASES[case]
+    model, cfg, _ = build_reference_model(m, sc["model"])
+    if sc["diffusion"] == "karras":
+        diffusion = m.k_diffusion.KarrasDenoiser(sigma_data=0.5)
+    else:
+        diffusion = m.diffusion_configs.diffusion_from_config(cases.DIFFUSION_CONFIGS[sc["diffusion"]])
+    shape = (sc["B"], cfg["input_channels"], cfg["n_ctx"])
+    with patched_noise(cases.DetNoise(sc["noise_seed"])), torch.no_grad():
+        outs = list(m.k_diffusion.karras_sample_progressive(
+            diffusion, model, shape, sc["steps"], clip_denoised=True, model_kwargs={}, device=torch.device("cpu"),
+            sigma_min=1e-3, sigma_max=sc["sigma_max"], sampler=sc["sampler"], s_churn=sc["s_churn"],
+            guidance_scale=0.0))
+    key = "denoised" if sc["sampler"] == "dpm" else "pred_xstart"
+    xs = torch.stack([o["x"] for o in outs])
+    preds = torch.stack([o.get(key, o.get("pred_xstart")) for o in outs])
+    print("  ", len(outs), xs.shape, float(preds.std()))
+    save("solver_" + case, x=xs, pred=preds)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also run the full-size (slow) cases")
@@ -209,6 +231,8 @@ def main():
             continue
         todo.append(("sampler_" + c, lambda c=c: gen_sampler(m, c)))
     todo.append(("sampler_two_stage", lambda: gen_two_stage(m)))
+    for c in cases.SOLVER_CASES:
+        todo.append(("solver_" + c, lambda c=c: gen_solver(m, c)))
     for name, fn in todo:
         if args.only and args.only != name:
             continue

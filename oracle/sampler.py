@@ -232,3 +232,93 @@ def make_model_fn(sd, cfg):
     def fn(x, t, **kw):
         return D.denoiser_forward(sd, cfg, x, t, **kw)
     return fn
+
+
+# ---------------------------------------------------------------------------
+# Other solvers / preconditioning of reference k_diffusion.py (rows a7 and f2 of SURVEY 8)
+# ---------------------------------------------------------------------------
+class KarrasScalings:
+    """reference k_diffusion.py:31-45,71-76 (KarrasDenoiser.get_scalings / denoise)."""
+
+    def __init__(self, sigma_data: float = 0.5):
+        self.sigma_data = sigma_data
+
+    def denoise(self, model_fn, x_t, sigmas, **kw):
+        sd = self.sigma_data
+        c_skip = sd ** 2 / (sigmas ** 2 + sd ** 2)
+        c_out = sigmas * sd / (sigmas ** 2 + sd ** 2) ** 0.5
+        c_in = 1 / (sigmas ** 2 + sd ** 2) ** 0.5
+        ex = (...,) + (None,) * (x_t.dim() - 1)
+        rescaled_t = 1000 * 0.25 * torch.log(sigmas + 1e-44)
+        out = model_fn(c_in[ex] * x_t, rescaled_t, **kw)
+        return c_out[ex] * out + c_skip[ex] * x_t
+
+
+def karras_progressive(model_fn, diffusion, shape, steps, sampler="heun", sigma_min=1e-3, sigma_max=120.0,
+                       rho=7.0, s_churn=0.0, clip_denoised=True, model_kwargs=None, noise_fn=None):
+    """reference k_diffusion.py:118-222 without guidance, for sampler in {heun, dpm, ancestral} and
+    diffusion = Tables (GaussianDiffusion) or KarrasScalings (KarrasDenoiser).  Yields like the reference."""
+    model_kwargs = model_kwargs or {}
+    sigmas = karras_sigmas(steps, sigma_min, sigma_max, rho)
+    x = noise_fn(tuple(shape)) * sigma_max
+    B = shape[0]
+    gaussian = isinstance(diffusion, Tables)
+    if gaussian:
+        s2t = SigmaToT(diffusion)
+
+        def denoiser(x_t, sigma):
+            t = torch.tensor([s2t(s) for s in sigma.numpy()], dtype=torch.long)
+            c_in = (1.0 / (sigma ** 2 + 1) ** 0.5)[(...,) + (None,) * (x_t.dim() - 1)]
+            x_in = x_t * c_in
+            out = model_fn(x_in, t, **model_kwargs)
+            return diffusion.pred_xstart(out, x_in, t, clip_denoised)
+        fin = diffusion.unscale
+    else:
+        def denoiser(x_t, sigma):
+            d = diffusion.denoise(model_fn, x_t, sigma, **model_kwargs)
+            return d.clamp(-1, 1) if clip_denoised else d
+        fin = lambda v: v
+
+    def to_d(x, sigma, den):
+        return (x - den) / sigma[(...,) + (None,) * (x.dim() - sigma.dim())]
+
+    s_in = x.new_ones([B])
+    n = len(sigmas) - 1
+    if sampler == "ancestral":  # :248-266
+        for i in range(n):
+            den = denoiser(x, sigmas[i] * s_in)
+            s_from, s_to = sigmas[i], sigmas[i + 1]
+            s_up = (s_to ** 2 * (s_from ** 2 - s_to ** 2) / s_from ** 2) ** 0.5
+            s_down = (s_to ** 2 - s_up ** 2) ** 0.5
+            yield {"x": fin(x), "i": i, "pred_xstart": fin(den)}
+            d = to_d(x, sigmas[i], den)
+            x = x + d * (s_down - sigmas[i])
+            x = x + noise_fn(tuple(x.shape)) * s_up
+        yield {"x": fin(x), "pred_xstart": fin(x)}
+        return
+    den = None
+    for i in range(n):
+        gamma = min(s_churn / n, 2 ** 0.5 - 1)
+        eps = noise_fn(tuple(x.shape))
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+        den = denoiser(x, sigma_hat * s_in)
+        d = to_d(x, sigma_hat, den)
+        yield {"x": fin(x), "i": i, ("denoised" if sampler == "dpm" else "pred_xstart"): fin(den)}
+        if sampler == "dpm":  # :313-351
+            sigma_mid = ((sigma_hat ** (1 / 3) + sigmas[i + 1] ** (1 / 3)) / 2) ** 3
+            x_2 = x + d * (sigma_mid - sigma_hat)
+            den_2 = denoiser(x_2, sigma_mid * s_in)
+            d_2 = to_d(x_2, sigma_mid, den_2)
+            x = x + d_2 * (sigmas[i + 1] - sigma_hat)
+        else:  # heun :299-309
+            dt = sigmas[i + 1] - sigma_hat
+            if sigmas[i + 1] == 0:
+                x = x + d * dt
+            else:
+                x_2 = x + d * dt
+                den_2 = denoiser(x_2, sigmas[i + 1] * s_in)
+                d_2 = to_d(x_2, sigmas[i + 1], den_2)
+                x = x + (d + d_2) / 2 * dt
+    yield {"x": fin(x), "pred_xstart": fin(den)}

@@ -155,3 +155,23 @@ def test_sampler_small(case):
     # trajectories are chaotic in the last ulp; compare early steps tightly, all loosely
     assert rel_l2(ys[:3], g["yields"][:3]) < 1e-5
     assert rel_l2(ys, g["yields"]) < 1e-3
+
+
+@pytest.mark.parametrize("case", list(cases.SOLVER_CASES))
+def test_solvers(case):
+    """DPM-2, Euler-ancestral and KarrasDenoiser preconditioning (oracle vs the reference)."""
+    g = load_golden("solver_" + case)
+    sc = cases.SOLVER_CASES[case]
+    sd, cfg = case_weights(sc["model"])
+    diffusion = S.KarrasScalings(0.5) if sc["diffusion"] == "karras" else S.Tables(**cases.DIFFUSION_CONFIGS["base"])
+    shape = (sc["B"], cfg["input_channels"], cfg["n_ctx"])
+    with torch.no_grad():
+        outs = list(S.karras_progressive(S.make_model_fn(sd, cfg), diffusion, shape, sc["steps"], sampler=sc["sampler"],
+                                         sigma_max=sc["sigma_max"], s_churn=sc["s_churn"],
+                                         noise_fn=cases.DetNoise(sc["noise_seed"])))
+    key = "denoised" if sc["sampler"] == "dpm" else "pred_xstart"
+    xs = torch.stack([o["x"] for o in outs])
+    preds = torch.stack([o.get(key, o.get("pred_xstart")) for o in outs])
+    assert xs.shape == g["x"].shape
+    assert rel_l2(xs[:2], g["x"][:2]) < 1e-5 and rel_l2(preds[:2], g["pred"][:2]) < 1e-5
+    assert rel_l2(preds, g["pred"]) < 1e-3
