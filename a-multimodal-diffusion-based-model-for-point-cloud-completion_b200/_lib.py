@@ -50,6 +50,7 @@ _SIGS = {
     "pcd_launch_count": (C.c_ulonglong, []),
     "pcd_check_device": (C.c_int, []),
     "pcd_set_attention_variant": (C.c_int, [C.c_int]),
+    "pcd_default_attention_variant": (C.c_int, []),
     "pcd_set_debug_flags": (C.c_int, [C.c_int]),
     "pcd_timestep_embed": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "pcd_layernorm": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]),

@@ -1152,6 +1152,10 @@ static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batc
   return encode_tmap_bf16(m, op->ptr, 4, dims, strides, box);
 }
 
+int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
+                    int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2,
+                    cudaStream_t st);  // attn_tc5.cu
+
 int g_attn_variant = 3;  // 3: double-buffered S/P, 64-key tiles, 2 CTAs/SM (default, fastest measured);
                          // 4: as 3 with rows split over two softmax threads; 2: ping-pong
                          // over two query tiles; 1: one tile per CTA, P in
@@ -1168,6 +1172,8 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
   if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
+  if (g_attn_variant == 5)
+    return launch_attn_tc5(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 4)
     return launch_attn_tc4(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 3)

@@ -58,12 +58,16 @@ PCD_API unsigned long long pcd_launch_count(void);
 PCD_API int pcd_check_device(void);
 
 /* Tuning / testing knob (no reference counterpart): tensor-core attention kernel variant,
+ * 5 = persistent CTAs over (query tile, head, sequence) items, softmax software-pipelined over KV
+ *     tiles (S_{j+1} loaded before the exponentials of S_j), separate K / V rings, packed f32x2 math,
  * 3 = one query tile per CTA, 64-key tiles, S and P double-buffered in TMEM, two CTAs per SM (default),
  * 4 = as 3, with every query row split over two softmax threads (16 softmax warps per SM),
  * 2 = ping-pong over two query tiles per CTA, P in TMEM,
  * 1 = one query tile per CTA, P in TMEM (tcgen05.mma with A from TMEM), two CTAs per SM,
  * 0 = one query tile per CTA, P staged through 128B-swizzled shared memory. */
 PCD_API int pcd_set_attention_variant(int variant);
+/* The variant the library starts with (what pcd_model_forward uses unless overridden). */
+PCD_API int pcd_default_attention_variant(void);
 /* Profiling aid -- results are INVALID while non-zero: bit 0 skips the GEMM epilogue, bit 1 skips
  * the GEMM TMA loads (separates main-loop, load and epilogue time in tools/gemm_probe.py). */
 PCD_API int pcd_set_debug_flags(int flags);

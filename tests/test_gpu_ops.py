@@ -121,7 +121,7 @@ def test_gemm_bf16_large_persistent():
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
-@pytest.mark.parametrize("variant", [4, 3, 2, 1, 0])
+@pytest.mark.parametrize("variant", [5, 4, 3, 2, 1, 0])
 def test_self_attention_golden(dtype, tol, variant):
     if dtype == torch.float32 and variant != 3:
         pytest.skip("variant only affects the tensor-core kernel")
@@ -138,7 +138,7 @@ def test_self_attention_golden(dtype, tol, variant):
             torch.cuda.synchronize()
             assert rel(got.float(), want) < tol, describe(got.float(), want, f"{name} {dtype} v{variant}")
     finally:
-        P._lib.load().pcd_set_attention_variant(3)
+        P._lib.load().pcd_set_attention_variant(P._lib.load().pcd_default_attention_variant())
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
@@ -152,6 +152,38 @@ def test_self_attention_lengths(dtype, tol, L):
     got = ops.self_attention(qkv.to(DEV).to(dtype), heads)
     torch.cuda.synchronize()
     assert rel(got.float(), want) < tol, describe(got.float(), want, f"L={L} {dtype}")
+
+
+@pytest.mark.parametrize("variant", [5, 3])
+@pytest.mark.parametrize("B,heads,L,std", [(2, 2, 1, 1.5), (2, 2, 63, 1.5), (3, 2, 64, 1.5), (2, 3, 65, 1.5),
+                                           (2, 2, 127, 1.5), (2, 2, 129, 1.5), (1, 2, 1026, 1.5),
+                                           (40, 8, 200, 1.0),    # 640 items on 296 persistent CTAs
+                                           (33, 8, 1026, 2.5),   # 9 query tiles x 17 KV tiles (odd), 8 items / CTA
+                                           (5, 16, 1281, 4.0)])  # large logits: lazy rescaling path
+def test_attention_bf16_variants_vs_torch(variant, B, heads, L, std):
+    """Tensor-core attention variants against an fp32 torch evaluation of the same bf16 inputs, at
+    shapes that give a persistent CTA several (query tile, head, sequence) items, odd KV-tile
+    counts and ragged query / key tails."""
+    lib = P._lib.load()
+    gen = torch.Generator(device="cpu").manual_seed(1000 + L + heads)
+    qkv = (torch.randn(B, L, heads * 192, generator=gen) * std).to(DEV).bfloat16()
+    x = qkv.float().view(B, L, heads, 192)
+    q, k, v = x[..., :64], x[..., 64:128], x[..., 128:]
+    want = torch.empty(B, L, heads * 64, device=DEV)
+    for b0 in range(0, B, 8):
+        w = torch.einsum("bthc,bshc->bhts", q[b0:b0 + 8], k[b0:b0 + 8]) / 8.0
+        want[b0:b0 + 8] = torch.einsum("bhts,bshc->bthc", torch.softmax(w, -1), v[b0:b0 + 8]).reshape(-1, L, heads * 64)
+    lib.pcd_set_attention_variant(variant)
+    try:
+        got = ops.self_attention(qkv, heads)
+        torch.cuda.synchronize()
+    finally:
+        lib.pcd_set_attention_variant(lib.pcd_default_attention_variant())
+    assert torch.isfinite(got.float()).all()
+    assert rel(got.float(), want) < 1e-2, describe(got.float(), want, f"v{variant} B{B} H{heads} L{L}")
+    # per-sequence check so that one bad item cannot hide in the norm of many good ones
+    per = ((got.float() - want).flatten(1).norm(dim=1) / want.flatten(1).norm(dim=1)).max()
+    assert float(per) < 1e-2, float(per)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])

@@ -25,7 +25,7 @@ def t(fn, it=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / it
 fl = 4.0 * L * L * 64 * H * B
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4, 3, 2, 1]
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [5, 3]
 for v in variants:
     lib.pcd_set_attention_variant(v)
     out = P.ops.self_attention(qkv, H)
@@ -33,4 +33,4 @@ for v in variants:
     err = float((out[:2].float() - want).norm() / want.norm())
     ms = t(lambda: P.ops.self_attention(qkv, H))
     print(f"variant {v}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  rel err {err:.2e}")
-lib.pcd_set_attention_variant(3)
+lib.pcd_set_attention_variant(lib.pcd_default_attention_variant())
