@@ -1154,9 +1154,10 @@ static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batc
 
 int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
                     int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2,
-                    cudaStream_t st);  // attn_tc5.cu
+                    int poly, cudaStream_t st);  // attn_tc5.cu
 
-int g_attn_variant = 3;  // 3: double-buffered S/P, 64-key tiles, 2 CTAs/SM (default, fastest measured);
+int g_attn_variant = 5;  // 5: persistent + software-pipelined softmax (default, fastest measured); 6, 7: as 5 with 1/4, 1/2 of the
+                         // exponentials evaluated by an FMA-pipe polynomial; 3: double-buffered S/P, 64-key tiles, 2 CTAs/SM;
                          // 4: as 3 with rows split over two softmax threads; 2: ping-pong
                          // over two query tiles; 1: one tile per CTA, P in
                          // TMEM, 2 CTAs/SM; 0: one tile per CTA, P in shared memory (SS MMA)
@@ -1172,8 +1173,9 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k,
   if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
-  if (g_attn_variant == 5)
-    return launch_attn_tc5(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
+  if (g_attn_variant >= 5)  // 5: all exponentials on the MUFU; 6: 1/4, 7: 1/2 of them on the FMA pipes
+    return launch_attn_tc5(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2,
+                           g_attn_variant == 6 ? 2 : (g_attn_variant == 7 ? 1 : 0), st);
   if (g_attn_variant == 4)
     return launch_attn_tc4(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
   if (g_attn_variant == 3)

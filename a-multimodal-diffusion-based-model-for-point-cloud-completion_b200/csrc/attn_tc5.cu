@@ -19,7 +19,7 @@
 //   * the scale/subtract and the row sum use the packed fma.rn.f32x2 / add.rn.f32x2 forms
 //     (half the FMA-pipe issue slots), shared-memory barrier addresses are 32-bit values computed
 //     once (variant 3 re-derived them with S2UR every iteration).
-// Warp roles (256 threads): 0 = Q/K TMA producer, 1 = MMA issuer, 2 = V TMA producer, 3 idle,
+// Warp roles (256 threads): 0 = Q/K TMA producer, 1 = QK^T issuer, 2 = V TMA producer, 3 = PV issuer,
 // 4-7 = softmax (thread = query row).
 #include "common.cuh"
 #include "tc_sm100.cuh"
@@ -99,6 +99,31 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
   return r;
 }
 
+// 2^x for a pair, x <= ~8, entirely on the FMA / ALU pipes (no MUFU): round-to-nearest split
+// x = n + f, |f| <= 0.5 (magic-number add), degree-3 minimax polynomial for 2^f (max rel. error
+// 7.5e-5, far below the bf16 rounding of P), exponent patched in with an integer shift-add.  The
+// clamp at -126 turns everything below (incl. the -inf of masked keys) into denormals (n = -127 would
+// wrap the exponent field of a polynomial value below 1.0 into the sign bit).
+__device__ __forceinline__ void exp2_poly2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t xc = pack2(x0, x1);
+  const uint64_t magic = pack2(12582912.f, 12582912.f);  // 1.5 * 2^23
+  const uint64_t r2 = add2(xc, magic);                    // n in the low mantissa bits
+  const uint64_t fl = add2(r2, pack2(-12582912.f, -12582912.f));
+  const uint64_t f2 = fma2(fl, pack2(-1.f, -1.f), xc);
+  uint64_t q = fma2(pack2(0.0551716685f, 0.0551716685f), f2, pack2(0.24261114f, 0.24261114f));
+  q = fma2(q, f2, pack2(0.693260968f, 0.693260968f));
+  q = fma2(q, f2, pack2(0.999928057f, 0.999928057f));
+  float q0, q1, r0, r1;
+  unpack2(q, q0, q1);
+  unpack2(r2, r0, r1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+
 // keep a value in its register: stops ptxas from re-deriving it (S2R / cvta chains) at every use
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
@@ -124,7 +149,8 @@ struct Sm {
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P <= 2^8, safe in bf16 / fp32
 
 // P = exp2(S * scale - m_used) for the first `ncols` (32 or 64) columns of cur -> bf16 in TMEM
-__device__ __forceinline__ void exp_tile(Sm& c, const uint32_t (&cur)[BKV], uint32_t p_tmem, int ncols) {
+template <int POLY>  // POLY: every POLY-th group of four columns takes two of its exponentials off the MUFU (0 = none)
+__device__ __forceinline__ float exp_tile(const Sm& c, const uint32_t (&cur)[BKV], uint32_t p_tmem, int ncols) {
   const uint64_t sc2 = pack2(c.scale, c.scale);
   const uint64_t nm2 = pack2(-c.m_used, -c.m_used);
   uint64_t sum_a = 0ull, sum_b = 0ull;  // (0.f, 0.f)
@@ -139,7 +165,14 @@ __device__ __forceinline__ void exp_tile(Sm& c, const uint32_t (&cur)[BKV], uint
         float a0, a1, b0, b1;
         unpack2(xa, a0, a1);
         unpack2(xb, b0, b1);
-        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1), p2 = ex2_approx(b0), p3 = ex2_approx(b1);
+        const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+        float p2, p3;
+        if (POLY > 0 && ((i >> 2) % POLY) == POLY - 1) {
+          exp2_poly2(xb, p2, p3);
+        } else {
+          p2 = ex2_approx(b0);
+          p3 = ex2_approx(b1);
+        }
         sum_a = add2(sum_a, pack2(p0, p1));
         sum_b = add2(sum_b, pack2(p2, p3));
         pk[i >> 1] = pack_bf16x2(p0, p1);
@@ -151,10 +184,10 @@ __device__ __forceinline__ void exp_tile(Sm& c, const uint32_t (&cur)[BKV], uint
   float s0, s1, s2, s3;
   unpack2(sum_a, s0, s1);
   unpack2(sum_b, s2, s3);
-  c.l_run += (s0 + s1) + (s2 + s3);
+  return (s0 + s1) + (s2 + s3);
 }
 
-// row maximum (log2 domain); keys >= nvalid are masked to -inf first
+// row maximum (log2 domain); keys >= nvalid of a ragged tile are masked to -inf first
 __device__ __forceinline__ float row_max(const Sm& c, uint32_t (&r)[BKV], int nvalid) {
   if (nvalid < BKV) {
 #pragma unroll
@@ -174,7 +207,10 @@ __device__ __forceinline__ float row_max(const Sm& c, uint32_t (&r)[BKV], int nv
 
 // pipelined step on the tile held in cur (S/P buffer X): the load of the next tile (buffer X^1)
 // is in flight while cur is exponentiated.  nvalid_next < 64 only for a ragged last tile.
-template <int X>
+// (A variant that skipped the per-tile row maximum and re-referenced only when a tile's row sum
+// exceeded 2^8 measured 6-17 % slower: the vote then sits between the exponentials and the P
+// hand-off instead of overlapping the next tile's maximum with them.)
+template <int X, int POLY>
 __device__ __forceinline__ void pstep(Sm& c, uint32_t (&cur)[BKV], uint32_t (&nxt)[BKV], int nvalid_next) {
   constexpr int Y = X ^ 1;
   uint32_t& ux = X ? c.u1 : c.u0;
@@ -187,7 +223,7 @@ __device__ __forceinline__ void pstep(Sm& c, uint32_t (&cur)[BKV], uint32_t (&nx
   // P buffer X is free once the PV product of its previous use has completed
   bar_wait(c.bars + 8 * (B_PV_DONE + X), ux ^ 1);
   tcgen05_fence_after();
-  exp_tile(c, cur, c.tm + P_COL + X * (BKV / 2), BKV);
+  c.l_run += exp_tile<POLY>(c, cur, c.tm + P_COL + X * (BKV / 2), BKV);
   tmem_st_wait();
   tmem_ld_wait();
   tcgen05_fence_before();
@@ -222,13 +258,13 @@ __device__ __forceinline__ void pstep(Sm& c, uint32_t (&cur)[BKV], uint32_t (&nx
 }
 
 // last tile of an item (buffer X, `nvalid` real keys): exponentiate, then O / l -> global
-template <int X>
+template <int X, int POLY>
 __device__ __forceinline__ void last_step(Sm& c, uint32_t (&cur)[BKV], int nvalid, uint16_t* __restrict__ orow,
                                           bool row_ok) {
   uint32_t& ux = X ? c.u1 : c.u0;
   bar_wait(c.bars + 8 * (B_PV_DONE + X), ux ^ 1);
   tcgen05_fence_after();
-  exp_tile(c, cur, c.tm + P_COL + X * (BKV / 2), nvalid);
+  c.l_run += exp_tile<POLY>(c, cur, c.tm + P_COL + X * (BKV / 2), nvalid);
   tmem_st_wait();
   tcgen05_fence_before();
   __syncwarp();
@@ -255,6 +291,7 @@ __device__ __forceinline__ void last_step(Sm& c, uint32_t (&cur)[BKV], int nvali
   ux ^= 1;
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(256, 2)
 attn_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs,
@@ -354,76 +391,71 @@ attn_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     } else if (warp == 1) {
-      // -------------------------- MMA issuer ------------------------
-      // Two cursors over the CTA's flat stream of KV tiles: QK products run up to three tiles ahead
-      // of the PV products.  S/P buffer of a tile = its index within the item & 1; a QK product
-      // waits until the previous S tile of its buffer sits in the softmax registers (s_free).
+      // ------------------------ QK^T issuer -------------------------
+      // Walks the CTA's flat stream of KV tiles.  S/P buffer of a tile = its index within the item
+      // & 1; S = Q K^T for a tile is issued as soon as the previous S tile of that buffer sits in
+      // the softmax registers (s_free) -- up to three tiles ahead of the exponentials.  The PV
+      // products have their own issuer (warp 3) so that neither stream ever waits for the other's
+      // barriers (a single in-order issuer either delays QK^T behind P_j or deadlocks on short
+      // sequences).
       if (elect_one()) {
-        constexpr uint32_t idesc_pv = idesc_bf16_f32(BQ, HD, /*B MN-major*/ 1);
         constexpr uint32_t idesc_qk_full = idesc_bf16_f32(BQ, BKV, 0);
         const uint32_t idesc_qk_last = idesc_bf16_f32(BQ, max(16, (last_valid + 15) & ~15), 0);
-        const int nks_last = (last_valid + 15) >> 4;
-        int kq = 0, jq = 0, stk = 0;          // QK cursor: item, tile, K ring stage
-        uint32_t phk = 0, uq0 = 0, uq1 = 0;   // K ring phase; completed uses of S buffer 0 / 1 (parity)
-        auto issue_qk = [&]() {
-          if (kq >= my_items) return;
-          const int b = jq & 1;
-          const uint32_t uq = b ? uq1 : uq0;
-          bar_wait(bar(B_S_FREE + b), uq ^ 1);  // (passes at once for the first use of a buffer)
-          if (b) uq1 ^= 1; else uq0 ^= 1;
-          const int qb = kq & 1;
-          if (jq == 0) bar_wait(bar(B_Q_FULL + qb), (kq >> 1) & 1);
-          bar_wait(bar(B_K_FULL + stk), phk);
-          tcgen05_fence_after();
-          const bool last = (jq == num_kv - 1);
-          const uint32_t idesc = last ? idesc_qk_last : idesc_qk_full;
+        int st = 0;
+        uint32_t ph = 0, u0 = 0, u1 = 0;  // K ring phase; completed uses of S buffer 0 / 1 (parity)
+        for (int k = 0; k < my_items; ++k) {
+          const int qb = k & 1;
           const uint64_t adesc = smem_desc_sw128(sQ + qb * Q_TILE);
-          const uint64_t bdesc = smem_desc_sw128(sK + stk * KV_TILE);
-          const uint32_t s_tmem = tmem_base + S_COL + b * BKV;
-#pragma unroll
-          for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(s_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
-          commit(bar(B_K_EMPTY + stk));
-          commit(bar(B_S_FULL + b));
-          if (++stk == KSK) {
-            stk = 0;
-            phk ^= 1;
-          }
-          if (last) {
-            commit(bar(B_Q_EMPTY + qb));
-            jq = 0;
-            ++kq;
-          } else {
-            ++jq;
-          }
-        };
-        issue_qk();
-        issue_qk();
-        issue_qk();
-        int stv = 0;
-        uint32_t phv = 0, up0 = 0, up1 = 0;
-        for (int kp = 0; kp < my_items; ++kp) {
-          for (int jp = 0; jp < num_kv; ++jp) {
-            const int b = jp & 1;
-            const uint32_t up = b ? up1 : up0;
-            bar_wait(bar(B_P_READY + b), up);  // P of this tile is in TMEM
-            if (b) up1 ^= 1; else up0 ^= 1;
-            if (jp == 0 && kp > 0) bar_wait(bar(B_O_FREE), (kp - 1) & 1);  // previous item's O read out
-            bar_wait(bar(B_V_FULL + stv), phv);
+          bar_wait(bar(B_Q_FULL + qb), (k >> 1) & 1);
+          for (int j = 0; j < num_kv; ++j) {
+            const int b = j & 1;
+            bar_wait(bar(B_K_FULL + st), ph);             // (loaded long ago: off the critical path)
+            bar_wait(bar(B_S_FREE + b), (b ? u1 : u0) ^ 1);  // passes at once for the first use of a buffer
+            if (b) u1 ^= 1; else u0 ^= 1;
             tcgen05_fence_after();
-            const bool last = (jp == num_kv - 1);
-            const int nks = last ? nks_last : BKV / 16;
-            const uint32_t v_addr = sV + stv * KV_TILE;
-            const uint32_t p_tmem = tmem_base + P_COL + b * (BKV / 2);
-            const uint32_t o_tmem = tmem_base + O_COL;
-            for (int kk = 0; kk < nks; ++kk)
-              umma_bf16_ts(o_tmem, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 2048), idesc_pv, (jp | kk) != 0);
-            commit(bar(B_V_EMPTY + stv));
-            commit(bar(B_PV_DONE + b));
-            if (++stv == KSV) {
-              stv = 0;
-              phv ^= 1;
+            const bool last = (j == num_kv - 1);
+            const uint32_t idesc = last ? idesc_qk_last : idesc_qk_full;
+            const uint64_t bdesc = smem_desc_sw128(sK + st * KV_TILE);
+            const uint32_t s_tmem = tmem_base + S_COL + b * BKV;
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(s_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
+            commit(bar(B_S_FULL + b));
+            commit(bar(B_K_EMPTY + st));
+            if (last) commit(bar(B_Q_EMPTY + qb));
+            if (++st == KSK) {
+              st = 0;
+              ph ^= 1;
             }
-            issue_qk();
+          }
+        }
+      }
+    } else {
+      // -------------------------- PV issuer -------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_pv = idesc_bf16_f32(BQ, HD, /*B MN-major*/ 1);
+        const int nks_last = (last_valid + 15) >> 4;
+        const uint32_t o_tmem = tmem_base + O_COL;
+        int st = 0;
+        uint32_t ph = 0, u0 = 0, u1 = 0;
+        for (int k = 0; k < my_items; ++k) {
+          for (int j = 0; j < num_kv; ++j) {
+            const int b = j & 1;
+            bar_wait(bar(B_V_FULL + st), ph);
+            if (j == 0 && k > 0) bar_wait(bar(B_O_FREE), (k - 1) & 1);  // previous item's O read out
+            bar_wait(bar(B_P_READY + b), b ? u1 : u0);                  // P of this tile is in TMEM
+            if (b) u1 ^= 1; else u0 ^= 1;
+            tcgen05_fence_after();
+            const int nks = (j == num_kv - 1) ? nks_last : BKV / 16;
+            const uint32_t v_addr = sV + st * KV_TILE;
+            const uint32_t p_tmem = tmem_base + P_COL + b * (BKV / 2);
+            for (int kk = 0; kk < nks; ++kk)
+              umma_bf16_ts(o_tmem, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0);
+            commit(bar(B_PV_DONE + b));
+            commit(bar(B_V_EMPTY + st));
+            if (++st == KSV) {
+              st = 0;
+              ph ^= 1;
+            }
           }
         }
       }
@@ -480,15 +512,15 @@ attn_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int j = 0;
       bool done = false;
       for (; j + 1 < num_kv; j += 2) {
-        pstep<0>(c, ra, rb, (partial && j + 2 == num_kv) ? last_valid : BKV);
+        pstep<0, POLY>(c, ra, rb, (partial && j + 2 == num_kv) ? last_valid : BKV);
         if (j + 2 < num_kv) {
-          pstep<1>(c, rb, ra, (partial && j + 3 == num_kv) ? last_valid : BKV);
+          pstep<1, POLY>(c, rb, ra, (partial && j + 3 == num_kv) ? last_valid : BKV);
         } else {
-          last_step<1>(c, rb, last_valid, orow, row_ok);
+          last_step<1, POLY>(c, rb, last_valid, orow, row_ok);
           done = true;
         }
       }
-      if (!done) last_step<0>(c, ra, last_valid, orow, row_ok);
+      if (!done) last_step<0, POLY>(c, ra, last_valid, orow, row_ok);
     }
   }
 
@@ -502,23 +534,21 @@ attn_bf16_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 }  // namespace a5
 
-int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
-                    int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2,
-                    cudaStream_t st) {
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(a5::attn_bf16_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::SMEM_BYTES);
+template <int POLY>
+static int launch_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
+                      int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2,
+                      cudaStream_t st) {
+  auto kern = a5::attn_bf16_tc5_kernel<POLY>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(a5::attn_bf16_tc5_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               cudaSharedmemCarveoutMaxShared);
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       set_error("attention_bf16: kernel attribute setup (%d B smem): %s", a5::SMEM_BYTES, cudaGetErrorString(e));
       return PCD_ERR_CUDA;
     }
-    // two CTAs per SM by construction: 2 x (104.5 KB smem + 1 KB reserved) <= 228 KB, 2 x 256 threads x 128
-    // registers = the whole file, 2 x 256 TMEM columns = all 512 (ncu: launch__occupancy_limit_* = 2;
-    // cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports it as 1 for this kernel)
-    ctas_per_sm = 2;
+    attr_set = true;
   }
   const int nq = ceil_div(len_q, a5::BQ);
   const int64_t n_items64 = (int64_t)nq * heads * batch;
@@ -527,11 +557,21 @@ int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
     return PCD_ERR_INVALID;
   }
   const int n_items = (int)n_items64;
-  const int grid = min(n_items, ctas_per_sm * num_sms());
-  a5::attn_bf16_tc5_kernel<<<grid, 256, a5::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2, nq,
-                                                             heads, n_items);
+  // two CTAs per SM by construction: 2 x (104.5 KB smem + 1 KB reserved) <= 228 KB, 2 x 256 threads x 128
+  // registers = the whole file, 2 x 256 TMEM columns = all 512 (ncu: launch__occupancy_limit_* = 2)
+  const int grid = min(n_items, 2 * num_sms());
+  kern<<<grid, 256, a5::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2, nq, heads, n_items);
   PCD_CHECK_LAUNCH("attention_bf16");
   return PCD_OK;
+}
+
+// poly: 0 = every exponential on the MUFU, 2 = 1/4 and 1 = 1/2 of them on the FMA pipes
+int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out,
+                    int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2,
+                    int poly, cudaStream_t st) {
+  if (poly == 2) return launch_tc5<2>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
+  if (poly == 1) return launch_tc5<1>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
+  return launch_tc5<0>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, st);
 }
 
 }  // namespace pcd

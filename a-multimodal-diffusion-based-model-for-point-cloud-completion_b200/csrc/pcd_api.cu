@@ -128,11 +128,11 @@ extern "C" int pcd_set_debug_flags(int flags) {
   return PCD_OK;
 }
 
-constexpr int kDefaultAttnVariant = 3;
+constexpr int kDefaultAttnVariant = 5;
 extern "C" int pcd_default_attention_variant(void) { return kDefaultAttnVariant; }
 
 extern "C" int pcd_set_attention_variant(int v) {
-  PCD_CHECK_ARG(v >= 0 && v <= 5, "attention variant must be 0..5");
+  PCD_CHECK_ARG(v >= 0 && v <= 7, "attention variant must be 0..7");
   g_attn_variant = v;
   return PCD_OK;
 }
