@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libpcd_b200.so")
 
 PCD_F32, PCD_BF16 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
+EPI_RESIDUAL_STATS, EPI_LN_BIAS, EPI_LN_BIAS_GELU = 3, 4, 5
 
 c_float_p = C.POINTER(C.c_float)
 vp = C.c_void_p
@@ -31,7 +32,15 @@ class StepScalars(C.Structure):
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, vp) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "w_proj", "w_fc",
-                                  "w_fc2", "b_qkv", "b_proj", "b_fc", "b_fc2")]
+                                  "w_fc2", "b_qkv", "b_proj", "b_fc", "b_fc2",
+                                  "w_qkv_ln", "w_fc_ln", "qkv_colsum", "qkv_const", "fc_colsum", "fc_const")]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("A", vp), ("lda", C.c_int), ("W", vp), ("ldw", C.c_int), ("bias", vp), ("residual", vp),
+                ("ldr", C.c_int), ("C", vp), ("ldc", C.c_int), ("out_precision", C.c_int), ("C2", vp),
+                ("ldc2", C.c_int), ("stats_out", vp), ("stats_in", vp), ("colsum", vp), ("ln_eps", C.c_float),
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int)]
 
 
 class ModelDesc(C.Structure):
@@ -64,6 +73,8 @@ _SIGS = {
                                C.c_int, C.c_int, vp]),
     "pcd_gemm_bf16": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, vp]),
+    "pcd_gemm_bf16_ex": (C.c_int, [C.POINTER(GemmArgs), vp]),
+    "pcd_cast_rowstats": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
     "pcd_attention": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 C.c_float, vp, C.c_int, vp]),

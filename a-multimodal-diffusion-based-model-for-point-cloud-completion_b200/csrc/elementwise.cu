@@ -126,6 +126,37 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, i
 }
 
 // ---------------------------------------------------------------------------
+// bf16 copy of the residual stream + per-128-column (mean, M2) of the rounded values: the inputs
+// of the LayerNorm-folded projections (gemm_tc.cu, PCD_EPI_LN_*).  Lane l holds columns
+// i*128 + 4l .. +3 of slot i, so one warp reduction per slot.
+// ---------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) cast_rowstats_kernel(const float* __restrict__ x, int ldx,
+                                                            uint16_t* __restrict__ out, int ldo,
+                                                            float2* __restrict__ stats, int rows, int dim) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * ldx;
+  const int slots = dim / 128;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < slots) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const uint32_t p0 = pack_bf16x2(v.x, v.y), p1 = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(out + (size_t)warp * ldo + c) = make_uint2(p0, p1);
+      const float q0 = __uint_as_float(p0 << 16), q1 = __uint_as_float(p0 & 0xffff0000u);
+      const float q2 = __uint_as_float(p1 << 16), q3 = __uint_as_float(p1 & 0xffff0000u);
+      const float mean = warp_sum((q0 + q1) + (q2 + q3)) * (1.f / 128.f);
+      const float a = q0 - mean, b = q1 - mean, cc = q2 - mean, d = q3 - mean;
+      const float m2 = warp_sum((a * a + b * b) + (cc * cc + d * d));
+      if (lane == 0) stats[(size_t)warp * slots + i] = make_float2(mean, m2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // token assembly + ln_pre (reference models/transformer.py:205-220)
 // ---------------------------------------------------------------------------
 constexpr int EMB_ROWS_PER_WARP = 16;
@@ -337,6 +368,18 @@ extern "C" int pcd_add_layernorm(float* h, int ldh, const void* y, int ldy, int 
   PCD_CHECK_ARG(y != nullptr, "add_layernorm: y missing");
   return launch_layernorm(h, ldh, y, ldy, y_precision, gamma, beta, out, ld_out, out_precision, rows, dim, eps,
                           stream, "add_layernorm");
+}
+
+extern "C" int pcd_cast_rowstats(const float* x, int ldx, uint16_t* out, int ld_out, float* stats, int rows,
+                                 int dim, void* stream) {
+  PCD_CHECK_ARG(x != nullptr && out != nullptr && stats != nullptr, "cast_rowstats: null argument");
+  PCD_CHECK_ARG(rows > 0 && dim > 0 && dim % 128 == 0 && dim <= 2048, "cast_rowstats: dim must be a multiple of 128, <= 2048 (got %d)", dim);
+  PCD_CHECK_ARG(ldx % 4 == 0 && ld_out % 4 == 0, "cast_rowstats: leading dims must be multiples of 4");
+  dim3 grid(ceil_div(rows, 8)), block(256);
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_MAXV(dim, (cast_rowstats_kernel<MAXV><<<grid, block, 0, st>>>(x, ldx, out, ld_out, reinterpret_cast<float2*>(stats), rows, dim)));
+  PCD_CHECK_LAUNCH("cast_rowstats");
+  return PCD_OK;
 }
 
 extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_points,

@@ -298,8 +298,11 @@ struct Gemm2Cfg {
   // two staging tiles per epilogue warp: a TMA store only has to have finished READING its tile
   // by the time the warp comes back to it two store groups later (the round trip is ~2k cycles)
   static constexpr int NBUF = 2;
-  static constexpr int OUT_BYTES = G_EPI_WARPS * NBUF * G_STAGE_TILE;
-  static constexpr int MISC_BYTES = 512 + 2 * BN * 4;
+  // the residual + row-statistics epilogue writes TWO tensors (fp32 residual stream and its bf16
+  // copy): a second set of staging tiles
+  static constexpr int OUT1_BYTES = G_EPI_WARPS * NBUF * G_STAGE_TILE;
+  static constexpr int OUT_BYTES = OUT1_BYTES + (EPI == PCD_EPI_RESIDUAL_STATS ? G_EPI_WARPS * G_STAGE_TILE : 0);
+  static constexpr int MISC_BYTES = 512 + 2 * BN * 4;  // barriers + per-tile bias slices
   static constexpr int BUDGET = 232448 - OUT_BYTES - MISC_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;
@@ -310,7 +313,9 @@ template <int EPI, bool OUT_BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                     const float* __restrict__ bias, int M, int N, int K, int dbg) {
+                     const __grid_constant__ CUtensorMap tmC2, const float* __restrict__ bias,
+                     const float* __restrict__ colsum, const float2* __restrict__ stats_in, int stats_in_slots,
+                     float2* __restrict__ stats_out, float ln_eps, int M, int N, int K, int dbg) {
   using Cfg = Gemm2Cfg<EPI>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
@@ -327,6 +332,10 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* res_bar = acc_empty + 2;        // [8 warps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * G_EPI_WARPS);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);  // [2][BN]
+  constexpr bool kResid = (EPI == PCD_EPI_BIAS_RESIDUAL || EPI == PCD_EPI_RESIDUAL_STATS);
+  constexpr bool kStats = (EPI == PCD_EPI_RESIDUAL_STATS);
+  constexpr bool kLnFold = (EPI == PCD_EPI_LN_BIAS || EPI == PCD_EPI_LN_BIAS_GELU);
+  constexpr bool kGelu = (EPI == PCD_EPI_BIAS_GELU || EPI == PCD_EPI_LN_BIAS_GELU);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();       // 0 = leader
@@ -339,7 +348,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmW);
     prefetch_tensormap(&tmC);
-    if (EPI == PCD_EPI_BIAS_RESIDUAL) prefetch_tensormap(&tmR);
+    if (kResid) prefetch_tensormap(&tmR);
+    if (kStats) prefetch_tensormap(&tmC2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -421,14 +431,46 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr int HALF_N = BN / 2;
     constexpr int NCH = HALF_N / 32;
     constexpr int CH_PER_STORE = OUT_BF16 ? 2 : 1;
-    static_assert(!(EPI == PCD_EPI_BIAS_RESIDUAL && OUT_BF16), "the residual stream is fp32");
+    static_assert(!(kResid && OUT_BF16), "the residual stream is fp32");
+    static_assert(!kLnFold || OUT_BF16, "the LayerNorm-folded projections write bf16");
     const int etid = threadIdx.x - 64;
     constexpr int NBUF = Cfg::NBUF;
     unsigned char* my_buf0 = stage_out + ew * NBUF * G_STAGE_TILE;
-    int sidx = 0;  // running store-group index of this warp
-    uint64_t* my_res_bar = res_bar + 2 * ew;
+    unsigned char* my_bbuf = stage_out + Cfg::OUT1_BYTES + ew * G_STAGE_TILE;  // bf16 copy (kStats), one tile
+    int sidx = 0;   // running store-group index of this warp
+    uint64_t* my_res_bar = res_bar + 2 * ew;  // [2]: residual chunk landed in staging tile 0 / 1
     const int sw = lane & 7;
-    uint32_t res_uses = 0;
+    uint32_t res_ph0 = 0, res_ph1 = 0;
+    static_assert(!kResid || (NBUF == 2 && NCH % 2 == 0), "residual prefetch assumes staging tile = chunk & 1");
+    // LayerNorm statistics (LN-folded projections): the producer wrote one (mean, M2) pair per 128
+    // columns of the normalised vector; they are combined with Chan's parallel-variance formula
+    constexpr int LN_MAXS = 8;
+    float2 ln_raw[LN_MAXS];
+    float ln_mu = 0.f, ln_rstd = 0.f;
+    auto ln_issue = [&](int row) {
+#pragma unroll
+      for (int s2 = 0; s2 < LN_MAXS; ++s2)
+        ln_raw[s2] = (s2 < stats_in_slots && row < M) ? __ldg(stats_in + (size_t)row * stats_in_slots + s2) : make_float2(0.f, 0.f);
+    };
+    auto ln_combine = [&]() {
+      float msum = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < LN_MAXS; ++s2) msum += ln_raw[s2].x;  // (absent slots hold zeros)
+      ln_mu = msum / (float)stats_in_slots;
+      float m2 = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < LN_MAXS; ++s2) {
+        if (s2 < stats_in_slots) {
+          const float dm = ln_raw[s2].x - ln_mu;
+          m2 += ln_raw[s2].y + 128.f * dm * dm;
+        }
+      }
+      ln_rstd = rsqrtf(m2 / (128.f * (float)stats_in_slots) + ln_eps);
+    };
+    if (kLnFold && stats_in_slots <= LN_MAXS && pair < num_tiles) {
+      ln_issue((pair / num_n) * 2 * G_BM + (int)rank * G_BM + quarter * 32 + lane);
+      ln_combine();
+    }
     int it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
       const int as = it & 1;
@@ -440,6 +482,46 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (etid < BN) {
         const int n = n_blk * BN + etid;
         sb[etid] = (bias != nullptr && n < N) ? __ldg(bias + n) : 0.f;
+      }
+      // LayerNorm statistics of this thread's row (LN-folded projections): normally prefetched during
+      // the previous tile (below); wide rows (> 8 slots) are loaded here
+      if (kLnFold && stats_in_slots > LN_MAXS) {
+        const int row = row0 + lane;
+        ln_mu = 0.f;
+        ln_rstd = 0.f;
+        if (row < M) {
+          const float2* sp = stats_in + (size_t)row * stats_in_slots;
+          float msum = 0.f;
+          for (int s2 = 0; s2 < stats_in_slots; ++s2) msum += sp[s2].x;
+          ln_mu = msum / (float)stats_in_slots;
+          float m2 = 0.f;
+          for (int s2 = 0; s2 < stats_in_slots; ++s2) {
+            const float2 v2 = sp[s2];
+            const float dm = v2.x - ln_mu;
+            m2 += v2.y + 128.f * dm * dm;
+          }
+          ln_rstd = rsqrtf(m2 / (128.f * (float)stats_in_slots) + ln_eps);
+        }
+      }
+      const float cur_mu = ln_mu, cur_rstd = ln_rstd;
+      if (kLnFold && stats_in_slots <= LN_MAXS && t + num_pairs < num_tiles) {
+        // next tile's statistics: loads in flight while this tile is written out (the epilogue is the
+        // critical path of these GEMMs, so a load-use stall at tile start would cost ~1 us per tile)
+        const int tn = t + num_pairs;
+        ln_issue((tn / num_n) * 2 * G_BM + (int)rank * G_BM + quarter * 32 + lane);
+      }
+      if (kResid && !(dbg & 1)) {
+        // residual chunks 0 and 1 of this tile -> the two staging tiles, while the accumulator is still
+        // being computed (the stores of the previous tile have long finished reading them)
+        if (elect_one()) {
+          tma_store_wait_read<0>();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            mbar_expect_tx(&my_res_bar[c], G_STAGE_TILE);
+            tma_load_2d(my_buf0 + c * G_STAGE_TILE, &tmR, &my_res_bar[c], colbase + c * 32, row0);
+          }
+        }
+        __syncwarp();
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&acc_full[as], aphase);
@@ -454,6 +536,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * HALF_N;
       uint32_t rbuf[2][32];
       tmem_ld_32x32b_x32(taddr, rbuf[0]);
+      // running (count, mean, M2) of the bf16-rounded row over this thread's 128 columns (kStats)
+      float st_mean = 0.f, st_m2 = 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         uint32_t* r = rbuf[c & 1];
@@ -461,33 +545,48 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const bool last_of_store = (c % CH_PER_STORE) == CH_PER_STORE - 1;
         unsigned char* my_buf = my_buf0 + (sidx % NBUF) * G_STAGE_TILE;
         unsigned char* buf_row = my_buf + lane * 128;
-        if (first_of_store) {
-          if (elect_one()) {
-            tma_store_wait_read<NBUF - 1>();  // the store that used this tile two groups ago has read it
-            if (EPI == PCD_EPI_BIAS_RESIDUAL) {
-              mbar_expect_tx(&my_res_bar[0], G_STAGE_TILE);
-              tma_load_2d(my_buf, &tmR, &my_res_bar[0], colbase + c * 32, row0);
-            }
+        if (kResid) {
+          // this chunk's residual was requested one chunk (or one tile) ahead
+          if (c & 1) {
+            mbar_wait(&my_res_bar[1], res_ph1);
+            res_ph1 ^= 1;
+          } else {
+            mbar_wait(&my_res_bar[0], res_ph0);
+            res_ph0 ^= 1;
           }
+        } else if (first_of_store) {
+          if (elect_one()) tma_store_wait_read<NBUF - 1>();  // the store that used this tile two groups ago has read it
           __syncwarp();
-          if (EPI == PCD_EPI_BIAS_RESIDUAL) {
-            mbar_wait(&my_res_bar[0], res_uses & 1);
-            res_uses++;
-          }
         }
         tmem_ld_wait();
         if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);
         const float* sbc = sb + half * HALF_N + c * 32;
         float v[32];
+        if (kLnFold) {
+          // LayerNorm folded into the projection: with W' = gamma o W (bf16), s_n = sum_k W'[n,k],
+          // c_n = beta . W[n,:] + b_n:   LN(x) W^T + b = rstd (x W'^T - mu s) + c
+          const float* scc = colsum + colbase + c * 32;  // warp-uniform addresses: broadcast loads, L1-resident
+          const float nmu = -cur_mu;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(sbc + j);
-          v[j] = __uint_as_float(r[j]) + b4.x;
-          v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-          v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sbc + j);
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scc + j));
+            v[j] = fmaf(cur_rstd, fmaf(nmu, s4.x, __uint_as_float(r[j])), b4.x);
+            v[j + 1] = fmaf(cur_rstd, fmaf(nmu, s4.y, __uint_as_float(r[j + 1])), b4.y);
+            v[j + 2] = fmaf(cur_rstd, fmaf(nmu, s4.z, __uint_as_float(r[j + 2])), b4.z);
+            v[j + 3] = fmaf(cur_rstd, fmaf(nmu, s4.w, __uint_as_float(r[j + 3])), b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sbc + j);
+            v[j] = __uint_as_float(r[j]) + b4.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+          }
         }
-        if (EPI == PCD_EPI_BIAS_GELU) {
+        if (kGelu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
@@ -504,12 +603,49 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int i = 0; i < 8; ++i) {
             float4* pp = reinterpret_cast<float4*>(buf_row + ((i ^ sw) * 16));
             float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            if (EPI == PCD_EPI_BIAS_RESIDUAL) {
+            if (kResid) {
               const float4 rr = *pp;
               o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+              if (kStats) {
+                v[4 * i] = o.x; v[4 * i + 1] = o.y; v[4 * i + 2] = o.z; v[4 * i + 3] = o.w;
+              }
             }
             *pp = o;
           }
+        }
+        if (kStats) {
+          // bf16 copy of the updated residual rows (the A operand of the next, LN-folded projection)
+          // and the row statistics of exactly those rounded values
+          unsigned char* bbuf_row = my_bbuf + lane * 128;
+          float q[32];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t pkd = pack_bf16x2(v[8 * i + 2 * u], v[8 * i + 2 * u + 1]);
+              w4[u] = pkd;
+              q[8 * i + 2 * u] = __uint_as_float(pkd << 16);
+              q[8 * i + 2 * u + 1] = __uint_as_float(pkd & 0xffff0000u);
+            }
+            const int piece = ((c & 1) * 4 + i) ^ sw;
+            *reinterpret_cast<uint4*>(bbuf_row + piece * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+          float csum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) csum += q[j];
+          const float cmean = csum * (1.f / 32.f);
+          float cm2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float dq = q[j] - cmean;
+            cm2 = fmaf(dq, dq, cm2);
+          }
+          // merge (32 values) into the running statistics of 32*c values
+          const float na = 32.f * c, nb = 32.f;
+          const float delta = cmean - st_mean;
+          st_mean += delta * (nb / (na + nb));
+          st_m2 += cm2 + delta * delta * (na * nb / (na + nb));
         }
         if (last_of_store) {
           fence_proxy_async_smem();
@@ -518,9 +654,28 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int col = colbase + (c / CH_PER_STORE) * (OUT_BF16 ? 64 : 32);
             tma_store_2d(&tmC, my_buf, col, row0);
             tma_store_commit();
+            if (kStats && (c & 1)) {
+              tma_store_2d(&tmC2, my_bbuf, colbase + (c >> 1) * 64, row0);
+              tma_store_commit();
+            }
+            if (kResid) {
+              // the stores just issued must have read their tiles before (a) the residual of chunk
+              // c + 2 lands in this staging tile and (b) the next chunk writes the bf16 tile
+              tma_store_wait_read<0>();
+              if (c + 2 < NCH) {
+                mbar_expect_tx(&my_res_bar[c & 1], G_STAGE_TILE);
+                tma_load_2d(my_buf, &tmR, &my_res_bar[c & 1], colbase + (c + 2) * 32, row0);
+              }
+            }
           }
+          if (kResid) __syncwarp();
           ++sidx;
         }
+      }
+      if (kLnFold && stats_in_slots <= LN_MAXS && t + num_pairs < num_tiles) ln_combine();
+      if (kStats) {
+        const int row = row0 + lane;
+        if (row < M) stats_out[(size_t)row * (N / HALF_N) + n_blk * 2 + half] = make_float2(st_mean, st_m2);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -538,9 +693,19 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+struct LnArgs {  // extra operands of the residual+statistics and LayerNorm-folded epilogues
+  CUtensorMap tmC2;
+  const float* colsum;
+  const float2* stats_in;
+  int stats_in_slots;
+  float2* stats_out;
+  float ln_eps;
+};
+
 template <int EPI, bool OUT_BF16>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC,
-                        const CUtensorMap& tmR, const float* bias, int M, int N, int K, cudaStream_t st) {
+                        const CUtensorMap& tmR, const float* bias, int M, int N, int K, cudaStream_t st,
+                        const LnArgs* ln = nullptr) {
   using Cfg = Gemm2Cfg<EPI>;
   auto kern = gemm_bf16_tc2_kernel<EPI, OUT_BF16>;
   static bool attr_set = false;
@@ -555,15 +720,28 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CU
   const int tiles = ceil_div(M, 2 * G_BM) * ceil_div(N, Cfg::BN);
   int pairs = num_sms() / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, bias, M, N, K, g_gemm_debug);
+  static const LnArgs none = {};
+  const LnArgs& x = ln ? *ln : none;
+  kern<<<2 * pairs, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, ln ? x.tmC2 : tmC, bias, x.colsum, x.stats_in,
+                                                       x.stats_in_slots, x.stats_out, x.ln_eps, M, N, K, g_gemm_debug);
   PCD_CHECK_LAUNCH("gemm_bf16(pair)");
   return PCD_OK;
 }
 
 static int dispatch_epi2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& c, const CUtensorMap& r,
-                         const float* bias, int out_prec, int M, int N, int K, int epi, cudaStream_t st) {
+                         const float* bias, int out_prec, int M, int N, int K, int epi, cudaStream_t st,
+                         const LnArgs* ln = nullptr) {
   const bool ob = out_prec == PCD_BF16;
   switch (epi) {
+    case PCD_EPI_RESIDUAL_STATS:
+      if (ob || ln == nullptr) break;
+      return launch_gemm2<PCD_EPI_RESIDUAL_STATS, false>(a, w, c, r, bias, M, N, K, st, ln);
+    case PCD_EPI_LN_BIAS:
+      if (!ob || ln == nullptr) break;
+      return launch_gemm2<PCD_EPI_LN_BIAS, true>(a, w, c, r, bias, M, N, K, st, ln);
+    case PCD_EPI_LN_BIAS_GELU:
+      if (!ob || ln == nullptr) break;
+      return launch_gemm2<PCD_EPI_LN_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st, ln);
     case PCD_EPI_BIAS:
       return ob ? launch_gemm2<PCD_EPI_BIAS, true>(a, w, c, r, bias, M, N, K, st)
                 : launch_gemm2<PCD_EPI_BIAS, false>(a, w, c, r, bias, M, N, K, st);
@@ -624,18 +802,34 @@ static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& w, const CUtens
 
 using namespace pcd;
 
-extern "C" int pcd_gemm_bf16(const uint16_t* A, int lda, const uint16_t* W, int ldw, const float* bias,
-                             const float* residual, int ldr, void* C, int ldc, int out_precision,
-                             int M, int N, int K, int epilogue, void* stream) {
+static int gemm_bf16_impl(const pcd_gemm_args& g, void* stream) {
+  const uint16_t* A = (const uint16_t*)g.A;
+  const uint16_t* W = (const uint16_t*)g.W;
+  const int M = g.M, N = g.N, K = g.K, lda = g.lda, ldw = g.ldw, ldc = g.ldc, ldr = g.ldr;
+  const int epilogue = g.epilogue, out_precision = g.out_precision;
+  void* C = g.C;
+  const float* residual = g.residual;
   PCD_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem");
   PCD_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm_bf16: K, lda, ldw must be multiples of 8 (K=%d lda=%d ldw=%d)", K, lda, ldw);
   PCD_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm_bf16: operands must be 16-byte aligned");
   const bool ob = out_precision == PCD_BF16;
   PCD_CHECK_ARG(out_precision == PCD_BF16 || out_precision == PCD_F32, "gemm_bf16: bad output precision");
   PCD_CHECK_ARG(ldc % (ob ? 8 : 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm_bf16: C must be 16-byte aligned with a 16-byte row pitch (ldc=%d)", ldc);
-  PCD_CHECK_ARG(epilogue != PCD_EPI_BIAS_RESIDUAL || (residual != nullptr && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && !ob),
+  const bool resid = epilogue == PCD_EPI_BIAS_RESIDUAL || epilogue == PCD_EPI_RESIDUAL_STATS;
+  const bool lnfold = epilogue == PCD_EPI_LN_BIAS || epilogue == PCD_EPI_LN_BIAS_GELU;
+  PCD_CHECK_ARG(!resid || (residual != nullptr && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && !ob),
                 "gemm_bf16: residual epilogue needs an fp32, 16-byte aligned residual and fp32 output");
   const bool use_pair = (N % 256 == 0) && M >= 512 && !(g_gemm_debug & 4);
+  if (epilogue == PCD_EPI_RESIDUAL_STATS) {
+    PCD_CHECK_ARG(use_pair, "gemm_bf16: the residual+statistics epilogue needs N %% 256 == 0 and M >= 512 (N=%d M=%d)", N, M);
+    PCD_CHECK_ARG(g.C2 != nullptr && g.ldc2 % 8 == 0 && (reinterpret_cast<uintptr_t>(g.C2) & 15) == 0 && g.stats_out != nullptr,
+                  "gemm_bf16: the residual+statistics epilogue needs a 16-byte aligned bf16 C2 and a stats_out buffer");
+  }
+  if (lnfold) {
+    PCD_CHECK_ARG(use_pair && ob, "gemm_bf16: LayerNorm-folded epilogues need N %% 256 == 0, M >= 512 and bf16 output (N=%d M=%d)", N, M);
+    PCD_CHECK_ARG(K % 128 == 0 && g.stats_in != nullptr && g.colsum != nullptr && g.bias != nullptr,
+                  "gemm_bf16: LayerNorm-folded epilogues need K %% 128 == 0, stats_in, colsum and the folded bias");
+  }
   const int BN = use_pair ? 128 /* W rows staged per CTA */ : ((N % 256 == 0 || N > 1024) ? 256 : 128);
   CUtensorMap tmA, tmW, tmC, tmR;
   uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[1] = {(uint64_t)lda * 2};
@@ -656,13 +850,44 @@ extern "C" int pcd_gemm_bf16(const uint16_t* A, int lda, const uint16_t* W, int 
     if ((rc = encode_tmap_f32(&tmC, C, 2, dimsC, strC, boxC)) != PCD_OK) return rc;
   }
   tmR = tmC;
-  if (epilogue == PCD_EPI_BIAS_RESIDUAL) {
+  if (resid) {
     uint64_t strR[1] = {(uint64_t)ldr * 4};
     uint32_t boxR[2] = {32, 32};
     if ((rc = encode_tmap_f32(&tmR, residual, 2, dimsC, strR, boxR)) != PCD_OK) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_pair) return dispatch_epi2(tmA, tmW, tmC, tmR, bias, out_precision, M, N, K, epilogue, st);
-  if (BN == 256) return dispatch_epi<256>(tmA, tmW, tmC, tmR, bias, out_precision, M, N, K, epilogue, st);
-  return dispatch_epi<128>(tmA, tmW, tmC, tmR, bias, out_precision, M, N, K, epilogue, st);
+  if (epilogue == PCD_EPI_RESIDUAL_STATS || lnfold) {
+    LnArgs ln = {};
+    ln.tmC2 = tmC;
+    if (epilogue == PCD_EPI_RESIDUAL_STATS) {
+      uint64_t strC2[1] = {(uint64_t)g.ldc2 * 2};
+      uint32_t boxC2[2] = {64, 32};
+      if ((rc = encode_tmap_bf16(&ln.tmC2, g.C2, 2, dimsC, strC2, boxC2)) != PCD_OK) return rc;
+    }
+    ln.colsum = g.colsum;
+    ln.stats_in = reinterpret_cast<const float2*>(g.stats_in);
+    ln.stats_in_slots = K / 128;
+    ln.stats_out = reinterpret_cast<float2*>(g.stats_out);
+    ln.ln_eps = g.ln_eps;
+    return dispatch_epi2(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st, &ln);
+  }
+  if (use_pair) return dispatch_epi2(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st);
+  if (BN == 256) return dispatch_epi<256>(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st);
+  return dispatch_epi<128>(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st);
+}
+
+extern "C" int pcd_gemm_bf16_ex(const pcd_gemm_args* args, void* stream) {
+  PCD_CHECK_ARG(args != nullptr, "gemm_bf16_ex: null argument block");
+  return gemm_bf16_impl(*args, stream);
+}
+
+extern "C" int pcd_gemm_bf16(const uint16_t* A, int lda, const uint16_t* W, int ldw, const float* bias,
+                             const float* residual, int ldr, void* C, int ldc, int out_precision,
+                             int M, int N, int K, int epilogue, void* stream) {
+  PCD_CHECK_ARG(epilogue >= PCD_EPI_BIAS && epilogue <= PCD_EPI_BIAS_RESIDUAL,
+                "gemm_bf16: epilogue %d needs pcd_gemm_bf16_ex", epilogue);
+  pcd_gemm_args g = {};
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.bias = bias; g.residual = residual; g.ldr = ldr;
+  g.C = C; g.ldc = ldc; g.out_precision = out_precision; g.M = M; g.N = N; g.K = K; g.epilogue = epilogue;
+  return gemm_bf16_impl(g, stream);
 }

@@ -98,7 +98,7 @@ extern int g_gemm_debug;
 
 using namespace pcd;
 
-extern "C" int pcd_abi_version(void) { return 1; }
+extern "C" int pcd_abi_version(void) { return 2; }
 extern "C" unsigned long long pcd_launch_count(void) { return g_launch_count; }
 extern "C" const char* pcd_last_error(void) { return g_err; }
 
@@ -123,8 +123,10 @@ extern "C" int pcd_check_device(void) {
 // (tcgen05.mma A-from-TMEM, 2 CTAs/SM), 0 = P staged in swizzled shared memory.
 // Profiling aid (results are WRONG when set): bit 0 = GEMM epilogue skipped, bit 1 = GEMM TMA
 // loads skipped.  Used by tools/ to separate main-loop from epilogue time.
+static int g_disable_ln_fold = 0;  // debug flag bit 4: run the forward with separate LayerNorm kernels
 extern "C" int pcd_set_debug_flags(int flags) {
-  g_gemm_debug = flags;
+  g_gemm_debug = flags & 15;
+  g_disable_ln_fold = (flags >> 4) & 1;
   return PCD_OK;
 }
 
@@ -179,7 +181,7 @@ struct pcd_model {
 
 namespace {
 struct Workspace {
-  float *temb, *thid, *tcond, *h;
+  float *temb, *thid, *tcond, *h, *stats;
   void *xn, *qkv, *att, *hid, *y;
   size_t total;
 };
@@ -205,6 +207,7 @@ Workspace carve(const pcd_model_desc& d, int seqs, unsigned char* base) {
   w.att = take(M * d.width * es);
   w.hid = take(M * d.width * 4 * es);
   w.y = take(M * d.width * es);
+  w.stats = (float*)take(M * (size_t)((d.width + 127) / 128) * 8);  // (mean, M2) per 128 columns (LN-folded path)
   w.total = off;
   return w;
 }
@@ -292,6 +295,45 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
       return pcd_gemm_bf16((const uint16_t*)A, lda, (const uint16_t*)Wt, K, bias, nullptr, 0, C, N, PCD_BF16, M, N, K, epi, stream);
     return pcd_gemm_f32((const float*)A, lda, (const float*)Wt, K, bias, nullptr, 0, (float*)C, N, M, N, K, epi, stream);
   };
+  // LayerNorm-folded path (bf16, width % 256 == 0, >= 512 tokens, folded weights supplied): no
+  // LayerNorm kernels at all.  The c_proj / mlp.c_proj GEMMs update the fp32 residual stream in their
+  // epilogue and emit its bf16 copy + per-row statistics; c_qkv / c_fc consume that copy with
+  // W' = gamma o W and apply mean / rstd algebraically in their epilogue (gemm_tc.cu).
+  bool fold = bf && W % 256 == 0 && M >= 512 && !g_disable_ln_fold;
+  for (int l = 0; l < d.layers && fold; ++l) {
+    const pcd_block_weights& b = m->blocks[l];
+    fold = b.w_qkv_ln && b.w_fc_ln && b.qkv_colsum && b.qkv_const && b.fc_colsum && b.fc_const;
+  }
+  if (fold) {
+    PCD_TRY(pcd_cast_rowstats(w.h, W, (uint16_t*)w.xn, W, w.stats, M, W, stream));
+    auto lin_ln = [&](const void* Wt, const float* colsum, const float* cst, void* C, int N, int epi) -> int {
+      pcd_gemm_args g = {};
+      g.A = w.xn; g.lda = W; g.W = Wt; g.ldw = W; g.bias = cst; g.colsum = colsum; g.stats_in = w.stats;
+      g.ln_eps = d.ln_eps; g.C = C; g.ldc = N; g.out_precision = PCD_BF16; g.M = M; g.N = N; g.K = W; g.epilogue = epi;
+      return pcd_gemm_bf16_ex(&g, stream);
+    };
+    auto lin_res = [&](const void* A, int K, const void* Wt, const float* bias) -> int {
+      pcd_gemm_args g = {};
+      g.A = A; g.lda = K; g.W = Wt; g.ldw = K; g.bias = bias; g.residual = w.h; g.ldr = W; g.C = w.h; g.ldc = W;
+      g.out_precision = PCD_F32; g.C2 = w.xn; g.ldc2 = W; g.stats_out = w.stats; g.M = M; g.N = W; g.K = K;
+      g.epilogue = PCD_EPI_RESIDUAL_STATS;
+      return pcd_gemm_bf16_ex(&g, stream);
+    };
+    for (int l = 0; l < d.layers; ++l) {
+      const pcd_block_weights& b = m->blocks[l];
+      PCD_TRY(lin_ln(b.w_qkv_ln, b.qkv_colsum, b.qkv_const, w.qkv, 3 * W, PCD_EPI_LN_BIAS));
+      pcd_attn_operand q = {w.qkv, (int64_t)L * 3 * W, 3 * W, 3 * 64};
+      pcd_attn_operand k = {(const unsigned char*)w.qkv + 64 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
+      pcd_attn_operand v = {(const unsigned char*)w.qkv + 128 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
+      PCD_TRY(pcd_attention(&q, &k, &v, w.att, (int64_t)L * W, W, seqs, d.heads, L, L, qk_scale, qk_scale, nullptr, prec, stream));
+      PCD_TRY(lin_res(w.att, W, b.w_proj, b.b_proj));
+      PCD_TRY(lin_ln(b.w_fc_ln, b.fc_colsum, b.fc_const, w.hid, 4 * W, PCD_EPI_LN_BIAS_GELU));
+      PCD_TRY(lin_res(w.hid, 4 * W, b.w_fc2, b.b_fc2));
+    }
+    PCD_TRY(pcd_output_proj(w.h, nullptr, prec, seqs, d.n_prefix, d.n_points, W, d.ln_post_g, d.ln_post_b, d.ln_eps,
+                            d.out_w, d.out_b, out_channels, out, stream));
+    return PCD_OK;
+  }
   for (int l = 0; l < d.layers; ++l) {
     const pcd_block_weights& b = m->blocks[l];
     if (l == 0) {

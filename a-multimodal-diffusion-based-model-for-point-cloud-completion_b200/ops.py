@@ -110,6 +110,56 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out.reshape(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
 
 
+def cast_rowstats(h: torch.Tensor):
+    """bf16 copy of the fp32 residual stream h [rows, dim] + per-128-column (mean, M2) of the rounded
+    values [rows, dim/128, 2]: the inputs of the LayerNorm-folded projections."""
+    require_cuda(h)
+    assert h.dtype == torch.float32 and h.dim() == 2 and h.shape[1] % 128 == 0
+    rows, dim = h.shape
+    hb = torch.empty(rows, dim, device=h.device, dtype=torch.bfloat16)
+    stats = torch.empty(rows, dim // 128, 2, device=h.device, dtype=torch.float32)
+    check(_lib.load().pcd_cast_rowstats(ptr(h), _rowmajor2d(h), ptr(hb), dim, ptr(stats), rows, dim, stream_ptr()),
+          "cast_rowstats")
+    return hb, stats
+
+
+def linear_residual_stats(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, h: torch.Tensor):
+    """h <- h + a W^T + b in place (fp32 residual stream, transformer.py:113-114); returns
+    (bf16 copy of the updated h, its row statistics [rows, N/128, 2])."""
+    require_cuda(a, weight, h)
+    assert a.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and h.dtype == torch.float32
+    M, K = a.shape
+    N = weight.shape[0]
+    assert h.shape == (M, N)
+    hb = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    stats = torch.empty(M, N // 128, 2, device=a.device, dtype=torch.float32)
+    g = _lib.GemmArgs()
+    g.A, g.lda, g.W, g.ldw, g.bias = ptr(a), _rowmajor2d(a), ptr(weight), _rowmajor2d(weight), ptr(bias)
+    g.residual, g.ldr, g.C, g.ldc, g.out_precision = ptr(h), _rowmajor2d(h), ptr(h), _rowmajor2d(h), _lib.PCD_F32
+    g.C2, g.ldc2, g.stats_out = ptr(hb), N, ptr(stats)
+    g.M, g.N, g.K, g.epilogue = M, N, K, _lib.EPI_RESIDUAL_STATS
+    check(_lib.load().pcd_gemm_bf16_ex(C.byref(g), stream_ptr()), "gemm_bf16_ex(residual+stats)")
+    return hb, stats
+
+
+def linear_layernorm_folded(hb: torch.Tensor, stats: torch.Tensor, w_folded: torch.Tensor, colsum: torch.Tensor,
+                            const: torch.Tensor, eps: float = 1e-5, gelu: bool = False) -> torch.Tensor:
+    """(gelu)(LayerNorm(h) W^T + b) evaluated from the bf16 copy hb of h, its row statistics and the
+    folded weights: rstd (hb (gamma o W)^T - mu colsum) + const."""
+    require_cuda(hb, w_folded)
+    assert hb.dtype == torch.bfloat16 and w_folded.dtype == torch.bfloat16
+    M, K = hb.shape
+    N = w_folded.shape[0]
+    out = torch.empty(M, N, device=hb.device, dtype=torch.bfloat16)
+    g = _lib.GemmArgs()
+    g.A, g.lda, g.W, g.ldw, g.bias = ptr(hb), _rowmajor2d(hb), ptr(w_folded), _rowmajor2d(w_folded), ptr(const)
+    g.colsum, g.stats_in, g.ln_eps = ptr(colsum), ptr(stats), eps
+    g.C, g.ldc, g.out_precision = ptr(out), N, _lib.PCD_BF16
+    g.M, g.N, g.K, g.epilogue = M, N, K, (_lib.EPI_LN_BIAS_GELU if gelu else _lib.EPI_LN_BIAS)
+    check(_lib.load().pcd_gemm_bf16_ex(C.byref(g), stream_ptr()), "gemm_bf16_ex(layernorm-folded)")
+    return out
+
+
 def _operand(t: torch.Tensor, offset: int, batch_stride: int, row_stride: int, head_stride: int):
     return AttnOperand(C.c_void_p(t.data_ptr() + offset * t.element_size()), batch_stride, row_stride, head_stride)
 

@@ -200,6 +200,20 @@ class PointDiffusionTransformer(nn.Module):
             b.w_proj, b.b_proj = mat(blk.attn.c_proj.weight), f32(blk.attn.c_proj.bias)
             b.w_fc, b.b_fc = mat(blk.mlp.c_fc.weight), f32(blk.mlp.c_fc.bias)
             b.w_fc2, b.b_fc2 = mat(blk.mlp.c_proj.weight), f32(blk.mlp.c_proj.bias)
+            if prec == PCD_BF16 and self.backbone.width % 256 == 0:
+                # LayerNorm folded into the projection that follows it (ln_1 -> c_qkv, ln_2 -> c_fc,
+                # transformer.py:108-114):  LN(x) W^T + b = rstd (x (gamma o W)^T - mu s) + c  with
+                # s_n = sum_k (gamma o W)[n, k] of the bf16-ROUNDED folded weights (what the tensor
+                # cores multiply by) and c_n = beta . W[n, :] + b_n.  Step-invariant: done once here.
+                def fold(lin, ln):
+                    w32, g, be = lin.weight.detach().float(), ln.weight.detach().float(), ln.bias.detach().float()
+                    wf = (w32 * g[None, :]).to(torch.bfloat16).contiguous()
+                    colsum = wf.float().sum(dim=1).contiguous()
+                    const = (w32.double() @ be.double() + lin.bias.detach().double()).float().contiguous()
+                    keep.extend((wf, colsum, const))
+                    return ptr(wf), ptr(colsum), ptr(const)
+                b.w_qkv_ln, b.qkv_colsum, b.qkv_const = fold(blk.attn.c_qkv, blk.ln_1)
+                b.w_fc_ln, b.fc_colsum, b.fc_const = fold(blk.mlp.c_fc, blk.ln_2)
         n_prefix, time_slot = self._prefix_layout()
         width = self.backbone.width
         freqs = ops.timestep_freqs(width, device=self.ln_pre.weight.device)

@@ -198,18 +198,37 @@ def kernel_breakdown(P, model, B2, L, width, heads, layers, Bc, C, N, pk):
     evals = 127
     per = evals * layers
     y = torch.empty(M, width, device=dev, dtype=bf)
-    add("gemm_qkv", lambda: ops.linear(a_d, w_qkv, bias(3 * width), out=qkv), per, flops=2.0 * M * 3 * width * width)
-    add("gemm_attn_proj", lambda: ops.linear(a_d, w_proj, bias(width), out=y), per, flops=2.0 * M * width * width)
-    add("gemm_fc1_gelu", lambda: ops.linear(a_d, w_fc, bias(4 * width), epilogue=1, out=hid), per,
-        flops=2.0 * M * 4 * width * width)
-    add("gemm_fc2", lambda: ops.linear(a_4d, w_fc2, bias(width), out=y), per, flops=2.0 * M * 4 * width * width)
+    fold = width % 256 == 0 and M >= 512   # the LayerNorm-folded forward (pcd_model_forward's default path)
+    if fold:
+        hb, stats = ops.cast_rowstats(h)
+        colsum = lambda w: w.float().sum(dim=1).contiguous()
+        cs_qkv, cs_fc = colsum(w_qkv), colsum(w_fc)
+        add("gemm_qkv_lnfold", lambda: ops.linear_layernorm_folded(hb, stats, w_qkv, cs_qkv, bias(3 * width)), per,
+            flops=2.0 * M * 3 * width * width)
+        # residual update + bf16 copy + row statistics in the epilogue: K = width makes this one HBM-bound
+        # (A 2K/N + h read 4 + h write 4 + bf16 copy 2 bytes per output element)
+        add("gemm_attn_proj_resid_stats", lambda: ops.linear_residual_stats(a_d, w_proj, bias(width), h), per,
+            bytes_=M * width * 12.0)
+        res["gemm_attn_proj_resid_stats"]["tflops"] = 2.0 * M * width * width / (res["gemm_attn_proj_resid_stats"]["ms"] * 1e-3) / 1e12
+        add("gemm_fc1_lnfold_gelu", lambda: ops.linear_layernorm_folded(hb, stats, w_fc, cs_fc, bias(4 * width), gelu=True),
+            per, flops=2.0 * M * 4 * width * width)
+        add("gemm_fc2_resid_stats", lambda: ops.linear_residual_stats(a_4d, w_fc2, bias(width), h), per,
+            flops=2.0 * M * 4 * width * width)
+        res["gemm_fc2_resid_stats"]["hbm_gbs"] = M * width * 18.0 / (res["gemm_fc2_resid_stats"]["ms"] * 1e-3) / 1e9
+        add("cast_rowstats", lambda: ops.cast_rowstats(h), evals, bytes_=M * width * 6.0)
+    else:
+        add("gemm_qkv", lambda: ops.linear(a_d, w_qkv, bias(3 * width), out=qkv), per, flops=2.0 * M * 3 * width * width)
+        add("gemm_attn_proj", lambda: ops.linear(a_d, w_proj, bias(width), out=y), per, flops=2.0 * M * width * width)
+        add("gemm_fc1_gelu", lambda: ops.linear(a_d, w_fc, bias(4 * width), epilogue=1, out=hid), per,
+            flops=2.0 * M * 4 * width * width)
+        add("gemm_fc2", lambda: ops.linear(a_4d, w_fc2, bias(width), out=y), per, flops=2.0 * M * 4 * width * width)
+        lnw, lnb = torch.ones(width, device=dev), torch.zeros(width, device=dev)
+        y.normal_()
+        # fused residual-add + LayerNorm: reads h (fp32) + y (bf16), writes h (fp32) + xn (bf16)
+        add("add_layernorm", lambda: ops.add_layernorm(h, y, lnw, lnb, out_dtype=bf), 2 * per, bytes_=M * width * 12.0)
     qkv3 = qkv.view(B2, L, 3 * width)
     qkv3.normal_()
     add("flash_attention", lambda: ops.self_attention(qkv3, heads), per, flops=4.0 * L * L * 64 * heads * B2)
-    lnw, lnb = torch.ones(width, device=dev), torch.zeros(width, device=dev)
-    y.normal_()
-    # fused residual-add + LayerNorm: reads h (fp32) + y (bf16), writes h (fp32) + xn (bf16)
-    add("add_layernorm", lambda: ops.add_layernorm(h, y, lnw, lnb, out_dtype=bf), 2 * per, bytes_=M * width * 12.0)
     # fused sampler update (state is tiny at the configured batch: L2-resident, launch bound)
     d = P.diffusion_from_config(P.DIFFUSION_CONFIGS["base40M"])
     plan = P.HeunPlan(d, 64, 1e-3, 120.0, 7.0, 3.0)

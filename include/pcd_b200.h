@@ -47,7 +47,13 @@ typedef enum { PCD_F32 = 0, PCD_BF16 = 1 } pcd_precision;
 typedef enum {
   PCD_EPI_BIAS = 0,          /* nn.Linear                         (transformer.py:45-47,55-56) */
   PCD_EPI_BIAS_GELU = 1,     /* Linear + exact-erf GELU           (transformer.py:57,62)       */
-  PCD_EPI_BIAS_RESIDUAL = 2  /* residual + Linear                 (transformer.py:113-114)     */
+  PCD_EPI_BIAS_RESIDUAL = 2, /* residual + Linear                 (transformer.py:113-114)     */
+  /* pcd_gemm_bf16_ex only -- the LayerNorms of a block folded into its projections: */
+  PCD_EPI_RESIDUAL_STATS = 3,/* h <- h + A W^T + b (fp32, in place), C2 = bf16(h), per-row (mean, M2)
+                                of C2 per 128 columns -> stats_out        (transformer.py:113-114) */
+  PCD_EPI_LN_BIAS = 4,       /* LayerNorm(x) W^T + b evaluated as rstd (x (gamma o W)^T - mu s) + c
+                                from the bf16 copy x and its row statistics (transformer.py:108-114) */
+  PCD_EPI_LN_BIAS_GELU = 5   /* same + exact-erf GELU                  (transformer.py:110,57,62) */
 } pcd_epilogue;
 
 PCD_API int pcd_abi_version(void);
@@ -69,7 +75,9 @@ PCD_API int pcd_set_attention_variant(int variant);
 /* The variant the library starts with (what pcd_model_forward uses unless overridden). */
 PCD_API int pcd_default_attention_variant(void);
 /* Profiling aid -- results are INVALID while non-zero: bit 0 skips the GEMM epilogue, bit 1 skips
- * the GEMM TMA loads (separates main-loop, load and epilogue time in tools/gemm_probe.py). */
+ * the GEMM TMA loads (separates main-loop, load and epilogue time in tools/gemm_probe.py).
+ * Bit 4 (results stay valid): pcd_model_forward runs with separate LayerNorm kernels even when the
+ * LayerNorm-folded weights are present (A/B timing and parity of the two paths). */
 PCD_API int pcd_set_debug_flags(int flags);
 
 /* ------------------------------------------------------------------ */
@@ -133,6 +141,33 @@ PCD_API int pcd_gemm_f32(const float* A, int lda, const float* W, int ldw, const
 PCD_API int pcd_gemm_bf16(const uint16_t* A, int lda, const uint16_t* W, int ldw, const float* bias,
                   const float* residual, int ldr, void* C, int ldc, int out_precision,
                   int M, int N, int K, int epilogue, void* stream);
+
+/* Extended form (argument block; zero-initialise, then fill in what the epilogue needs).
+ *  PCD_EPI_RESIDUAL_STATS: residual (fp32, may alias C), C fp32, C2 = bf16 copy of the updated C,
+ *    stats_out float2 [M, N/128] = (mean, M2 = sum (x - mean)^2) of C2 per 128 columns.
+ *  PCD_EPI_LN_BIAS(_GELU): A = that bf16 copy [M, K], W = bf16(gamma o W_lin), colsum[n] = sum_k W[n, k]
+ *    (of the rounded folded weights), bias[n] = beta . W_lin[n, :] + b_lin[n], stats_in float2 [M, K/128],
+ *    ln_eps; C bf16.  Both need N % 256 == 0 and M >= 512 (CTA-pair kernel). */
+typedef struct {
+  const void* A; int lda;          /* bf16 [M, K] */
+  const void* W; int ldw;          /* bf16 [N, K] */
+  const float* bias;               /* fp32 [N] or NULL */
+  const float* residual; int ldr;  /* fp32 [M, N] (residual epilogues) */
+  void* C; int ldc; int out_precision;
+  void* C2; int ldc2;              /* bf16 [M, N] second output (RESIDUAL_STATS) */
+  float* stats_out;                /* float2 [M, N/128] (RESIDUAL_STATS) */
+  const float* stats_in;           /* float2 [M, K/128] (LN_*) */
+  const float* colsum;             /* fp32 [N] (LN_*) */
+  float ln_eps;
+  int M, N, K, epilogue;
+} pcd_gemm_args;
+PCD_API int pcd_gemm_bf16_ex(const pcd_gemm_args* args, void* stream);
+
+/* bf16 copy + row statistics of an fp32 matrix x [rows, dim] (dim % 128 == 0): out = bf16(x),
+ * stats float2 [rows, dim/128] = (mean, M2) of the ROUNDED values per 128 columns -- the form the
+ * LN-folded projections consume (used once per forward, after ln_pre). */
+PCD_API int pcd_cast_rowstats(const float* x, int ldx, uint16_t* out, int ld_out, float* stats,
+                              int rows, int dim, void* stream);
 
 /* ------------------------------------------------------------------ */
 /* Attention (head dim 64), softmax in fp32                             */
@@ -220,6 +255,12 @@ typedef struct {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;          /* ln_1, ln_2                     */
   const void *w_qkv, *w_proj, *w_fc, *w_fc2;           /* [3d,d] [d,d] [4d,d] [d,4d]; fp32 or bf16 per precision */
   const float *b_qkv, *b_proj, *b_fc, *b_fc2;
+  /* Optional (bf16 mode; all six or none): LayerNorm-folded forms of c_qkv and mlp.c_fc, prepared by
+   * the host once per weight load -- w_*_ln = bf16(gamma o W), *_colsum[n] = sum_k w_*_ln[n, k],
+   * *_const[n] = beta . W[n, :] + b[n].  When present (and width % 256 == 0, >= 512 tokens) the
+   * forward runs without LayerNorm kernels. */
+  const void *w_qkv_ln, *w_fc_ln;
+  const float *qkv_colsum, *qkv_const, *fc_colsum, *fc_const;
 } pcd_block_weights;
 
 typedef struct {

@@ -41,6 +41,36 @@ def test_forward_full_size(case, dtype, tol):
     assert rel(y, g["out"]) < tol, describe(y, g["out"], f"{case} {dtype}")
 
 
+@pytest.mark.parametrize("case", ["full_imagevec", "full_base300M"])
+def test_forward_layernorm_folded_vs_separate(case):
+    """The LayerNorm-folded bf16 forward (no LayerNorm kernels; residual update, bf16 copy and row
+    statistics in the c_proj epilogues) against the same forward with separate LayerNorm kernels
+    (debug flag bit 4), and both against the reference golden."""
+    import pcd_b200 as P
+    lib = P._lib.load()
+    g = load_golden("forward_" + case)
+    model, cfg, _ = build_model(case, torch.bfloat16)
+    x, t, kw = cases.forward_inputs(case)
+    n0 = lib.pcd_launch_count()
+    with torch.no_grad():
+        y_fold = model(x.to(DEV), t.to(DEV), **to_dev(kw)).clone()
+    n_fold = lib.pcd_launch_count() - n0
+    lib.pcd_set_debug_flags(16)
+    try:
+        n0 = lib.pcd_launch_count()
+        with torch.no_grad():
+            y_sep = model(x.to(DEV), t.to(DEV), **to_dev(kw)).clone()
+        n_sep = lib.pcd_launch_count() - n0
+    finally:
+        lib.pcd_set_debug_flags(0)
+    torch.cuda.synchronize()
+    layers = cfg["layers"]
+    assert n_sep - n_fold == 2 * layers - 1, (n_sep, n_fold)   # 2 LayerNorm launches per block vs one cast
+    assert rel(y_fold, g["out"]) < TOL_BF16 and rel(y_sep, g["out"]) < TOL_BF16
+    assert rel(y_fold, y_sep) < 1e-2, describe(y_fold, y_sep, case)
+    print(f"{case}: folded vs golden {rel(y_fold, g['out']):.2e}, separate vs golden {rel(y_sep, g['out']):.2e}")
+
+
 def test_forward_cfg_shares_x():
     """2B-sequence CFG forward (cond rows then uncond rows sharing x) == two B-sized calls."""
     model, cfg, _ = build_model("small_imagevec", torch.float32)

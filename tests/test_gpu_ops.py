@@ -120,6 +120,64 @@ def test_gemm_bf16_large_persistent():
     assert rel(got, want) < 1e-4, describe(got, want)
 
 
+def _slot_stats(hb):
+    x = hb.float().view(hb.shape[0], -1, 128)
+    mean = x.mean(dim=2)
+    return torch.stack([mean, ((x - mean[..., None]) ** 2).sum(dim=2)], dim=2)
+
+
+def test_cast_rowstats():
+    """bf16 copy of the residual stream + (mean, M2) per 128 columns of the rounded values."""
+    h = (det.normal((777, 512), 801) * 3.0 + 0.7).to(DEV)
+    hb, stats = ops.cast_rowstats(h)
+    torch.cuda.synchronize()
+    assert torch.equal(hb, h.bfloat16())
+    want = _slot_stats(hb)
+    assert rel(stats, want) < 1e-5, describe(stats, want)
+
+
+@pytest.mark.parametrize("M,N,K", [(128 * 37 + 5, 512, 512), (2048, 512, 2048), (1500, 1024, 1024)])
+def test_gemm_residual_stats(M, N, K):
+    """PCD_EPI_RESIDUAL_STATS: h <- h + A W^T + b in place, bf16 copy and row statistics
+    (reference transformer.py:113-114, the residual update of a block)."""
+    a = bf16_round(det.normal((M, K), 810)).to(DEV).bfloat16()
+    w = bf16_round(det.uniform((N, K), 811, 1 / math.sqrt(K))).to(DEV).bfloat16()
+    bias = det.uniform((N,), 812, 0.5).to(DEV)
+    h0 = (det.normal((M, N), 813) * 2.0).to(DEV)
+    want = h0.double() + a.double() @ w.double().t() + bias.double()
+    h = h0.clone()
+    hb, stats = ops.linear_residual_stats(a, w, bias, h)
+    torch.cuda.synchronize()
+    assert rel(h, want) < 1e-5, describe(h, want)
+    assert torch.equal(hb, h.bfloat16()), "bf16 copy must be the rounding of the fp32 result"
+    ws = _slot_stats(hb)
+    assert rel(stats[..., 0], ws[..., 0]) < 1e-4 and rel(stats[..., 1], ws[..., 1]) < 1e-4, describe(stats, ws)
+
+
+@pytest.mark.parametrize("gelu", [False, True])
+@pytest.mark.parametrize("M,N,K", [(128 * 9 + 77, 1536, 512), (1026 * 2, 2048, 512), (600, 1024, 1024)])
+def test_gemm_layernorm_folded(M, N, K, gelu):
+    """PCD_EPI_LN_BIAS(_GELU): LayerNorm folded into the projection (transformer.py:108-114) against
+    torch's LayerNorm -> Linear (-> GELU) in fp64 on the same bf16 activations."""
+    h = (det.normal((M, K), 820) * 1.7 + det.normal((M, 1), 821) * 0.5).to(DEV)   # rows with non-zero means
+    gamma = (1.0 + 0.3 * det.normal((K,), 822)).to(DEV)
+    beta = (0.2 * det.normal((K,), 823)).to(DEV)
+    w = bf16_round(det.uniform((N, K), 824, 1 / math.sqrt(K))).to(DEV)
+    b = det.uniform((N,), 825, 0.5).to(DEV)
+    hb, stats = ops.cast_rowstats(h)
+    wf = (w * gamma[None, :]).bfloat16().contiguous()
+    colsum = wf.float().sum(dim=1).contiguous()
+    const = (w.double() @ beta.double() + b.double()).float().contiguous()
+    got = ops.linear_layernorm_folded(hb, stats, wf, colsum, const, eps=1e-5, gelu=gelu)
+    torch.cuda.synchronize()
+    xn = torch.nn.functional.layer_norm(hb.double(), (K,), gamma.double(), beta.double(), 1e-5)
+    want = xn @ w.double().t() + b.double()
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    # bf16 output rounding + bf16 rounding of gamma o W (vs. rounding LayerNorm's output in the unfused path)
+    assert rel(got.float(), want) < 6e-3, describe(got.float(), want, f"lnfold {M}x{N}x{K} gelu={gelu}")
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize("variant", [5, 4, 3, 2, 1, 0])
 def test_self_attention_golden(dtype, tol, variant):
