@@ -79,26 +79,6 @@ __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// ---- packed fp32x2 arithmetic (sm_100: two FMA-pipe results per issue slot) ----
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-
 // 2^x for a pair, x <= ~8, entirely on the FMA / ALU pipes (no MUFU): round-to-nearest split
 // x = n + f, |f| <= 0.5 (magic-number add), degree-3 minimax polynomial for 2^f (max rel. error
 // 7.5e-5, far below the bf16 rounding of P), exponent patched in with an integer shift-add.  The
@@ -167,7 +147,7 @@ __device__ __forceinline__ float exp_tile(const Sm& c, const uint32_t (&cur)[BKV
         unpack2(xb, b0, b1);
         const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
         float p2, p3;
-        if (POLY > 0 && ((i >> 2) % POLY) == POLY - 1) {
+        if (POLY > 0 && ((i >> 2) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
           exp2_poly2(xb, p2, p3);
         } else {
           p2 = ex2_approx(b0);

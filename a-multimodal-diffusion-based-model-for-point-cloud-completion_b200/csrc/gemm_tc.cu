@@ -562,33 +562,33 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);
         const float* sbc = sb + half * HALF_N + c * 32;
         float v[32];
-        if (kLnFold) {
-          // LayerNorm folded into the projection: with W' = gamma o W (bf16), s_n = sum_k W'[n,k],
-          // c_n = beta . W[n,:] + b_n:   LN(x) W^T + b = rstd (x W'^T - mu s) + c
-          const float* scc = colsum + colbase + c * 32;  // warp-uniform addresses: broadcast loads, L1-resident
-          const float nmu = -cur_mu;
+        {
+          // bias / LayerNorm fold / GELU on pairs (fma.rn.f32x2: half the FMA-pipe issue slots -- the
+          // epilogue warps, two per scheduler, are issue-latency bound).  LayerNorm folded into the
+          // projection: with W' = gamma o W (bf16), s_n = sum_k W'[n,k], c_n = beta . W[n,:] + b_n:
+          //   LN(x) W^T + b = rstd (x W'^T - mu s) + c
+          const float* scc = kLnFold ? colsum + colbase + c * 32 : nullptr;  // warp-uniform: broadcast loads
+          const uint64_t nmu2 = pack2(-cur_mu, -cur_mu), rstd2 = pack2(cur_rstd, cur_rstd);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(sbc + j);
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scc + j));
-            v[j] = fmaf(cur_rstd, fmaf(nmu, s4.x, __uint_as_float(r[j])), b4.x);
-            v[j + 1] = fmaf(cur_rstd, fmaf(nmu, s4.y, __uint_as_float(r[j + 1])), b4.y);
-            v[j + 2] = fmaf(cur_rstd, fmaf(nmu, s4.z, __uint_as_float(r[j + 2])), b4.z);
-            v[j + 3] = fmaf(cur_rstd, fmaf(nmu, s4.w, __uint_as_float(r[j + 3])), b4.w);
+            uint64_t a01 = pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+            uint64_t a23 = pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (kLnFold) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(scc + j));
+              a01 = fma2(rstd2, fma2(nmu2, pack2(s4.x, s4.y), a01), pack2(b4.x, b4.y));
+              a23 = fma2(rstd2, fma2(nmu2, pack2(s4.z, s4.w), a23), pack2(b4.z, b4.w));
+            } else {
+              a01 = add2(a01, pack2(b4.x, b4.y));
+              a23 = add2(a23, pack2(b4.z, b4.w));
+            }
+            if (kGelu) {
+              a01 = gelu_fast2(a01);
+              a23 = gelu_fast2(a23);
+            }
+            unpack2(a01, v[j], v[j + 1]);
+            unpack2(a23, v[j + 2], v[j + 3]);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sbc + j);
-            v[j] = __uint_as_float(r[j]) + b4.x;
-            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-          }
-        }
-        if (kGelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
         if (OUT_BF16) {
 #pragma unroll

@@ -265,6 +265,49 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
+// ---- packed fp32x2 arithmetic (sm_100: two FMA-pipe results per issue slot) ----
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// gelu_fast (common.cuh) on a pair: seven packed FMA-pipe instructions, two clamps and two tanh.approx
+// for two elements instead of 2 x 10 scalar ones
+__device__ __forceinline__ uint64_t gelu_fast2(uint64_t x2) {
+  float z0, z1;
+  unpack2(mul2(x2, pack2(0.70710678118654752440f, 0.70710678118654752440f)), z0, z1);
+  z0 = fminf(fmaxf(z0, -3.3f), 3.3f);
+  z1 = fminf(fmaxf(z1, -3.3f), 3.3f);
+  const uint64_t z = pack2(z0, z1);
+  const uint64_t zz = mul2(z, z);
+  uint64_t p = fma2(pack2(-0.00204817f, -0.00204817f), zz, pack2(0.10449843f, 0.10449843f));
+  p = fma2(p, zz, pack2(1.12819195f, 1.12819195f));
+  float u0, u1, t0, t1;
+  unpack2(mul2(z, p), u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t hx = mul2(x2, pack2(0.5f, 0.5f));
+  return fma2(hx, pack2(t0, t1), hx);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
