@@ -31,6 +31,22 @@ def init_linear(l, stddev):
         nn.init.constant_(l.bias, 0.0)
 
 
+def fold_layernorm_into_linear(weight: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm(x; gamma, beta) followed by Linear(weight, bias) (reference transformer.py:108-114:
+    ``attn(ln_1(x))``, ``mlp(ln_2(x))``) as ONE projection of the un-normalised row:
+
+        LN(x) W^T + b = rstd * (x W'^T - mu * colsum) + const,
+
+    W' = bf16(gamma o W) (what the tensor cores multiply by), colsum[n] = sum_k W'[n, k] (of the ROUNDED
+    folded weights, so that the mean correction cancels exactly) and const[n] = beta . W[n, :] + b[n].
+    mu / rstd are the statistics of the row the GEMM actually reads (its bf16 copy)."""
+    w32, g, be = weight.float(), gamma.float(), beta.float()
+    wf = (w32 * g[None, :]).to(torch.bfloat16).contiguous()
+    colsum = wf.float().sum(dim=1).contiguous()
+    const = (w32.double() @ be.double() + bias.double()).float().contiguous()
+    return wf, colsum, const
+
+
 def _compute_dtype(t: torch.Tensor, precision: int):
     return t.to(torch.bfloat16) if precision == PCD_BF16 else t.float()
 
@@ -206,10 +222,8 @@ class PointDiffusionTransformer(nn.Module):
                 # s_n = sum_k (gamma o W)[n, k] of the bf16-ROUNDED folded weights (what the tensor
                 # cores multiply by) and c_n = beta . W[n, :] + b_n.  Step-invariant: done once here.
                 def fold(lin, ln):
-                    w32, g, be = lin.weight.detach().float(), ln.weight.detach().float(), ln.bias.detach().float()
-                    wf = (w32 * g[None, :]).to(torch.bfloat16).contiguous()
-                    colsum = wf.float().sum(dim=1).contiguous()
-                    const = (w32.double() @ be.double() + lin.bias.detach().double()).float().contiguous()
+                    wf, colsum, const = fold_layernorm_into_linear(lin.weight.detach(), lin.bias.detach(),
+                                                                   ln.weight.detach(), ln.bias.detach())
                     keep.extend((wf, colsum, const))
                     return ptr(wf), ptr(colsum), ptr(const)
                 b.w_qkv_ln, b.qkv_colsum, b.qkv_const = fold(blk.attn.c_qkv, blk.ln_1)

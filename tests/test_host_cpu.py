@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(P._lib.EXPORTED_SYMBOLS), declared ^ set(P._lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pcd_abi_version() == 1
+    assert lib.pcd_abi_version() == 2
 
 
 def test_product_never_imports_the_oracle():
@@ -113,3 +113,27 @@ def test_configs_mirror_reference_registry():
     d = P.diffusion_from_config(P.DIFFUSION_CONFIGS["base40M"])
     x = torch.randn(2, 6, 5)
     assert torch.allclose(d.unscale_channels(d.scale_channels(x)), x, atol=1e-5)
+
+
+def test_layernorm_fold_algebra():
+    """Host-side weight folding used by the LayerNorm-folded forward: rstd (x W'^T - mu colsum) + const
+    equals LayerNorm -> Linear on the same (bf16-rounded) rows."""
+    from importlib import import_module
+    T = import_module(P.__name__ + ".transformer")
+    g = torch.Generator().manual_seed(5)
+    d, n, m = 256, 96, 40
+    w = (torch.randn(n, d, generator=g) / d ** 0.5).bfloat16().float()
+    b = torch.randn(n, generator=g) * 0.1
+    gamma = 1 + 0.3 * torch.randn(d, generator=g)
+    beta = 0.2 * torch.randn(d, generator=g)
+    x = (torch.randn(m, d, generator=g) * 2 + torch.randn(m, 1, generator=g)).bfloat16().double()
+    wf, colsum, const = T.fold_layernorm_into_linear(w, b, gamma, beta)
+    assert wf.dtype == torch.bfloat16 and colsum.dtype == torch.float32 and const.dtype == torch.float32
+    mu = x.mean(dim=1, keepdim=True)
+    rstd = 1.0 / torch.sqrt(x.var(dim=1, unbiased=False, keepdim=True) + 1e-5)
+    got = rstd * (x @ wf.double().t() - mu * colsum.double()[None, :]) + const.double()[None, :]
+    want = torch.nn.functional.layer_norm(x, (d,), gamma.double(), beta.double(), 1e-5) @ w.double().t() + b.double()
+    # the only difference is the bf16 rounding of gamma o W
+    assert float((got - want).norm() / want.norm()) < 3e-3
+    exact = rstd * (x @ (w.double() * gamma.double()[None, :]).t() - mu * (w.double() * gamma.double()[None, :]).sum(1)[None, :]) + const.double()
+    assert float((exact - want).norm() / want.norm()) < 1e-6
