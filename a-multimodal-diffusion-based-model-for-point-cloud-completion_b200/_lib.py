@@ -10,7 +10,8 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpcd_b200.so")
+# PCD_B200_LIB: A/B timing of two builds of the library in one process tree (tools/ab.sh); never a fallback
+LIB_PATH = os.environ.get("PCD_B200_LIB") or os.path.join(HERE, "libpcd_b200.so")
 
 PCD_F32, PCD_BF16 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2

@@ -6,9 +6,14 @@ from collections import Counter
 rep = sys.argv[1]
 blk = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 thr = int(sys.argv[3]) if len(sys.argv) > 3 else 150
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
+import os
+extra = os.environ.get("NCU_SELECT", "").split()   # e.g. NCU_SELECT="--launch-skip 1 --launch-count 1"
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", *extra], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-hdr = rows[1]; ix = {k: i for i, k in enumerate(hdr)}; data = rows[2:]
+hdr = rows[1]; ix = {k: i for i, k in enumerate(hdr)}
+end = next((i for i in range(2, len(rows)) if rows[i] and rows[i][0] == 'Kernel Name'), len(rows))
+data = [r for r in rows[2:end] if len(r) == len(hdr)]
+print(rows[0][1][:90])
 keys = [k for k in hdr if k.startswith('stall_') and 'Not Issued' not in k]
 tot_s = sum(int(r[ix['# Samples']]) for r in data)
 print("total samples", tot_s, "instructions", len(data))
