@@ -79,6 +79,7 @@ _SIGS = {
     "pcd_attention": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 C.c_float, vp, C.c_int, vp]),
+    "pcd_rope_bf16": (C.c_int, [C.POINTER(AttnOperand), vp, C.c_int, C.c_int, C.c_int, vp]),
     "pcd_sampler_begin": (C.c_int, [vp, vp, vp, C.POINTER(StepScalars), C.c_int64, vp]),
     "pcd_sampler_predictor": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                         C.POINTER(StepScalars), C.c_int, C.c_int, C.c_int, C.c_int, vp]),

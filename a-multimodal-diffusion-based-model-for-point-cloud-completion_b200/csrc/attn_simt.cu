@@ -168,6 +168,35 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(
   }
 }
 
+// In-place 3-axis RoPE on head dims 0..5 of a bf16 q or k operand (reference rotaryencoderpcd.py:6-27):
+// the tensor-core attention kernel consumes its tiles straight from TMA, so in bf16 mode the rotation
+// is applied to the projection output before it (12 bytes per token and head; fp32 arithmetic).
+__global__ void rope_bf16_kernel(uint16_t* __restrict__ x, int64_t bs, int64_t ls, int64_t hs,
+                                 const float* __restrict__ coords, int batch, int heads, int len) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)batch * len * heads;
+  if (idx >= total) return;
+  const int h = (int)(idx % heads);
+  const int64_t bl = idx / heads;
+  const int l = (int)(bl % len);
+  const int b = (int)(bl / len);
+  uint16_t* p = x + b * bs + (int64_t)l * ls + (int64_t)h * hs;
+  float v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = __uint_as_float((uint32_t)p[i] << 16);
+  rope6(v, coords + ((int64_t)b * len + l) * 3);
+#pragma unroll
+  for (int i = 0; i < 6; i += 2) *reinterpret_cast<uint32_t*>(p + i) = pack_bf16x2(v[i], v[i + 1]);
+}
+
+int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const float* coords, int batch, int heads,
+                     int len, cudaStream_t st) {
+  const int64_t total = (int64_t)batch * len * heads;
+  rope_bf16_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(x, bs, ls, hs, coords, batch, heads, len);
+  PCD_CHECK_LAUNCH("rope_bf16");
+  return PCD_OK;
+}
+
 int launch_attention_f32(const pcd_attn_operand* q, const pcd_attn_operand* k,
                          const pcd_attn_operand* v, float* out, int64_t o_bs, int64_t o_ls,
                          int batch, int heads, int len_q, int len_kv, float q_scale, float k_scale,

@@ -88,6 +88,8 @@ static int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
 int launch_attention_f32(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                          float* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
                          int len_kv, float q_scale, float k_scale, const float* rope, cudaStream_t st);
+int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const float* coords, int batch, int heads,
+                     int len, cudaStream_t st);
 int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                           uint16_t* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
                           int len_kv, float q_scale, float k_scale, cudaStream_t st);
@@ -163,12 +165,23 @@ extern "C" int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* 
     PCD_CHECK_ARG(operand_ok(q, 8, 2) && operand_ok(k, 8, 2) && operand_ok(v, 8, 2), "attention(bf16): operands must be 16-byte aligned with strides %% 8 == 0");
     PCD_CHECK_ARG(o_ls % 8 == 0 && o_bs % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "attention(bf16): output must be 16-byte aligned with strides %% 8 == 0");
     if (rope_coords != nullptr) {
-      set_error("attention(bf16): rotary is applied by pcd_rope_bf16 before the tensor-core kernel");
+      set_error("attention(bf16): apply the rotation with pcd_rope_bf16 (in place on q and k) before the tensor-core kernel");
       return PCD_ERR_UNSUPPORTED;
     }
     return launch_attention_bf16(q, k, v, (uint16_t*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, st);
   }
   PCD_CHECK_ARG(false, "attention: unknown precision %d", precision);
+}
+
+extern "C" int pcd_rope_bf16(const pcd_attn_operand* x, const float* coords, int batch, int heads, int len,
+                             void* stream) {
+  PCD_CHECK_ARG(x != nullptr && x->ptr != nullptr && coords != nullptr, "rope_bf16: null argument");
+  PCD_CHECK_ARG(batch > 0 && heads > 0 && len > 0, "rope_bf16: empty problem");
+  PCD_CHECK_ARG(reinterpret_cast<uintptr_t>(x->ptr) % 4 == 0 && x->row_stride % 2 == 0 && x->head_stride % 2 == 0 &&
+                    x->batch_stride % 2 == 0,
+                "rope_bf16: operand must be 4-byte aligned with even strides");
+  return launch_rope_bf16((uint16_t*)const_cast<void*>(x->ptr), x->batch_stride, x->row_stride, x->head_stride, coords,
+                          batch, heads, len, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------

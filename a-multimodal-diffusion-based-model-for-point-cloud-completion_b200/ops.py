@@ -209,12 +209,21 @@ def rotary_attention(qkv: torch.Tensor, coords: torch.Tensor, heads: int) -> tor
     B, N, D3 = qkv.shape
     D = D3 // 3
     assert D // heads == 64
-    assert qkv.dtype == torch.float32, "rotary attention runs in the fp32 kernel (RoPE applied on load)"
     qkv = qkv.contiguous()
     coords = coords.to(torch.float32).contiguous()
     out = torch.empty(B, N, D, device=qkv.device, dtype=qkv.dtype)
     ops = [_operand(qkv, i * D, N * D3, D3, 64) for i in range(3)]
-    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, N, N, D ** -0.5, 1.0, coords)
+    if qkv.dtype == torch.float32:  # RoPE applied in registers while the tiles are loaded
+        return attention_packed(ops[0], ops[1], ops[2], out, B, heads, N, N, D ** -0.5, 1.0, coords)
+    # bf16: the tensor-core kernel takes its tiles straight from TMA -> rotate q and k in place first
+    # (qkv is this call's own projection output / contiguous copy, never the caller's tensor)
+    assert qkv.dtype == torch.bfloat16
+    qkv = qkv.clone()
+    ops = [_operand(qkv, i * D, N * D3, D3, 64) for i in range(3)]
+    lib = _lib.load()
+    for o in ops[:2]:
+        check(lib.pcd_rope_bf16(C.byref(o), ptr(coords), B, heads, N, stream_ptr()), "rope_bf16")
+    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, N, N, D ** -0.5, 1.0)
 
 
 def chamfer_distance_xyz(p1: torch.Tensor, p2: torch.Tensor) -> torch.Tensor:

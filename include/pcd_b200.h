@@ -196,6 +196,12 @@ PCD_API int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* k, 
                   float q_scale, float k_scale, const float* rope_coords,
                   int precision, void* stream);
 
+/* bf16 mode of the rotary attention: rotate head dims 0..5 of a q or k operand IN PLACE with
+ * theta = pi * coords[b, l, :] (apply_rotary_pos_emb, rotaryencoderpcd.py:6-27; fp32 arithmetic), then call
+ * pcd_attention(..., rope_coords = NULL, PCD_BF16).  The fp32 kernel rotates in registers on load instead. */
+PCD_API int pcd_rope_bf16(const pcd_attn_operand* x, const float* coords, int batch, int heads, int len,
+                          void* stream);
+
 /* ------------------------------------------------------------------ */
 /* Fused Karras/Heun sampler updates (k_diffusion.py:270-310,79-108,182-207;  */
 /* gaussian_diffusion.py:320-357,949-958).  State fp32 [B, C, N].              */

@@ -272,6 +272,32 @@ def test_rotary_attention_golden():
     assert rel(out, qkv[..., 256:]) < 1e-6
 
 
+def test_rotary_attention_bf16():
+    """bf16 mode of RotarySelfAttention (rotaryencoderpcd.py:58-84): tensor-core projections and
+    attention with pcd_rope_bf16 in between, against the reference golden and against an fp32
+    evaluation of the rotation on the same bf16 inputs."""
+    g = load_golden("ops")
+    coords = det.uniform((2, 70, 3), 307, std=0.5 / 3 ** 0.5)
+    sd = det.fill_state_dict({"qkv.weight": torch.zeros(384, 128), "qkv.bias": torch.zeros(384),
+                              "out_proj.weight": torch.zeros(128, 128), "out_proj.bias": torch.zeros(128)}, 308)
+    mod = P.rotaryencoderpcd.RotarySelfAttention(128, heads=2, dtype=torch.bfloat16).to(DEV)
+    mod.load_state_dict(sd)
+    got = mod(det.normal((2, 70, 128), 309).to(DEV), coords.to(DEV))
+    assert got.dtype == torch.float32
+    assert rel(got, g["rotary_self_attn"]) < 2e-2, describe(got, g["rotary_self_attn"])
+    # kernel level: larger problem, bf16 rotary attention vs the fp32 rotary kernel on the same values
+    B, N, H = 3, 333, 4
+    qkv = bf16_round(det.normal((B, N, 3 * H * 64), 330, std=1.2)).to(DEV)
+    pos = det.uniform((B, N, 3), 331, std=0.4).to(DEV)
+    want = ops.rotary_attention(qkv, pos, H)
+    keep = qkv.bfloat16()
+    snapshot = keep.clone()
+    got2 = ops.rotary_attention(keep, pos, H)
+    torch.cuda.synchronize()
+    assert torch.equal(keep, snapshot), "the caller's qkv must not be modified"
+    assert rel(got2.float(), want) < 1e-2, describe(got2.float(), want)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 def test_perceiver_golden(dtype, tol):
     from test_oracle_golden import perceiver_shapes
