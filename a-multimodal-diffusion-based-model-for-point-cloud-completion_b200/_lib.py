@@ -80,6 +80,9 @@ _SIGS = {
                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 C.c_float, vp, C.c_int, vp]),
     "pcd_rope_bf16": (C.c_int, [C.POINTER(AttnOperand), vp, C.c_int, C.c_int, C.c_int, vp]),
+    "pcd_farthest_point_sample": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "pcd_nearest_points": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "pcd_fscore": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp]),
     "pcd_sampler_begin": (C.c_int, [vp, vp, vp, C.POINTER(StepScalars), C.c_int64, vp]),
     "pcd_sampler_predictor": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp,
                                         C.POINTER(StepScalars), C.c_int, C.c_int, C.c_int, C.c_int, vp]),

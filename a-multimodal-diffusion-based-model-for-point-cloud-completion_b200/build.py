@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpcd_b200.so")
 SOURCES = ["pcd_api.cu", "elementwise.cu", "sampler.cu", "gemm_simt.cu", "attn_simt.cu",
-           "gemm_tc.cu", "attn_tc.cu", "attn_tc5.cu"]
+           "gemm_tc.cu", "attn_tc.cu", "attn_tc5.cu", "pointops.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

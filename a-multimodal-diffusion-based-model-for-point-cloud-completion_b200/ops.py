@@ -238,6 +238,50 @@ def chamfer_distance_xyz(p1: torch.Tensor, p2: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def farthest_point_sample(points: torch.Tensor, n_samples: int, init_idx) -> torch.Tensor:
+    """Greedy farthest-point sampling (reference util/point_cloud.py:82-118, evaluation.py:40-48):
+    points [B, N, 3] fp32 -> int64 indices [B, n_samples]; init_idx int or [B] tensor."""
+    require_cuda(points)
+    assert points.dim() == 3 and points.shape[2] == 3 and points.dtype == torch.float32
+    B, N, _ = points.shape
+    points = points.contiguous()
+    if not torch.is_tensor(init_idx):
+        init_idx = torch.full((B,), int(init_idx), dtype=torch.int32, device=points.device)
+    init_idx = init_idx.to(device=points.device, dtype=torch.int32).contiguous()
+    out = torch.empty(B, n_samples, dtype=torch.int64, device=points.device)
+    check(_lib.load().pcd_farthest_point_sample(ptr(points), B, N, n_samples, ptr(init_idx), ptr(out), stream_ptr()),
+          "farthest_point_sample")
+    return out
+
+
+def nearest_points(queries: torch.Tensor, cloud: torch.Tensor, form: int = 1):
+    """For every query [B, Nq, 3] the index of / squared distance to its nearest cloud point [B, Nc, 3]
+    (PointCloud.nearest_points, reference util/point_cloud.py:148-165)."""
+    require_cuda(queries, cloud)
+    assert queries.dtype == torch.float32 and cloud.dtype == torch.float32
+    queries, cloud = queries.contiguous(), cloud.contiguous()
+    B, Nq, _ = queries.shape
+    idx = torch.empty(B, Nq, dtype=torch.int64, device=queries.device)
+    d2 = torch.empty(B, Nq, dtype=torch.float32, device=queries.device)
+    check(_lib.load().pcd_nearest_points(ptr(queries), Nq, ptr(cloud), cloud.shape[1], B, form, ptr(d2), ptr(idx),
+                                         stream_ptr()), "nearest_points")
+    return idx, d2
+
+
+def fscore_point_cloud_batch(pred: torch.Tensor, gt: torch.Tensor, threshold: float = 0.03, squared: bool = False):
+    """F-score / precision / recall of batched clouds (reference models/util.py:195-262; squared=True is
+    fscore_point_cloud_batch_squared): pred [B, N, 3], gt [B, M, 3] -> three [B] tensors."""
+    require_cuda(pred, gt)
+    pred, gt = pred.float().contiguous(), gt.float().contiguous()
+    B, N, _ = pred.shape
+    M = gt.shape[1]
+    out = torch.empty(3, B, dtype=torch.float32, device=pred.device)
+    ws = torch.empty(B * (N + M), dtype=torch.float32, device=pred.device)
+    check(_lib.load().pcd_fscore(ptr(pred), N, ptr(gt), M, B, float(threshold), int(squared), ptr(out), ptr(ws),
+                                 stream_ptr()), "fscore")
+    return out[0], out[1], out[2]
+
+
 def step_scalars(**kw) -> StepScalars:
     s = StepScalars()
     for k, v in kw.items():

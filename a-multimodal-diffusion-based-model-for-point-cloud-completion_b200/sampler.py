@@ -14,6 +14,8 @@ Same constructor, attributes and methods as the reference's
 from typing import Any, Callable, Dict, Iterator, List, Optional, Sequence, Tuple
 
 import torch
+
+from .point_cloud import PointCloud
 import torch.nn as nn
 
 from .gaussian_diffusion import GaussianDiffusion
@@ -287,16 +289,13 @@ class PointCloudSampler:
             aux[name] = v
         return pos, aux
 
-    def output_to_point_clouds(self, output: torch.Tensor) -> List[Dict[str, Any]]:
-        """The reference returns ``point_e.util.point_cloud.PointCloud`` dataclasses
-        (sampler.py:255-265); the IO/visualisation layer is out of scope here, so each
-        cloud is returned as ``dict(coords=[N,3] ndarray, channels={name: [N] ndarray})``
-        with the same field names and values."""
+    def output_to_point_clouds(self, output: torch.Tensor) -> List[PointCloud]:
+        """One ``PointCloud`` per sample, colours rescaled to [0, 1] (reference sampler.py:255-265)."""
         res = []
         for sample in output:
             xyz, aux = self.split_model_output(sample[None], rescale_colors=True)
-            res.append(dict(coords=xyz[0].t().cpu().numpy(),
-                            channels={k: v[0].cpu().numpy() for k, v in aux.items()}))
+            res.append(PointCloud(coords=xyz[0].t().cpu().numpy(),
+                                  channels={k: v[0].cpu().numpy() for k, v in aux.items()}))
         return res
 
     def with_options(

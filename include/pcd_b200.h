@@ -254,6 +254,26 @@ PCD_API int pcd_chamfer(const float* p1, int c1, int n1, const float* p2, int c2
                 void* stream);
 
 /* ------------------------------------------------------------------ */
+/* Point-cloud utilities either side of the sampler (evaluation / IO layer) */
+/* ------------------------------------------------------------------ */
+
+/* Greedy farthest-point sampling (util/point_cloud.py:82-118; evaluation.py:40-48): points fp32
+ * [batch, n, 3] row-major, init_idx int32 [batch] -> out_idx int64 [batch, n_samples]; distances in the
+ * reference's |a|^2 + |b|^2 - 2 a.b form, first arg-max.  n <= 8192 (the reference evaluates at <= 8192 points). */
+PCD_API int pcd_farthest_point_sample(const float* points, int batch, int n, int n_samples, const int* init_idx,
+                                      long long* out_idx, void* stream);
+/* For every point of a [batch, na, 3]: squared distance to / index of its nearest point of b [batch, nb, 3]
+ * (either output may be NULL).  form 0: sum (a-b)^2 (models/util.py:213-214); form 1: |a|^2 + |b|^2 - 2 a.b
+ * (PointCloud.nearest_points, util/point_cloud.py:148-165).  First minimum wins. */
+PCD_API int pcd_nearest_points(const float* a, int na, const float* b, int nb, int batch, int form, float* out_d2,
+                               long long* out_idx, void* stream);
+/* fscore_point_cloud_batch (squared == 0: threshold on the distance) / _squared (threshold on the squared
+ * distance), models/util.py:195-262: pred [batch, n, 3], gt [batch, m, 3] -> out fp32 [3, batch] =
+ * (fscore, precision, recall); workspace >= batch * (n + m) floats.  No [n, m, 3] tensor. */
+PCD_API int pcd_fscore(const float* pred, int n, const float* gt, int m, int batch, float threshold, int squared,
+                       float* out, float* workspace, void* stream);
+
+/* ------------------------------------------------------------------ */
 /* Whole-denoiser forward (transformer.py:118-152,195-226)             */
 /* ------------------------------------------------------------------ */
 
