@@ -22,7 +22,7 @@ from .gaussian_diffusion import GaussianDiffusion, get_named_beta_schedule  # no
 from .k_diffusion import (HeunPlan, get_sigmas_karras, karras_sample,  # noqa: F401
                           karras_sample_progressive)
 from .sampler import PointCloudSampler  # noqa: F401
-from . import dist, ops, perceiver, ply_util, point_cloud, rotaryencoderpcd, transformer  # noqa: F401
+from . import dist, download, ops, perceiver, ply_util, point_cloud, rotaryencoderpcd, transformer  # noqa: F401
 from .point_cloud import PointCloud  # noqa: F401
 
 __all__ = ["MODEL_CONFIGS", "DIFFUSION_CONFIGS", "model_from_config", "diffusion_from_config",

@@ -137,3 +137,18 @@ def test_layernorm_fold_algebra():
     assert float((got - want).norm() / want.norm()) < 3e-3
     exact = rstd * (x @ (w.double() * gamma.double()[None, :]).t() - mu * (w.double() * gamma.double()[None, :]).sum(1)[None, :]) + const.double()
     assert float((exact - want).norm() / want.norm()) < 1e-6
+
+
+def test_checkpoint_lookup_is_local_only(tmp_path):
+    """Reference checkpoint names resolve to the files its downloader would have cached; nothing is fetched."""
+    with pytest.raises(ValueError):
+        P.download.load_checkpoint("nope", torch.device("cpu"), cache_dir=str(tmp_path))
+    with pytest.raises(FileNotFoundError):
+        P.download.load_checkpoint("base40M-uncond", torch.device("cpu"), cache_dir=str(tmp_path))
+    cfg = dict(P.MODEL_CONFIGS["base40M-uncond"], width=128, layers=1, heads=2, n_ctx=16)
+    model = P.model_from_config(cfg, torch.device("cpu"))
+    torch.save(model.state_dict(), tmp_path / "base_40m_uncond.pt")
+    sd = P.download.load_checkpoint("base40M-uncond", torch.device("cpu"), cache_dir=str(tmp_path))
+    model2 = P.model_from_config(cfg, torch.device("cpu"))
+    model2.load_state_dict(sd)
+    assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), model2.state_dict().values()))
