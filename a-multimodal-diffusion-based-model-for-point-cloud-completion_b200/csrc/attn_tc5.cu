@@ -69,6 +69,21 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// one non-blocking probe: issued early, its ~90-cycle round trip overlaps whatever is scheduled before the
+// result is consumed
+__device__ __forceinline__ uint32_t bar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void tma4(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -167,6 +182,35 @@ __device__ __forceinline__ float exp_tile(const Sm& c, const uint32_t (&cur)[BKV
   return (s0 + s1) + (s2 + s3);
 }
 
+// the two 32-column halves of exp_tile as separate calls (sums carried by the caller), so that barrier probes and
+// the next tile's TMEM load can sit between them
+template <int POLY>
+__device__ __forceinline__ void exp_half32(const Sm& c, const uint32_t (&cur)[BKV], int h, uint32_t (&pk)[16], uint64_t& sum_a,
+                                           uint64_t& sum_b) {
+  const uint64_t sc2 = pack2(c.scale, c.scale);
+  const uint64_t nm2 = pack2(-c.m_used, -c.m_used);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const uint64_t xa = fma2(pack2(__uint_as_float(cur[h * 32 + i]), __uint_as_float(cur[h * 32 + i + 1])), sc2, nm2);
+    const uint64_t xb = fma2(pack2(__uint_as_float(cur[h * 32 + i + 2]), __uint_as_float(cur[h * 32 + i + 3])), sc2, nm2);
+    float a0, a1, b0, b1;
+    unpack2(xa, a0, a1);
+    unpack2(xb, b0, b1);
+    const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+    float p2, p3;
+    if (POLY > 0 && ((i >> 2) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+      exp2_poly2(xb, p2, p3);
+    } else {
+      p2 = ex2_approx(b0);
+      p3 = ex2_approx(b1);
+    }
+    sum_a = add2(sum_a, pack2(p0, p1));
+    sum_b = add2(sum_b, pack2(p2, p3));
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+  }
+}
+
 // row maximum (log2 domain); keys >= nvalid of a ragged tile are masked to -inf first
 __device__ __forceinline__ float row_max(const Sm& c, uint32_t (&r)[BKV], int nvalid) {
   if (nvalid < BKV) {
@@ -195,15 +239,30 @@ __device__ __forceinline__ void pstep(Sm& c, uint32_t (&cur)[BKV], uint32_t (&nx
   constexpr int Y = X ^ 1;
   uint32_t& ux = X ? c.u1 : c.u0;
   uint32_t& uy = X ? c.u0 : c.u1;
+  // Both barriers of the step are normally complete already, but a try_wait still takes ~90 cycles to say so:
+  // probe them now and consume the answers after the first half of the exponentials.
+  const uint32_t ok_s = bar_try(c.bars + 8 * (B_S_FULL + Y), uy);
+  const uint32_t ok_pv = bar_try(c.bars + 8 * (B_PV_DONE + X), ux ^ 1);
+  uint64_t sum_a = 0ull, sum_b = 0ull;
+  uint32_t pk[16];
+  exp_half32<POLY>(c, cur, 0, pk, sum_a, sum_b);
   // S of the next tile -> registers (not waited for yet)
-  bar_wait(c.bars + 8 * (B_S_FULL + Y), uy);
+  if (!ok_s) bar_wait(c.bars + 8 * (B_S_FULL + Y), uy);
   tcgen05_fence_after();
   tmem_ld_32x32b_x32(c.tm + S_COL + Y * BKV, nxt);
   tmem_ld_32x32b_x32(c.tm + S_COL + Y * BKV + 32, nxt + 32);
   // P buffer X is free once the PV product of its previous use has completed
-  bar_wait(c.bars + 8 * (B_PV_DONE + X), ux ^ 1);
+  if (!ok_pv) bar_wait(c.bars + 8 * (B_PV_DONE + X), ux ^ 1);
   tcgen05_fence_after();
-  c.l_run += exp_tile<POLY>(c, cur, c.tm + P_COL + X * (BKV / 2), BKV);
+  tmem_st_32x32b_x16(c.tm + P_COL + X * (BKV / 2), pk);
+  exp_half32<POLY>(c, cur, 1, pk, sum_a, sum_b);
+  tmem_st_32x32b_x16(c.tm + P_COL + X * (BKV / 2) + 16, pk);
+  {
+    float s0, s1, s2, s3;
+    unpack2(sum_a, s0, s1);
+    unpack2(sum_b, s2, s3);
+    c.l_run += (s0 + s1) + (s2 + s3);
+  }
   tmem_st_wait();
   tmem_ld_wait();
   tcgen05_fence_before();
