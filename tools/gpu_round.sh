@@ -10,13 +10,14 @@ PYT="python -m pytest -q -p no:cacheprovider --timeout 240 -m gpu"
 run() { # name, timeout, cmd...
   local name=$1 to=$2; shift 2
   echo "=== $name ($(date +%T))"
-  timeout $to "$@" > $OUT/$name.log 2>&1
+  timeout -s KILL $to "$@" > $OUT/$name.log 2>&1
   echo "    exit=$? ; tail:"; tail -n ${TAILN:-6} $OUT/$name.log | sed 's/^/    /'
 }
 run ops_simt   600 $PYT tests/test_gpu_ops.py -k "device or timestep or layernorm or gemm_f32 or chamfer or rotary or rowstats"
 run probe 300 python tools/gemm_probe.py
 run gemm_tc    600 $PYT tests/test_gpu_ops.py -k "gemm_bf16 or residual_stats or layernorm_folded"
-run attn       600 $PYT tests/test_gpu_ops.py -k "attention or perceiver"
+run attn       600 $PYT tests/test_gpu_ops.py -k "attention or perceiver or rotary"
+run pointcloud 300 $PYT tests/test_gpu_point_cloud.py
 run forward    900 $PYT tests/test_gpu_forward.py
 run sampler    900 $PYT tests/test_gpu_sampler.py -s
 run smoke      600 python __graft_entry__.py --smoke
