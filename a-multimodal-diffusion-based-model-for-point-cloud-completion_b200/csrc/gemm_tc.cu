@@ -289,7 +289,9 @@ extern int g_gemm_debug;
 // kernel bound by shared-memory bandwidth (TMA writes + UMMA operand reads + epilogue staging =
 // ~1 MB per 128x256 tile at 128 B/clk), which is what this layout relieves.
 // ---------------------------------------------------------------------------
-template <int EPI>
+// DEEPK (residual epilogues, K >= 1024): the main loop is the critical path and wants pipeline stages more than
+// the epilogue wants a second staging tile -- one staging tile per warp, residual chunks fetched on demand.
+template <int EPI, bool DEEPK = false>
 struct Gemm2Cfg {
   static constexpr int BN = 256;                     // N of the pair tile (each CTA stages 128 rows of W)
   static constexpr int A_BYTES = G_BM * G_BK * 2;    // 16 KB
@@ -297,7 +299,7 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // two staging tiles per epilogue warp: a TMA store only has to have finished READING its tile
   // by the time the warp comes back to it two store groups later (the round trip is ~2k cycles)
-  static constexpr int NBUF = 2;
+  static constexpr int NBUF = DEEPK ? 1 : 2;
   // the residual + row-statistics epilogue writes TWO tensors (fp32 residual stream and its bf16
   // copy): a second set of staging tiles
   static constexpr int OUT1_BYTES = G_EPI_WARPS * NBUF * G_STAGE_TILE;
@@ -309,14 +311,14 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + MISC_BYTES;
 };
 
-template <int EPI, bool OUT_BF16>
+template <int EPI, bool OUT_BF16, bool DEEPK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                      const __grid_constant__ CUtensorMap tmC2, const float* __restrict__ bias,
                      const float* __restrict__ colsum, const float2* __restrict__ stats_in, int stats_in_slots,
                      float2* __restrict__ stats_out, float ln_eps, int M, int N, int K, int dbg) {
-  using Cfg = Gemm2Cfg<EPI>;
+  using Cfg = Gemm2Cfg<EPI, DEEPK>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -441,7 +443,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t* my_res_bar = res_bar + 2 * ew;  // [2]: residual chunk landed in staging tile 0 / 1
     const int sw = lane & 7;
     uint32_t res_ph0 = 0, res_ph1 = 0;
-    static_assert(!kResid || (NBUF == 2 && NCH % 2 == 0), "residual prefetch assumes staging tile = chunk & 1");
+    constexpr bool kPrefetch = kResid && NBUF == 2;  // residual chunks requested ahead (staging tile = chunk & 1)
+    static_assert(!kPrefetch || NCH % 2 == 0, "residual prefetch assumes staging tile = chunk & 1");
     // LayerNorm statistics (LN-folded projections): the producer wrote one (mean, M2) pair per 128
     // columns of the normalised vector; they are combined with Chan's parallel-variance formula
     constexpr int LN_MAXS = 8;
@@ -510,7 +513,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int tn = t + num_pairs;
         ln_issue((tn / num_n) * 2 * G_BM + (int)rank * G_BM + quarter * 32 + lane);
       }
-      if (kResid && !(dbg & 1)) {
+      if (kPrefetch && !(dbg & 1)) {
         // residual chunks 0 and 1 of this tile -> the two staging tiles, while the accumulator is still
         // being computed (the stores of the previous tile have long finished reading them)
         if (elect_one()) {
@@ -545,7 +548,17 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const bool last_of_store = (c % CH_PER_STORE) == CH_PER_STORE - 1;
         unsigned char* my_buf = my_buf0 + (sidx % NBUF) * G_STAGE_TILE;
         unsigned char* buf_row = my_buf + lane * 128;
-        if (kResid) {
+        if (kResid && !kPrefetch) {
+          // one staging tile: wait until its previous stores have read it, then fetch this chunk's residual
+          if (elect_one()) {
+            tma_store_wait_read<0>();
+            mbar_expect_tx(&my_res_bar[0], G_STAGE_TILE);
+            tma_load_2d(my_buf, &tmR, &my_res_bar[0], colbase + c * 32, row0);
+          }
+          __syncwarp();
+          mbar_wait(&my_res_bar[0], res_ph0);
+          res_ph0 ^= 1;
+        } else if (kResid) {
           // this chunk's residual was requested one chunk (or one tile) ahead
           if (c & 1) {
             mbar_wait(&my_res_bar[1], res_ph1);
@@ -658,7 +671,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               tma_store_2d(&tmC2, my_bbuf, colbase + (c >> 1) * 64, row0);
               tma_store_commit();
             }
-            if (kResid) {
+            if (kPrefetch) {
               // the stores just issued must have read their tiles before (a) the residual of chunk
               // c + 2 lands in this staging tile and (b) the next chunk writes the bf16 tile
               tma_store_wait_read<0>();
@@ -668,7 +681,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               }
             }
           }
-          if (kResid) __syncwarp();
+          if (kPrefetch) __syncwarp();
           ++sidx;
         }
       }
@@ -702,12 +715,12 @@ struct LnArgs {  // extra operands of the residual+statistics and LayerNorm-fold
   float ln_eps;
 };
 
-template <int EPI, bool OUT_BF16>
+template <int EPI, bool OUT_BF16, bool DEEPK = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC,
                         const CUtensorMap& tmR, const float* bias, int M, int N, int K, cudaStream_t st,
                         const LnArgs* ln = nullptr) {
-  using Cfg = Gemm2Cfg<EPI>;
-  auto kern = gemm_bf16_tc2_kernel<EPI, OUT_BF16>;
+  using Cfg = Gemm2Cfg<EPI, DEEPK>;
+  auto kern = gemm_bf16_tc2_kernel<EPI, OUT_BF16, DEEPK>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -735,6 +748,7 @@ static int dispatch_epi2(const CUtensorMap& a, const CUtensorMap& w, const CUten
   switch (epi) {
     case PCD_EPI_RESIDUAL_STATS:
       if (ob || ln == nullptr) break;
+      if (K >= 1024) return launch_gemm2<PCD_EPI_RESIDUAL_STATS, false, true>(a, w, c, r, bias, M, N, K, st, ln);
       return launch_gemm2<PCD_EPI_RESIDUAL_STATS, false>(a, w, c, r, bias, M, N, K, st, ln);
     case PCD_EPI_LN_BIAS:
       if (!ob || ln == nullptr) break;
