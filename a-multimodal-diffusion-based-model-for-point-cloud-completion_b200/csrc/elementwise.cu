@@ -396,7 +396,13 @@ extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_poin
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)dim * (c_in + 1) * sizeof(float);  // <= 2048 * 9 * 4 = 72 KB
   if (smem > 48 * 1024) {
-    PCD_CHECK_ARG(false, "embed_tokens: width %d with %d channels needs %zu B of shared memory (> 48 KB)", dim, c_in, smem);
+    // width 2048 (base1B) with >= 5 channels: opt in to more than 48 KB of dynamic shared memory
+    cudaError_t e = cudaSuccess;
+    DISPATCH_MAXV(dim, (e = cudaFuncSetAttribute(embed_tokens_kernel<MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+    if (e != cudaSuccess) {
+      set_error("embed_tokens: width %d with %d channels needs %zu B of shared memory: %s", dim, c_in, smem, cudaGetErrorString(e));
+      return PCD_ERR_CUDA;
+    }
   }
   DISPATCH_MAXV(dim, (embed_tokens_kernel<MAXV><<<grid, block, smem, st>>>(x, x_seqs, c_in, n_points, w_in, b_in, prefix, n_prefix, add_cond, ln_g, ln_b, eps, h, seqs, dim)));
   PCD_CHECK_LAUNCH("embed_tokens");

@@ -71,6 +71,33 @@ def test_forward_layernorm_folded_vs_separate(case):
     print(f"{case}: folded vs golden {rel(y_fold, g['out']):.2e}, separate vs golden {rel(y_sep, g['out']):.2e}")
 
 
+def test_forward_width_2048_layernorm_folded():
+    """base1B width (2048 = 32 heads, 16 statistics slots per row) on the LayerNorm-folded path against
+    the separate-LayerNorm path and the fp32 parity mode (no golden at this width: 2 layers, short sequence)."""
+    import pcd_b200 as P
+    lib = P._lib.load()
+    cfg = dict(P.MODEL_CONFIGS["base40M-uncond"], width=2048, heads=32, layers=2, n_ctx=300)
+    torch.manual_seed(3)
+    m16 = P.model_from_config(cfg, DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        m16.output_proj.weight.normal_(std=0.02)
+    m32 = P.model_from_config(cfg, DEV, dtype=torch.float32)
+    m32.load_state_dict(m16.state_dict())
+    x = torch.randn(2, cfg["input_channels"], 300, device=DEV)
+    t = torch.tensor([900, 17], device=DEV)
+    with torch.no_grad():
+        y_fold = m16(x, t).clone()
+        lib.pcd_set_debug_flags(16)
+        try:
+            y_sep = m16(x, t).clone()
+        finally:
+            lib.pcd_set_debug_flags(0)
+        y32 = m32(x, t)
+    torch.cuda.synchronize()
+    assert rel(y_fold, y32) < TOL_BF16 and rel(y_sep, y32) < TOL_BF16, (rel(y_fold, y32), rel(y_sep, y32))
+    assert rel(y_fold, y_sep) < 1e-2
+
+
 def test_forward_cfg_shares_x():
     """2B-sequence CFG forward (cond rows then uncond rows sharing x) == two B-sized calls."""
     model, cfg, _ = build_model("small_imagevec", torch.float32)

@@ -136,7 +136,7 @@ def test_cast_rowstats():
     assert rel(stats, want) < 1e-5, describe(stats, want)
 
 
-@pytest.mark.parametrize("M,N,K", [(128 * 37 + 5, 512, 512), (2048, 512, 2048), (1500, 1024, 1024)])
+@pytest.mark.parametrize("M,N,K", [(128 * 37 + 5, 512, 512), (2048, 512, 2048), (1500, 1024, 1024), (700, 2048, 512)])
 def test_gemm_residual_stats(M, N, K):
     """PCD_EPI_RESIDUAL_STATS: h <- h + A W^T + b in place, bf16 copy and row statistics
     (reference transformer.py:113-114, the residual update of a block)."""
@@ -155,7 +155,8 @@ def test_gemm_residual_stats(M, N, K):
 
 
 @pytest.mark.parametrize("gelu", [False, True])
-@pytest.mark.parametrize("M,N,K", [(128 * 9 + 77, 1536, 512), (1026 * 2, 2048, 512), (600, 1024, 1024)])
+@pytest.mark.parametrize("M,N,K", [(128 * 9 + 77, 1536, 512), (1026 * 2, 2048, 512), (600, 1024, 1024),
+                                   (520, 512, 2048)])   # width 2048 (base1B): 16 statistics slots, un-prefetched path
 def test_gemm_layernorm_folded(M, N, K, gelu):
     """PCD_EPI_LN_BIAS(_GELU): LayerNorm folded into the projection (transformer.py:108-114) against
     torch's LayerNorm -> Linear (-> GELU) in fp64 on the same bf16 activations."""
