@@ -98,6 +98,43 @@ def test_forward_width_2048_layernorm_folded():
     assert rel(y_fold, y_sep) < 1e-2
 
 
+@pytest.mark.parametrize("name", ["base40M-imagevec", "base40M-textvec", "base40M-uncond", "base40M", "base300M",
+                                  "base1B", "upsample"])
+def test_every_registered_config_runs_at_full_size(name):
+    """Each entry of the reference's MODEL_CONFIGS (models/configs.py:15-114) at its real shape, B = 1:
+    the bf16 tensor-core forward against the fp32 parity-mode forward of the same weights."""
+    import pcd_b200 as P
+    cfg = P.MODEL_CONFIGS[name]
+    torch.manual_seed(11)
+    m16 = P.model_from_config(cfg, DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        m16.output_proj.weight.normal_(std=0.02)
+    m32 = P.model_from_config(cfg, DEV, dtype=torch.float32)
+    m32.load_state_dict(m16.state_dict())
+    for m in (m16, m32):
+        if hasattr(m, "accept_grid_embeddings"):
+            m.accept_grid_embeddings = True
+    cls = cfg["name"]
+    kw = {}
+    if cls == "CLIPImagePointDiffusionTransformer":
+        e = torch.randn(1, 768, device=DEV)
+        kw["embeddings"] = e / e.norm(dim=1, keepdim=True)
+    if "Grid" in cls:
+        kw["embeddings"] = torch.randn(1, 1024, 256, device=DEV)
+    if "Upsample" in cls:
+        lr = torch.rand(1, cfg["input_channels"], cfg["cond_ctx"], device=DEV) - 0.5
+        lr[:, 3:] = (lr[:, 3:] + 0.5) * 255.0
+        kw["low_res"] = lr
+    x = torch.randn(1, cfg["input_channels"], cfg["n_ctx"], device=DEV)
+    t = torch.tensor([500], device=DEV)
+    with torch.no_grad():
+        y16 = m16(x, t, **kw)
+        y32 = m32(x, t, **kw)
+    torch.cuda.synchronize()
+    assert y16.shape == (1, cfg["output_channels"], cfg["n_ctx"]) and torch.isfinite(y16).all()
+    assert rel(y16, y32) < TOL_BF16, (name, rel(y16, y32))
+
+
 def test_forward_cfg_shares_x():
     """2B-sequence CFG forward (cond rows then uncond rows sharing x) == two B-sized calls."""
     model, cfg, _ = build_model("small_imagevec", torch.float32)
