@@ -79,6 +79,8 @@ _SIGS = {
     "pcd_attention": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 C.c_float, vp, C.c_int, vp]),
+    "pcd_attention_hd32": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
+                                     C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
     "pcd_rope_bf16": (C.c_int, [C.POINTER(AttnOperand), vp, C.c_int, C.c_int, C.c_int, vp]),
     "pcd_farthest_point_sample": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "pcd_nearest_points": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),

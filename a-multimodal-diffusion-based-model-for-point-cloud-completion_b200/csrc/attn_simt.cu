@@ -1,4 +1,4 @@
-// fp32 CUDA-core flash attention (head dim 64) for the 1e-4 parity mode.
+// fp32 CUDA-core flash attention (head dim 64, or 32 for the TwoStream denoiser) for the 1e-4 parity mode.
 // Online softmax in fp32 with exact expf; q and k are scaled separately on load
 // exactly like the reference (q*hd^-1/4, k*hd^-1/4, transformer.py:76-80), optional
 // 3-axis rotary on head dims 0..5 (rotaryencoderpcd.py:6-27).
@@ -6,8 +6,9 @@
 
 namespace pcd {
 
-constexpr int AQ = 64, AKV = 64, HD = 64, APAD = 4;
+constexpr int AQ = 64, AKV = 64, APAD = 4;
 
+template <int HD>
 struct AttnSmem {
   float Qt[HD][AQ + APAD];    // [k][query]
   float Kt[HD][AKV + APAD];   // [k][key]
@@ -29,6 +30,7 @@ __device__ __forceinline__ void rope6(float* x /*6 values: dims 0..5*/, const fl
   x[5] = e2 * s2 + o2 * c2;
 }
 
+template <int HD>
 __global__ void __launch_bounds__(256) attn_f32_kernel(
     const float* __restrict__ q, int64_t q_bs, int64_t q_ls, int64_t q_hs,
     const float* __restrict__ k, int64_t k_bs, int64_t k_ls, int64_t k_hs,
@@ -36,7 +38,8 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(
     float* __restrict__ out, int64_t o_bs, int64_t o_ls, int len_q, int len_kv, float q_scale,
     float k_scale, const float* __restrict__ rope) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
+  AttnSmem<HD>& sm = *reinterpret_cast<AttnSmem<HD>*>(smem_raw);
+  constexpr int OC = HD / 16;  // output columns per thread (16 threads span a head)
   int tid = threadIdx.x;
   int q0 = blockIdx.x * AQ, h = blockIdx.y, b = blockIdx.z;
   const float* qb = q + b * q_bs + h * q_hs;
@@ -63,13 +66,13 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(
   for (int i = tid; i < HD * AQ; i += 256) sm.Qt[i / AQ][i % AQ] *= q_scale;
 
   int tx = tid & 15, ty = tid >> 4;
-  float m_run[4], l_run[4], acc[4][4];
+  float m_run[4], l_run[4], acc[4][OC];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     m_run[i] = -INFINITY;
     l_run[i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < OC; ++j) acc[i][j] = 0.f;
   }
 
   for (int kv0 = 0; kv0 < len_kv; kv0 += AKV) {
@@ -145,16 +148,17 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] *= alpha[i];
+      for (int j = 0; j < OC; ++j) acc[i][j] *= alpha[i];
 #pragma unroll 8
     for (int kk = 0; kk < AKV; ++kk) {
       float4 a = *reinterpret_cast<const float4*>(&sm.Pt[kk][ty * 4]);
-      float4 bb = *reinterpret_cast<const float4*>(&sm.Vs[kk][tx * 4]);
-      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[OC];
+#pragma unroll
+      for (int j = 0; j < OC; ++j) bv[j] = sm.Vs[kk][tx * OC + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < OC; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
   }
 #pragma unroll
@@ -162,8 +166,9 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(
     int r = q0 + ty * 4 + i;
     if (r < len_q) {
       float inv = 1.f / l_run[i];
-      *reinterpret_cast<float4*>(out + b * o_bs + (int64_t)r * o_ls + h * HD + tx * 4) =
-          make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
+      float* o = out + b * o_bs + (int64_t)r * o_ls + h * HD + tx * OC;
+#pragma unroll
+      for (int j = 0; j < OC; ++j) o[j] = acc[i][j] * inv;
     }
   }
 }
@@ -197,14 +202,14 @@ int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const floa
   return PCD_OK;
 }
 
-int launch_attention_f32(const pcd_attn_operand* q, const pcd_attn_operand* k,
-                         const pcd_attn_operand* v, float* out, int64_t o_bs, int64_t o_ls,
-                         int batch, int heads, int len_q, int len_kv, float q_scale, float k_scale,
-                         const float* rope, cudaStream_t st) {
+template <int HD>
+static int launch_attention_f32_hd(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
+                                   float* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv,
+                                   float q_scale, float k_scale, const float* rope, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(AttnSmem));
+    cudaError_t e = cudaFuncSetAttribute(attn_f32_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(AttnSmem<HD>));
     if (e != cudaSuccess) {
       set_error("attention_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PCD_ERR_CUDA;
@@ -212,13 +217,22 @@ int launch_attention_f32(const pcd_attn_operand* q, const pcd_attn_operand* k,
     attr_set = true;
   }
   dim3 grid(ceil_div(len_q, AQ), heads, batch);
-  attn_f32_kernel<<<grid, 256, sizeof(AttnSmem), st>>>(
+  attn_f32_kernel<HD><<<grid, 256, sizeof(AttnSmem<HD>), st>>>(
       (const float*)q->ptr, q->batch_stride, q->row_stride, q->head_stride,
       (const float*)k->ptr, k->batch_stride, k->row_stride, k->head_stride,
       (const float*)v->ptr, v->batch_stride, v->row_stride, v->head_stride, out, o_bs, o_ls, len_q,
       len_kv, q_scale, k_scale, rope);
   PCD_CHECK_LAUNCH("attention_f32");
   return PCD_OK;
+}
+
+int launch_attention_f32(const pcd_attn_operand* q, const pcd_attn_operand* k,
+                         const pcd_attn_operand* v, float* out, int64_t o_bs, int64_t o_ls,
+                         int batch, int heads, int len_q, int len_kv, float q_scale, float k_scale,
+                         const float* rope, int head_dim, cudaStream_t st) {
+  if (head_dim == 32)
+    return launch_attention_f32_hd<32>(q, k, v, out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, rope, st);
+  return launch_attention_f32_hd<64>(q, k, v, out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, rope, st);
 }
 
 }  // namespace pcd

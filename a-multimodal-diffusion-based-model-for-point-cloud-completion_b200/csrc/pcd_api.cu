@@ -87,7 +87,7 @@ static int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, const void* bas
 
 int launch_attention_f32(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                          float* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
-                         int len_kv, float q_scale, float k_scale, const float* rope, cudaStream_t st);
+                         int len_kv, float q_scale, float k_scale, const float* rope, int head_dim, cudaStream_t st);
 int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const float* coords, int batch, int heads,
                      int len, cudaStream_t st);
 int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
@@ -159,7 +159,7 @@ extern "C" int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* 
   if (precision == PCD_F32) {
     PCD_CHECK_ARG(operand_ok(q, 4, 4) && operand_ok(k, 4, 4) && operand_ok(v, 4, 4), "attention(f32): operands must be 16-byte aligned with strides %% 4 == 0");
     PCD_CHECK_ARG(o_ls % 4 == 0 && o_bs % 4 == 0, "attention(f32): output strides must be multiples of 4");
-    return launch_attention_f32(q, k, v, (float*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, rope_coords, st);
+    return launch_attention_f32(q, k, v, (float*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, rope_coords, 64, st);
   }
   if (precision == PCD_BF16) {
     PCD_CHECK_ARG(operand_ok(q, 8, 2) && operand_ok(k, 8, 2) && operand_ok(v, 8, 2), "attention(bf16): operands must be 16-byte aligned with strides %% 8 == 0");
@@ -171,6 +171,18 @@ extern "C" int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* 
     return launch_attention_bf16(q, k, v, (uint16_t*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, st);
   }
   PCD_CHECK_ARG(false, "attention: unknown precision %d", precision);
+}
+
+extern "C" int pcd_attention_hd32(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
+                                  float* out, int64_t out_batch_stride, int64_t out_row_stride, int batch, int heads,
+                                  int len_q, int len_kv, float q_scale, float k_scale, void* stream) {
+  PCD_CHECK_ARG(q != nullptr && k != nullptr && v != nullptr && out != nullptr, "attention_hd32: null argument");
+  PCD_CHECK_ARG(batch > 0 && heads > 0 && len_q > 0 && len_kv > 0, "attention_hd32: empty problem");
+  PCD_CHECK_ARG(batch <= 65535 && heads <= 65535, "attention_hd32: batch/heads exceed grid limits");
+  PCD_CHECK_ARG(q_scale > 0.f && k_scale > 0.f, "attention_hd32: scales must be positive");
+  PCD_CHECK_ARG(operand_ok(q, 4, 4) && operand_ok(k, 4, 4) && operand_ok(v, 4, 4), "attention_hd32: operands must be 16-byte aligned with strides %% 4 == 0");
+  return launch_attention_f32(q, k, v, out, out_batch_stride, out_row_stride, batch, heads, len_q, len_kv, q_scale, k_scale,
+                              nullptr, 32, (cudaStream_t)stream);
 }
 
 extern "C" int pcd_rope_bf16(const pcd_attn_operand* x, const float* coords, int batch, int heads, int len,

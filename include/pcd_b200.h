@@ -196,6 +196,13 @@ PCD_API int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* k, 
                   float q_scale, float k_scale, const float* rope_coords,
                   int precision, void* stream);
 
+/* fp32 attention with head dim 32 (c in [0, 32) in the operand description): the cross-attention of the TwoStream
+ * denoiser's read / compute / write blocks (models/modules.py:17-63: z_dim = x_dim = 256, 8 heads); CUDA-core kernel,
+ * softmax((q_scale q) . (k_scale k)) v like pcd_attention. */
+PCD_API int pcd_attention_hd32(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
+                               float* out, int64_t out_batch_stride, int64_t out_row_stride, int batch, int heads,
+                               int len_q, int len_kv, float q_scale, float k_scale, void* stream);
+
 /* bf16 mode of the rotary attention: rotate head dims 0..5 of a q or k operand IN PLACE with
  * theta = pi * coords[b, l, :] (apply_rotary_pos_emb, rotaryencoderpcd.py:6-27; fp32 arithmetic), then call
  * pcd_attention(..., rope_coords = NULL, PCD_BF16).  The fp32 kernel rotates in registers on load instead. */

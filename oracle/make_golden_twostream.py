@@ -1,0 +1,84 @@
+"""Golden vectors of the unmodified reference's TwoStreamDenoiser (models/model.py, models/modules.py):
+
+    python -m oracle.make_golden_twostream     # -> tests/golden/twostream_{small,config}.npz
+
+Weights and inputs are regenerated from hash seeds (oracle/det.py); only the outputs are stored."""
+import importlib
+import os
+
+import numpy as np
+import torch
+
+from oracle import det
+from oracle.ref_harness import load_reference
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# "config": the shapes of the reference's config.yaml:24-38 restricted to the class / view modalities
+CASES = {
+    "small": dict(num_points=96, num_latents=24, latent_dim=64, x_dim=64, num_blocks=2, num_compute_layers=2,
+                  num_heads=2, num_classes=16, active_modalities=["class", "view"], B=3, seed=1501),
+    "config": dict(num_points=1024, num_latents=256, latent_dim=256, x_dim=256, num_blocks=6, num_compute_layers=4,
+                   num_heads=8, num_classes=16, active_modalities=["class", "view"], B=2, seed=1502),
+}
+
+
+def ctor_kwargs(c):
+    return {k: v for k, v in c.items() if k not in ("B", "seed")}
+
+
+def inputs(c):
+    B, N, s = c["B"], c["num_points"], c["seed"]
+    x = det.normal((B, 3, N), s + 1)
+    t = torch.tensor([(37 * i + 5) % 1000 for i in range(B)], dtype=torch.long)
+    labels = torch.tensor([(3 * i + 1) % c["num_classes"] for i in range(B)], dtype=torch.long)
+    views = det.uniform((B, 3), s + 2, 1.0)
+    n_lat = c["num_latents"] + 2 + 1
+    prev = det.normal((B, n_lat, c["latent_dim"]), s + 3, std=0.5)
+    return x, t, labels, views, prev
+
+
+def fill(shapes, seed):
+    """Deterministic weights: N(0, 0.25/sqrt(fan_in)) matrices, small biases, LayerNorm near identity -- including
+    ln_latent (zero-initialised in the reference, which would hide the self-conditioning path)."""
+    sd = {}
+    for i, (k, shp) in enumerate(shapes.items()):
+        if k == "token_types_template":
+            continue
+        if k.endswith("weight") and len(shp) == 1:      # LayerNorm gain
+            sd[k] = 1.0 + 0.1 * det.normal(shp, seed + 7 * i)
+        elif k.endswith("bias"):
+            sd[k] = 0.05 * det.normal(shp, seed + 7 * i)
+        elif len(shp) >= 2:
+            sd[k] = det.normal(shp, seed + 7 * i) * (1.0 / (shp[-1] ** 0.5))
+        else:
+            sd[k] = 0.02 * det.normal(shp, seed + 7 * i)
+    return sd
+
+
+def main():
+    load_reference()
+    model_mod = importlib.import_module("point_e.models.model")
+    for name, c in CASES.items():
+        torch.manual_seed(0)
+        ref = model_mod.TwoStreamDenoiser(**ctor_kwargs(c)).eval()
+        shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+        sd = fill(shapes, c["seed"])
+        sd["token_types_template"] = ref.state_dict()["token_types_template"]
+        ref.load_state_dict(sd)
+        x, t, labels, views, prev = inputs(c)
+        with torch.no_grad():
+            y0, z0 = ref(x, t, class_labels=labels, viewpoints=views)
+            y1, z1 = ref(x, t, class_labels=labels, viewpoints=views, prev_latent=prev)
+            y2, z2 = ref(x, t, class_labels=torch.zeros_like(labels), viewpoints=None, prev_latent=z0)  # unconditional branch
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"twostream_{name}.npz"),
+                            y0=y0.numpy(), z0=z0.numpy(), y1=y1.numpy(), y2=y2.numpy(),
+                            # later latents: every 8th token row is enough to pin them (file size)
+                            z1=z1[:, ::8].numpy(), z2=z2[:, ::8].numpy(),
+                            shapes_keys=np.array(list(shapes.keys())),
+                            shapes_vals=np.array([",".join(map(str, v)) for v in shapes.values()]))
+        print(name, y0.shape, z0.shape, float(y0.abs().mean()), float(z1.abs().mean()), len(shapes), "tensors")
+
+
+if __name__ == "__main__":
+    main()
