@@ -75,6 +75,7 @@ _SIGS = {
     "pcd_gemm_bf16": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_int, vp]),
     "pcd_gemm_bf16_ex": (C.c_int, [C.POINTER(GemmArgs), vp]),
+    "pcd_add_f32": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
     "pcd_cast_rowstats": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
     "pcd_attention": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,

@@ -156,6 +156,19 @@ __global__ void __launch_bounds__(256) cast_rowstats_kernel(const float* __restr
   }
 }
 
+// out = a + b (fp32, out may alias a): the stream additions of the TwoStream denoiser that are not the
+// tail of a projection (z + ln_latent(..), token-type embeddings; models/modules.py:228-229, model.py:536)
+__global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                               int64_t n4, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  } else if (i == n4) {
+    for (int64_t k = n4 * 4; k < n; ++k) out[k] = a[k] + b[k];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // token assembly + ln_pre (reference models/transformer.py:205-220)
 // ---------------------------------------------------------------------------
@@ -368,6 +381,16 @@ extern "C" int pcd_add_layernorm(float* h, int ldh, const void* y, int ldy, int 
   PCD_CHECK_ARG(y != nullptr, "add_layernorm: y missing");
   return launch_layernorm(h, ldh, y, ldy, y_precision, gamma, beta, out, ld_out, out_precision, rows, dim, eps,
                           stream, "add_layernorm");
+}
+
+extern "C" int pcd_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) {
+  PCD_CHECK_ARG(a != nullptr && b != nullptr && out != nullptr && n > 0, "add_f32: bad arguments");
+  PCD_CHECK_ARG(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                "add_f32: operands must be 16-byte aligned");
+  const int64_t n4 = n / 4;
+  add_f32_kernel<<<(unsigned)ceil_div64(n4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n4, n);
+  PCD_CHECK_LAUNCH("add_f32");
+  return PCD_OK;
 }
 
 extern "C" int pcd_cast_rowstats(const float* x, int ldx, uint16_t* out, int ld_out, float* stats, int rows,

@@ -110,6 +110,36 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out.reshape(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
 
 
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = a + b (fp32, same shape, contiguous; ``out`` may be ``a``)."""
+    require_cuda(a, b)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape
+    a, b = a.contiguous(), b.contiguous()
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.load().pcd_add_f32(ptr(a), ptr(b), ptr(out), a.numel(), stream_ptr()), "add_f32")
+    return out
+
+
+def attention_hd32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int) -> torch.Tensor:
+    """softmax(q k^T * 32^-1/2) v per head for head dim 32 (TwoStream CrossAttention, reference
+    models/modules.py:40-63): q [B, Lq, H*32], k / v [B, Lkv, H*32] fp32 (views with a unit last stride are fine)."""
+    require_cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype == torch.float32
+    B, Lq, W = q.shape
+    Lkv = k.shape[1]
+    assert W == heads * 32 and k.shape == v.shape == (B, Lkv, W)
+    for t in (q, k, v):
+        assert t.stride(2) == 1
+    out = torch.empty(B, Lq, W, device=q.device, dtype=torch.float32)
+    s = 32.0 ** -0.25
+    opnd = lambda t: _operand(t, 0, t.stride(0), t.stride(1), 32)
+    qo, ko, vo = opnd(q), opnd(k), opnd(v)
+    check(_lib.load().pcd_attention_hd32(C.byref(qo), C.byref(ko), C.byref(vo), ptr(out), out.stride(0), out.stride(1),
+                                         B, heads, Lq, Lkv, s, s, stream_ptr()), "attention_hd32")
+    return out
+
+
 def cast_rowstats(h: torch.Tensor):
     """bf16 copy of the fp32 residual stream h [rows, dim] + per-128-column (mean, M2) of the rounded
     values [rows, dim/128, 2]: the inputs of the LayerNorm-folded projections."""

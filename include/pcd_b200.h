@@ -163,6 +163,10 @@ typedef struct {
 } pcd_gemm_args;
 PCD_API int pcd_gemm_bf16_ex(const pcd_gemm_args* args, void* stream);
 
+/* out = a + b, fp32, n elements (out may alias a): stream additions of the TwoStream denoiser that are not the tail of
+ * a projection (models/modules.py:228-229, models/model.py:536). */
+PCD_API int pcd_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+
 /* bf16 copy + row statistics of an fp32 matrix x [rows, dim] (dim % 128 == 0): out = bf16(x),
  * stats float2 [rows, dim/128] = (mean, M2) of the ROUNDED values per 128 columns -- the form the
  * LN-folded projections consume (used once per forward, after ln_pre). */

@@ -80,5 +80,34 @@ def main():
         print(name, y0.shape, z0.shape, float(y0.abs().mean()), float(z1.abs().mean()), len(shapes), "tensors")
 
 
+def gen_sampler():
+    """The reference's own sampling setup for this model (run.py:119-141, config.yaml:40-58): guided Heun with the
+    latent self-conditioning threaded by guided_denoiser, on the small case, deterministic noise."""
+    from oracle import cases
+    from oracle.make_golden import patched_noise
+    load_reference()
+    model_mod = importlib.import_module("point_e.models.model")
+    gd = importlib.import_module("point_e.diffusion.gaussian_diffusion")
+    smp = importlib.import_module("point_e.diffusion.sampler")
+    c = CASES["small"]
+    ref = model_mod.TwoStreamDenoiser(**ctor_kwargs(c)).eval()
+    shapes = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    sd = fill(shapes, c["seed"])
+    sd["token_types_template"] = ref.state_dict()["token_types_template"]
+    ref.load_state_dict(sd)
+    diffusion = gd.GaussianDiffusion(betas=gd.get_named_beta_schedule("linear", 1000), model_mean_type="epsilon",
+                                     model_var_type="fixed_small", loss_type="mse")
+    sampler = smp.PointCloudSampler(device=torch.device("cpu"), models=[ref], diffusions=[diffusion], num_points=[c["num_points"]],
+                                    aux_channels=[], guidance_scale=[3.0], clip_denoised=True, use_karras=[True],
+                                    karras_steps=[6], sigma_min=[1e-3], sigma_max=[120], s_churn=[0.0])
+    _, _, labels, views, _ = inputs(c)
+    with patched_noise(cases.DetNoise(777)), torch.no_grad():
+        ys = [y.clone() for y in sampler.sample_batch_progressive(c["B"], dict(class_labels=labels, viewpoints=views))]
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "twostream_sampler_small.npz"), yields=torch.stack(ys).numpy())
+    print("sampler", len(ys), float(ys[-1].abs().mean()))
+
+
 if __name__ == "__main__":
+    main()
+    gen_sampler()
     main()

@@ -134,21 +134,32 @@ def heun_progressive(
     s2t = SigmaToT(tables)
     B = shape[0]
 
-    def denoise(x_t, sigma, kwargs):
+    # latent self-conditioning of tuple-returning models (TwoStreamDenoiser): the guided denoiser keeps one
+    # latent per branch and feeds it back as prev_latent at the next evaluation (k_diffusion.py:171-203);
+    # the unguided path passes model_kwargs through unchanged and drops the latent (:160-164,
+    # gaussian_diffusion.py:285-289)
+    latents = {"cond": None, "uncond": None}
+
+    def denoise(x_t, sigma, kwargs, branch=None):
         t = torch.tensor([s2t(s) for s in sigma.cpu().numpy()], dtype=torch.long)
         c_in = (1.0 / (sigma ** 2 + 1) ** 0.5)[(...,) + (None,) * (x_t.dim() - 1)]
         x_in = x_t * c_in
+        kwargs = dict(kwargs)
+        if branch is not None and latents[branch] is not None:
+            kwargs["prev_latent"] = latents[branch]
         out = model_fn(x_in, t, **kwargs)
         if isinstance(out, tuple):
-            out = out[0]
+            out, extra = out
+            if branch is not None:
+                latents[branch] = extra
         if trace is not None:
             trace.append((t.clone(), x_in.clone(), out.clone()))
         return tables.pred_xstart(out, x_in, t, clip_denoised)
 
     if guidance_scale != 0 and guidance_scale != 1:
         def denoiser(x_t, sigma):
-            cond = denoise(x_t, sigma, {k: v[:B] for k, v in model_kwargs.items()})
-            uncond = denoise(x_t, sigma, {k: v[B:] for k, v in model_kwargs.items()})
+            cond = denoise(x_t, sigma, {k: v[:B] for k, v in model_kwargs.items() if k != "prev_latent"}, "cond")
+            uncond = denoise(x_t, sigma, {k: v[B:] for k, v in model_kwargs.items() if k != "prev_latent"}, "uncond")
             return uncond + guidance_scale * (cond - uncond)
     else:
         def denoiser(x_t, sigma):

@@ -28,3 +28,23 @@ def test_oracle_matches_reference(name):
     assert rel(y0, g["y0"]) < 2e-6 and rel(z0, g["z0"]) < 2e-6
     assert rel(y1, g["y1"]) < 2e-6 and rel(z1[:, ::8], g["z1"]) < 2e-6
     assert rel(y2, g["y2"]) < 2e-6 and rel(z2[:, ::8], g["z2"]) < 2e-6
+
+
+def test_oracle_sampler_threads_the_latent_like_the_reference():
+    """Guided Heun sampling with latent self-conditioning (k_diffusion.py:171-203): the oracle's loop against the
+    reference's own PointCloudSampler run on the small TwoStream model."""
+    from oracle import cases
+    from oracle import sampler as S
+    c = CASES["small"]
+    g, sd = golden_state("small")
+    want = torch.from_numpy(load_golden("twostream_sampler_small")["yields"])
+    _, _, labels, views, _ = inputs(c)
+    tab = S.Tables(schedule="linear", timesteps=1000)
+    fn = lambda xx, tt, **k: OT.twostream_forward(sd, c, xx, tt, k.get("class_labels"), k.get("viewpoints"), k.get("prev_latent"))
+    with torch.no_grad():
+        ys = list(S.sample_batch_progressive([fn], [lambda b, k: k], [tab], [c["num_points"]], [], c["B"],
+                                             dict(class_labels=labels, viewpoints=views), guidance_scale=[3.0], karras_steps=[6],
+                                             sigma_min=[1e-3], sigma_max=[120], s_churn=[0.0], noise_fn=cases.DetNoise(777)))
+    got = torch.stack(ys)
+    assert got.shape == want.shape
+    assert float((got - want).norm() / want.norm()) < 1e-4
