@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: completed clouds/s of the full 64-step Karras/Heun sampler.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|eager-gpu]
 
 A "step" is one complete sampling pass over one batch: 64 Heun steps = 127 denoiser
 evaluations (each a 2B-sequence classifier-free-guidance forward) + the fused sampler
@@ -148,6 +148,64 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# Same-box comparator: the reference algorithm (oracle port, plain PyTorch ops) run eagerly on the
+# GPU, fp32 and bf16-autocast.  Reported beside the headline; none of this repo's kernels are on that path.
+# ---------------------------------------------------------------------------
+def run_eager_gpu(args):
+    import torch
+
+    from oracle import cases, det
+    from oracle import sampler as S
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_golden import shapes_of
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    mcfg, dcfg, B, smax, churn, guidance = WORKLOADS[args.workload]
+    assert mcfg.startswith("base40M-"), "the eager comparator covers the base40M vector-conditioned workloads"
+    B = args.batch or B
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = dict(cases.MODEL_CONFIGS[mcfg])
+    sd = {k: v.to(dev) for k, v in det.fill_state_dict(shapes_of(cfg), 201, mode="reference", width=cfg["width"]).items()}
+    tab = S.Tables(**cases.DIFFUSION_CONFIGS["base"])
+    g = torch.Generator(device=dev).manual_seed(1234)
+    e = torch.randn(B, 768, device=dev, generator=g)
+    kw = dict(embeddings=torch.cat([e / e.norm(dim=1, keepdim=True), torch.zeros_like(e)], 0))
+    heun_steps = max(1, args.steps)
+    out = {}
+    for mode in ("fp32", "bf16-autocast"):
+        base_fn = S.make_model_fn(sd, cfg)
+        if mode == "fp32":
+            fn = base_fn
+        else:
+            def fn(x, t, _f=base_fn, **k):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return _f(x, t, **k).float()
+        gen = S.heun_progressive(fn, tab, (B, 6, cfg["n_ctx"]), steps=64, sigma_min=1e-3, sigma_max=smax, s_churn=churn,
+                                 guidance_scale=guidance, model_kwargs=kw,
+                                 noise_fn=lambda shp: torch.randn(*shp, device=dev, generator=g))
+        with torch.no_grad():
+            for _ in range(1 + args.warmup):
+                next(gen)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(heun_steps):
+                next(gen)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out[mode] = B / (dt / heun_steps * 64.0)
+        del gen
+        torch.cuda.empty_cache()
+    print(json.dumps({"impl": "eager-gpu", "metric": METRIC, "unit": UNIT, "value": out["bf16-autocast"],
+                      "fp32": out["fp32"], "bf16_autocast": out["bf16-autocast"], "n_gpus": 1,
+                      "config": {"workload": args.workload, "batch": B,
+                                 "note": f"reference algorithm as plain PyTorch ops on cuda:0 (oracle port; [B,H,L,L] attention "
+                                         f"materialised, fp32 softmax); {heun_steps} of 64 Heun steps timed by wall clock "
+                                         f"around synchronize, scaled to 64"}}))
 
 
 # ---------------------------------------------------------------------------
@@ -423,13 +481,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager-gpu"])
     ap.add_argument("--workload", default="base40M-imagevec-1024pt-b64", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "eager-gpu":
+        run_eager_gpu(args)
     else:
         run_b200(args)
 

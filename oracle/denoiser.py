@@ -16,7 +16,7 @@ LN_EPS = 1e-5  # nn.LayerNorm default, reference models/transformer.py:108,110,1
 def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
     """reference models/util.py:72-89 -- [cos(t f_k) || sin(t f_k)], f_k = exp(-ln(P) k/half)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].to(t.dtype) * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -108,7 +108,7 @@ def denoiser_forward(sd, cfg, x: Tensor, t: Tensor, *, embeddings: Optional[Tens
         cond = [(t_embed, time_tok)]
     elif name == "CLIPImagePointDiffusionTransformer":  # :255-287
         if embeddings is None:
-            embeddings = torch.zeros(x.shape[0], 768)
+            embeddings = torch.zeros(x.shape[0], 768, device=x.device)
         clip_out = math.sqrt(embeddings.shape[1]) * embeddings
         cond = [(linear(clip_out, sd, "clip_embed"), cfg.get("token_cond", False)),
                 (t_embed, time_tok)]
@@ -118,7 +118,7 @@ def denoiser_forward(sd, cfg, x: Tensor, t: Tensor, *, embeddings: Optional[Tens
         cond = [(t_embed, time_tok), (embed_low_res(sd, low_res), True)]
     elif name == "CLIPImageGridUpsamplePointDiffusionTransformer":  # :453-494
         if embeddings is None:
-            embeddings = torch.zeros(x.shape[0], 1024, 256, dtype=x.dtype)
+            embeddings = torch.zeros(x.shape[0], 1024, 256, dtype=x.dtype, device=x.device)
         cond = [(t_embed, time_tok), (embed_grid(sd, embeddings), True),
                 (embed_low_res(sd, low_res), True)]
     else:

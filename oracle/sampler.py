@@ -59,8 +59,8 @@ class Tables:
         eps = first C channels; x0 = a_t*x - b_t*eps; clamp to [-1, 1]."""
         C = x_in.shape[1]
         eps = model_out[:, :C]
-        a = torch.from_numpy(self.sqrt_recip_alphas_cumprod)[t].float()
-        b = torch.from_numpy(self.sqrt_recipm1_alphas_cumprod)[t].float()
+        a = torch.from_numpy(self.sqrt_recip_alphas_cumprod)[t.cpu()].float().to(x_in.device)
+        b = torch.from_numpy(self.sqrt_recipm1_alphas_cumprod)[t.cpu()].float().to(x_in.device)
         while a.dim() < x_in.dim():
             a, b = a[..., None], b[..., None]
         x0 = a * x_in - b * eps
@@ -141,7 +141,7 @@ def heun_progressive(
     latents = {"cond": None, "uncond": None}
 
     def denoise(x_t, sigma, kwargs, branch=None):
-        t = torch.tensor([s2t(s) for s in sigma.cpu().numpy()], dtype=torch.long)
+        t = torch.tensor([s2t(s) for s in sigma.cpu().numpy()], dtype=torch.long, device=x_t.device)
         c_in = (1.0 / (sigma ** 2 + 1) ** 0.5)[(...,) + (None,) * (x_t.dim() - 1)]
         x_in = x_t * c_in
         kwargs = dict(kwargs)
@@ -166,7 +166,7 @@ def heun_progressive(
             return denoise(x_t, sigma, model_kwargs)
 
     def to_d(x, sigma, denoised):
-        return (x - denoised) / sigma[(...,) + (None,) * (x.dim() - sigma.dim())]
+        return (x - denoised) / sigma[(...,) + (None,) * (x.dim() - sigma.dim())].to(x.device)
 
     s_in = x.new_ones([B])
     denoised = None
