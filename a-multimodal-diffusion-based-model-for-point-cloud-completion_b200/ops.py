@@ -110,6 +110,11 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return out.reshape(*x.shape[:-1], N) if out.dim() == 2 and x.dim() != 2 else out
 
 
+def launch_count() -> int:
+    """Kernels this library has launched so far in the process (pcd_launch_count)."""
+    return int(_lib.load().pcd_launch_count())
+
+
 def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = a + b (fp32, same shape, contiguous; ``out`` may be ``a``)."""
     require_cuda(a, b)

@@ -10,10 +10,13 @@ embedding and the few plain stream additions through their kernels; PyTorch only
 embedding-table gathers / concatenations, which are memory movement).  The nn.Module tree below is a parameter
 container with the reference's names -- it is never called.
 
-Scope of this round: the backbone and the "class" / "view" condition encoders.  The partial-cloud and depth-map
-encoders (nn.TransformerEncoder / Decoder stacks, model.py:262-434) are not built yet: constructing the model
-with those modalities raises NotImplementedError instead of silently running something else.
+All four condition encoders are built: "class", "view", and the partial-cloud / depth-map encoders (stacks of
+norm-first GELU transformer encoder / decoder layers with 8 heads, model.py:262-434; the depth map is patchified by
+one GEMM over its 32 x 32 patches).  Their outputs do not depend on the diffusion step, so they are computed once
+per distinct input tensor and reused by every denoiser evaluation of a sampling run (the reference re-runs them
+in every forward, model.py:498-509); set ``model.cache_conditioning = False`` to recompute every call.
 """
+import math
 from typing import List, Optional
 
 import torch
@@ -126,6 +129,70 @@ class _ViewAngleEmbedding(nn.Module):  # models/model.py:235-259
                 nn.init.constant_(m.bias, 0)
 
 
+ENC_LAYERS, ENC_HEADS = 8, 8  # PartialPointCloudEncoder / DepthMapEncoder defaults, never overridden (model.py:264-266,343-355)
+
+
+def _tx_stack(decoder: bool, dim: int, layers: int) -> nn.Module:
+    """torch's own transformer stack, used as a parameter container only (reference state_dict keys:
+    layers.{i}.self_attn.in_proj_weight, .multihead_attn.*, .linear1/2, .norm1/2/3)."""
+    kw = dict(d_model=dim, nhead=ENC_HEADS, dim_feedforward=4 * dim, dropout=0.1, activation="gelu", batch_first=True,
+              norm_first=True)
+    if decoder:
+        return nn.TransformerDecoder(nn.TransformerDecoderLayer(**kw), num_layers=layers)
+    return nn.TransformerEncoder(nn.TransformerEncoderLayer(**kw), num_layers=layers, enable_nested_tensor=False)
+
+
+class _TokenEncoder(nn.Module):
+    """What PartialPointCloudEncoder and DepthMapEncoder share (model.py:278-300, 355-383): an encoder stack over
+    [CLS, sequence] (named ``encoder`` / ``mixer``), learned queries, a decoder and a refiner of half the depth."""
+    def __init__(self, dim, num_tokens, stack_name):
+        super().__init__()
+        self.num_tokens, self.stack_name = num_tokens, stack_name
+        setattr(self, stack_name, _tx_stack(False, dim, ENC_LAYERS))
+        self.cls_token = nn.Parameter(torch.randn(1, 1, dim) * 0.02)
+        self.token_queries = nn.Parameter(nn.init.xavier_uniform_(torch.empty(1, num_tokens - 1, dim)))
+        self.decoder = _tx_stack(True, dim, ENC_LAYERS // 2)
+        self.query_refiner = _tx_stack(False, dim, ENC_LAYERS // 2)
+        self.ln_out = nn.LayerNorm(dim)
+        self.proj_out = nn.Linear(dim, dim)
+
+    def _init_linears(self):
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+
+class _PartialCloudEncoder(_TokenEncoder):  # models/model.py:262-338
+    def __init__(self, dim, num_tokens):
+        super().__init__(dim, num_tokens, "encoder")
+        self.input_proj = nn.Linear(3, dim)
+        self._init_linears()
+
+
+def sincos_position_table(h: int, w: int, dim: int, temperature: float = 10000.0) -> torch.Tensor:
+    """Fixed 2-D positional table of the depth encoder (model.py:190-213): per grid cell (row-major)
+    [sin(x f) | cos(x f) | sin(y f) | cos(y f)], f_k = temperature^(-2k / (dim/4)), k < dim/4."""
+    assert dim % 4 == 0
+    k = torch.arange(dim // 4, dtype=torch.float32)
+    f = torch.exp(-2.0 * k * (math.log(temperature) / (dim // 4)))
+    cell = torch.arange(h * w)
+    cx, cy = (cell % w).float()[:, None] * f, (cell // w).float()[:, None] * f
+    return torch.cat([cx.sin(), cx.cos(), cy.sin(), cy.cos()], dim=1)
+
+
+class _DepthEncoder(_TokenEncoder):  # models/model.py:341-434
+    PATCH, IMAGE = 32, 512
+
+    def __init__(self, dim, num_tokens):
+        super().__init__(dim, num_tokens, "mixer")
+        self.proj = nn.Conv2d(1, dim, kernel_size=self.PATCH, stride=self.PATCH)  # container: weight [dim, 1, 32, 32]
+        side = self.IMAGE // self.PATCH
+        self.register_buffer("pos_embed", sincos_position_table(side, side, dim))
+        self._init_linears()
+
+
 _TOKEN_TYPE = {"class": 0, "view": 1, "partial_pcd": 2, "depth": 3}
 
 
@@ -137,10 +204,9 @@ class TwoStreamDenoiser(nn.Module):
                  active_modalities: List[str] = ("class", "view", "partial_pcd", "depth"),
                  device: Optional[torch.device] = None, dtype: torch.dtype = torch.float32):
         super().__init__()
-        unsupported = [m for m in active_modalities if m in ("partial_pcd", "depth")]
-        if unsupported:
-            raise NotImplementedError(f"condition encoders {unsupported} are not built yet (models/model.py:262-434); "
-                                      "construct the model with active_modalities=['class', 'view']")
+        unknown = [m for m in active_modalities if m not in _TOKEN_TYPE]
+        if unknown:
+            raise KeyError(unknown[0])  # the reference indexes its modality table (model.py:466)
         if latent_dim % num_heads or x_dim != latent_dim or latent_dim // num_heads != 32:
             # CrossAttention projects both streams to the query stream's width and splits it into heads
             # (modules.py:30-37); the attention kernel behind it is built for head dim 32 (the shipped config.yaml)
@@ -149,6 +215,8 @@ class TwoStreamDenoiser(nn.Module):
             raise ValueError("dtype must be torch.float32 (parity mode) or torch.bfloat16 (tensor-core projections)")
         if dtype == torch.bfloat16 and latent_dim % 128:
             raise ValueError("bf16 mode needs latent_dim % 128 == 0")
+        if any(m in ("partial_pcd", "depth") for m in active_modalities) and latent_dim != 32 * ENC_HEADS:
+            raise ValueError("the partial-cloud / depth encoders always use 8 heads (model.py:264,355): latent_dim must be 256")
         self.num_points, self.latent_dim, self.cond_drop_prob = num_points, latent_dim, cond_drop_prob
         self.active_modalities = list(active_modalities)
         self.compute_dtype = dtype
@@ -156,14 +224,25 @@ class TwoStreamDenoiser(nn.Module):
                                            num_blocks, num_compute_layers, num_heads)
         self.encoders = nn.ModuleDict()
         types = []
+        self._cond_sizes = []
         for m in self.active_modalities:
-            self.encoders[m] = (_ClassEmbedding(num_classes, latent_dim) if m == "class"
-                                else _ViewAngleEmbedding(3, latent_dim))
-            types.append(_TOKEN_TYPE[m])  # one token per class / view modality
+            if m == "class":
+                enc, count = _ClassEmbedding(num_classes, latent_dim), 1
+            elif m == "view":
+                enc, count = _ViewAngleEmbedding(3, latent_dim), 1
+            elif m == "partial_pcd":
+                enc, count = _PartialCloudEncoder(latent_dim, num_tokens_ppcd), num_tokens_ppcd
+            else:
+                enc, count = _DepthEncoder(latent_dim, num_tokens_depth), num_tokens_depth
+            self.encoders[m] = enc
+            self._cond_sizes.append(count)
+            types += [_TOKEN_TYPE[m]] * count
         self.token_type_embeddings = nn.Embedding(4, latent_dim)
         nn.init.normal_(self.token_type_embeddings.weight, std=0.005)
         self.register_buffer("token_types_template", torch.tensor(types, dtype=torch.long))
         self._bf16 = {}
+        self.cache_conditioning = True
+        self._cond_cache = {}
         if device is not None:
             self.to(device)
         self.eval()
@@ -172,17 +251,25 @@ class TwoStreamDenoiser(nn.Module):
         return model_kwargs
 
     # ---- kernels ---------------------------------------------------------------------------------
-    def _w(self, lin: nn.Linear) -> torch.Tensor:
-        """Weight in the compute dtype (bf16 copies are cached per parameter version)."""
-        w = lin.weight
-        if self.compute_dtype == torch.float32:
-            return w.detach()
-        key = (id(w), w._version, w.data_ptr())
-        hit = self._bf16.get(id(w))
-        if hit is None or hit[0] != key:
-            hit = (key, w.detach().to(torch.bfloat16).contiguous())
-            self._bf16[id(w)] = hit
+    def _wb(self, w: torch.Tensor) -> torch.Tensor:
+        """bf16 copy of a weight matrix (a parameter or a row slice of one), cached per parameter version."""
+        slot = (w.data_ptr(), tuple(w.shape))
+        hit = self._bf16.get(slot)
+        if hit is None or hit[0] != w._version:
+            hit = (w._version, w.detach().to(torch.bfloat16).contiguous())
+            self._bf16[slot] = hit
         return hit[1]
+
+    def _proj(self, a2: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], gelu: bool = False,
+              residual: Optional[torch.Tensor] = None, out_fp32: bool = True) -> torch.Tensor:
+        """Projection of [M, K] activations by an nn.Linear-layout weight [N, K].  fp32 activations use the CUDA-core
+        GEMM (parity mode and the tiny layers whose K is not a multiple of 8); bf16 activations the tcgen05 GEMM."""
+        bias = bias.detach().float() if bias is not None else None
+        epi = EPI_BIAS_GELU if gelu else EPI_BIAS
+        if a2.dtype == torch.float32:
+            return ops.linear(a2, weight.detach().float(), bias, epilogue=epi, residual=residual)
+        return ops.linear(a2, self._wb(weight), bias, epilogue=epi, residual=residual,
+                          out_dtype=torch.float32 if (out_fp32 or residual is not None) else torch.bfloat16)
 
     def _ln(self, x2: torch.Tensor, norm: nn.LayerNorm, act: bool = True) -> torch.Tensor:
         """LayerNorm of an fp32 [M, d] stream; act=True -> in the dtype the next projection consumes."""
@@ -191,14 +278,7 @@ class TwoStreamDenoiser(nn.Module):
 
     def _lin(self, a2: torch.Tensor, lin: nn.Linear, gelu: bool = False, residual: Optional[torch.Tensor] = None,
              out_fp32: bool = True) -> torch.Tensor:
-        """Projection of [M, K] activations.  fp32 activations use the CUDA-core GEMM (parity mode and the tiny
-        layers whose K is not a multiple of 8); bf16 activations use the tcgen05 GEMM."""
-        bias = lin.bias.detach().float() if lin.bias is not None else None
-        if a2.dtype == torch.float32:
-            return ops.linear(a2, lin.weight.detach().float(), bias, epilogue=EPI_BIAS_GELU if gelu else EPI_BIAS,
-                              residual=residual)
-        return ops.linear(a2, self._w(lin), bias, epilogue=EPI_BIAS_GELU if gelu else EPI_BIAS, residual=residual,
-                          out_dtype=torch.float32 if (out_fp32 or residual is not None) else torch.bfloat16)
+        return self._proj(a2, lin.weight, lin.bias, gelu, residual, out_fp32)
 
     @staticmethod
     def _lin_k3(a2: torch.Tensor, lin: nn.Linear, gelu: bool = False) -> torch.Tensor:
@@ -230,27 +310,119 @@ class TwoStreamDenoiser(nn.Module):
         a = ops.attention_hd32(q, k, v, heads).view(-1, d)
         return self._lin(self._act(a), attn.proj, residual=residual)
 
-    # ---- conditioning (model.py:489-538, eval branch) ------------------------------------------------
-    def _cond_tokens(self, B, dev, class_labels, viewpoints) -> torch.Tensor:
+    # ---- torch-layout transformer layers of the partial-cloud / depth encoders ----------------------------
+    def _mha(self, q_in: torch.Tensor, kv_in: torch.Tensor, B: int, mha: nn.MultiheadAttention,
+             residual: torch.Tensor) -> torch.Tensor:
+        """residual + out_proj(softmax(q k^T / sqrt(32)) v), nn.MultiheadAttention weights: in_proj_weight is
+        [Wq; Wk; Wv] stacked on the output axis, so self-attention is ONE projection to [M, 3d] whose column
+        blocks the attention kernel reads in place, cross-attention one projection per stream."""
+        d = residual.shape[1]
+        W, b = mha.in_proj_weight, mha.in_proj_bias
+        if q_in is kv_in:
+            qkv = self._proj(q_in, W, b).view(B, -1, 3 * d)
+            q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        else:
+            q = self._proj(q_in, W[:d], b[:d]).view(B, -1, d)
+            kv = self._proj(kv_in, W[d:], b[d:]).view(B, -1, 2 * d)
+            k, v = kv[..., :d], kv[..., d:]
+        a = ops.attention_hd32(q, k, v, ENC_HEADS).view(-1, d)
+        return self._proj(self._act(a), mha.out_proj.weight, mha.out_proj.bias, residual=residual)
+
+    def _ffn(self, x2: torch.Tensor, norm: nn.LayerNorm, layer) -> torch.Tensor:
+        hid = self._proj(self._ln(x2, norm), layer.linear1.weight, layer.linear1.bias, gelu=True, out_fp32=False)
+        return self._proj(hid, layer.linear2.weight, layer.linear2.bias, residual=x2)
+
+    def _encoder_stack(self, x2: torch.Tensor, B: int, stack: nn.TransformerEncoder) -> torch.Tensor:
+        for layer in stack.layers:  # norm-first: x += SA(LN1 x); x += FFN(LN2 x)
+            h = self._ln(x2, layer.norm1)
+            x2 = self._mha(h, h, B, layer.self_attn, x2)
+            x2 = self._ffn(x2, layer.norm2, layer)
+        return x2
+
+    def _decoder_stack(self, x2: torch.Tensor, memory2: torch.Tensor, B: int, stack: nn.TransformerDecoder) -> torch.Tensor:
+        for layer in stack.layers:  # x += SA(LN1 x); x += MHA(LN2 x, memory); x += FFN(LN3 x); memory is not normalised
+            h = self._ln(x2, layer.norm1)
+            x2 = self._mha(h, h, B, layer.self_attn, x2)
+            x2 = self._mha(self._ln(x2, layer.norm2), memory2, B, layer.multihead_attn, x2)
+            x2 = self._ffn(x2, layer.norm3, layer)
+        return x2
+
+    def _token_encoder(self, enc: _TokenEncoder, seq: torch.Tensor) -> torch.Tensor:
+        """seq [B, L, d] fp32 (embedded points / patches) -> [B, num_tokens, d]  (model.py:321-338, 417-434)."""
+        B, L, d = seq.shape
+        x = torch.empty(B, 1 + L, d, device=seq.device)
+        x[:, 0].copy_(enc.cls_token.detach()[0].expand(B, d))
+        x[:, 1:].copy_(seq)
+        x = self._encoder_stack(x.view(-1, d), B, getattr(enc, enc.stack_name)).view(B, 1 + L, d)
+        memory = self._act(x[:, 1:].contiguous().view(-1, d))
+        q = enc.token_queries.detach()[0].expand(B, -1, -1).contiguous().view(-1, d)
+        tok = self._decoder_stack(q, memory, B, enc.decoder)
+        tok = ops.add(tok, self._encoder_stack(tok, B, enc.query_refiner))
+        out = torch.empty(B, enc.num_tokens, d, device=seq.device)
+        out[:, 0].copy_(x[:, 0])
+        out[:, 1:].copy_(tok.view(B, -1, d))
+        out = self._proj(self._act(out.view(-1, d)), enc.proj_out.weight, enc.proj_out.bias)
+        return self._ln(out, enc.ln_out, act=False).view(B, enc.num_tokens, d)
+
+    def _encode(self, m: str, value: torch.Tensor, dev) -> torch.Tensor:
+        """Tokens of one modality, [B, n_tok, d] fp32, before the token-type embedding."""
+        enc = self.encoders[m]
         d = self.latent_dim
-        cond = torch.zeros(B, len(self.active_modalities), d, device=dev)
-        te = self.token_type_embeddings.weight.detach()[self.token_types_template]  # gather: [n_cond, d]
-        for i, m in enumerate(self.active_modalities):
-            value = class_labels if m == "class" else viewpoints
-            if value is None or bool(torch.all(value == 0)):
-                continue  # zero token, masked type embedding
-            if m == "class":
-                enc = self.encoders["class"]
-                rows = enc.embedding.weight.detach()[value.to(dev).long()].float().contiguous()  # table gather
-                tok = ops.layernorm(rows, enc.norm.weight.detach(), enc.norm.bias.detach(), eps=LN_EPS)
-            else:
-                mlp = self.encoders["view"].mlp
-                h = value.to(dev).float().contiguous()
-                h = self._lin_k3(h, mlp[0], gelu=True)
-                h = ops.linear(h, mlp[2].weight.detach(), mlp[2].bias.detach(), epilogue=EPI_BIAS_GELU)
-                h = ops.linear(h, mlp[4].weight.detach(), mlp[4].bias.detach())
-                tok = ops.layernorm(h, mlp[5].weight.detach(), mlp[5].bias.detach(), eps=LN_EPS)
-            cond[:, i].copy_(ops.add(tok, te[i].expand(B, d).contiguous()))
+        if m == "class":
+            rows = enc.embedding.weight.detach()[value.to(dev).long()].float().contiguous()  # table gather
+            return ops.layernorm(rows, enc.norm.weight.detach(), enc.norm.bias.detach(), eps=LN_EPS).view(-1, 1, d)
+        if m == "view":
+            mlp = enc.mlp
+            h = self._lin_k3(value.to(dev).float().contiguous(), mlp[0], gelu=True)
+            h = ops.linear(h, mlp[2].weight.detach(), mlp[2].bias.detach(), epilogue=EPI_BIAS_GELU)
+            h = ops.linear(h, mlp[4].weight.detach(), mlp[4].bias.detach())
+            return ops.layernorm(h, mlp[5].weight.detach(), mlp[5].bias.detach(), eps=LN_EPS).view(-1, 1, d)
+        if m == "partial_pcd":
+            B, P, _ = value.shape
+            pts = value.to(dev).float().contiguous().view(B * P, -1)
+            return self._token_encoder(enc, self._lin_k3(pts, enc.input_proj).view(B, P, d))
+        # depth: Conv2d with kernel = stride = 32 is one GEMM over the flattened non-overlapping patches
+        B, Cin, H, W = value.shape
+        Pp = enc.PATCH
+        assert H == enc.IMAGE and W == enc.IMAGE, "the positional table is built for 512 x 512 depth maps (model.py:352)"
+        gh, gw = H // Pp, W // Pp
+        patches = (value.to(dev).float().view(B, Cin, gh, Pp, gw, Pp).permute(0, 2, 4, 1, 3, 5).contiguous()
+                   .view(B * gh * gw, Cin * Pp * Pp))
+        emb = self._proj(self._act(patches), enc.proj.weight.view(d, -1), enc.proj.bias)
+        emb = ops.add(emb, enc.pos_embed.detach().float().expand(B, -1, -1).contiguous().view(-1, d))
+        return self._token_encoder(enc, emb.view(B, gh * gw, d))
+
+    # ---- conditioning (model.py:489-538, eval branch) ------------------------------------------------
+    def _modality_tokens(self, m: str, value, B: int, dev, type_row: torch.Tensor, count: int) -> torch.Tensor:
+        """encoder tokens + token-type embedding, or zeros when the input is None / all zero (model.py:503-507,
+        527-535).  Step-invariant: cached per input tensor (storage address, shape, version) across forwards."""
+        d = self.latent_dim
+        if value is None:
+            return torch.zeros(B, count, d, device=dev)
+        key = (m, value.data_ptr(), tuple(value.shape), tuple(value.stride()), value._version, str(value.device))
+        if self.cache_conditioning:
+            hit = self._cond_cache.get(key)
+            if hit is not None:
+                return hit[1]
+        if bool(torch.all(value == 0)):
+            tok = torch.zeros(B, count, d, device=dev)
+        else:
+            tok = self._encode(m, value, dev)
+            tok = ops.add(tok.view(-1, d), type_row.expand(B * count, d).contiguous()).view(B, count, d)
+        if self.cache_conditioning:
+            for k in [k for k in self._cond_cache if k[0] == m][:-3]:  # keep the last few inputs of a modality
+                del self._cond_cache[k]
+            self._cond_cache[key] = (value, tok)  # holding `value` keeps its storage address from being reused
+        return tok
+
+    def _cond_tokens(self, B, dev, values) -> torch.Tensor:
+        d = self.latent_dim
+        cond = torch.empty(B, sum(self._cond_sizes), d, device=dev)
+        table = self.token_type_embeddings.weight.detach()
+        at = 0
+        for m, count in zip(self.active_modalities, self._cond_sizes):
+            cond[:, at:at + count].copy_(self._modality_tokens(m, values[m], B, dev, table[_TOKEN_TYPE[m]], count))
+            at += count
         return cond
 
     # ---- forward ---------------------------------------------------------------------------------
@@ -258,14 +430,14 @@ class TwoStreamDenoiser(nn.Module):
     def forward(self, x, t, class_labels=None, viewpoints=None, partial_pcd=None, depth_maps=None, prev_latent=None):
         assert x.shape[-1] == self.num_points, \
             f"Input point cloud must have {self.num_points} points, got {x.shape[-1]} points."
-        assert partial_pcd is None and depth_maps is None, "partial_pcd / depth encoders are not built yet"
         if self.training:
             raise NotImplementedError("inference path only (the reference's training branch draws dropout masks)")
         bb = self.denoiser_backbone
         B, dev = x.shape[0], x.device
-        d, n_cond = self.latent_dim, len(self.active_modalities)
+        d, n_cond = self.latent_dim, sum(self._cond_sizes)
         n_lat = bb.num_z + n_cond + 1
-        cond = self._cond_tokens(B, dev, class_labels, viewpoints)
+        cond = self._cond_tokens(B, dev, {"class": class_labels, "view": viewpoints, "partial_pcd": partial_pcd,
+                                          "depth": depth_maps})
 
         # timestep token (modules.py:220): Mlp(timestep_embedding(t)) -- two tiny fp32 projections
         te = ops.timestep_embedding(t, d)

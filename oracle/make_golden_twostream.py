@@ -20,11 +20,28 @@ CASES = {
                   num_heads=2, num_classes=16, active_modalities=["class", "view"], B=3, seed=1501),
     "config": dict(num_points=1024, num_latents=256, latent_dim=256, x_dim=256, num_blocks=6, num_compute_layers=4,
                    num_heads=8, num_classes=16, active_modalities=["class", "view"], B=2, seed=1502),
+    # all four modalities: the partial-cloud and depth-map encoders always have 8 + 4 + 4 layers of 8 heads
+    # (model.py:264-266,343-344), so latent_dim = 256 keeps their head dim at the config's 32; the backbone is shallow
+    "full4": dict(num_points=128, num_latents=32, latent_dim=256, x_dim=256, num_blocks=1, num_compute_layers=1,
+                  num_heads=8, num_classes=16, num_tokens_ppcd=16, num_tokens_depth=8,
+                  active_modalities=["class", "view", "partial_pcd", "depth"], B=2, seed=1503, partial_points=80),
 }
 
 
 def ctor_kwargs(c):
-    return {k: v for k, v in c.items() if k not in ("B", "seed")}
+    return {k: v for k, v in c.items() if k not in ("B", "seed", "partial_points")}
+
+
+def n_cond(c):
+    sizes = {"class": 1, "view": 1, "partial_pcd": c.get("num_tokens_ppcd", 64), "depth": c.get("num_tokens_depth", 32)}
+    return sum(sizes[m] for m in c["active_modalities"])
+
+
+def extra_inputs(c):
+    """partial cloud [B, P, 3] in the dataset's range and depth maps [B, 1, 512, 512] (model.py:352: the positional
+    table is built for 512 x 512 inputs)."""
+    B, s = c["B"], c["seed"]
+    return det.uniform((B, c["partial_points"], 3), s + 4, 0.5), det.uniform((B, 1, 512, 512), s + 5, 1.0).abs()
 
 
 def inputs(c):
@@ -33,7 +50,7 @@ def inputs(c):
     t = torch.tensor([(37 * i + 5) % 1000 for i in range(B)], dtype=torch.long)
     labels = torch.tensor([(3 * i + 1) % c["num_classes"] for i in range(B)], dtype=torch.long)
     views = det.uniform((B, 3), s + 2, 1.0)
-    n_lat = c["num_latents"] + 2 + 1
+    n_lat = c["num_latents"] + n_cond(c) + 1
     prev = det.normal((B, n_lat, c["latent_dim"]), s + 3, std=0.5)
     return x, t, labels, views, prev
 
@@ -67,6 +84,9 @@ def main():
         sd["token_types_template"] = ref.state_dict()["token_types_template"]
         ref.load_state_dict(sd)
         x, t, labels, views, prev = inputs(c)
+        if "partial_pcd" in c["active_modalities"]:
+            gen_full(ref, name, c, shapes)
+            continue
         with torch.no_grad():
             y0, z0 = ref(x, t, class_labels=labels, viewpoints=views)
             y1, z1 = ref(x, t, class_labels=labels, viewpoints=views, prev_latent=prev)
@@ -78,6 +98,27 @@ def main():
                             shapes_keys=np.array(list(shapes.keys())),
                             shapes_vals=np.array([",".join(map(str, v)) for v in shapes.values()]))
         print(name, y0.shape, z0.shape, float(y0.abs().mean()), float(z1.abs().mean()), len(shapes), "tensors")
+
+
+def gen_full(ref, name, c, shapes):
+    """All four modalities: the two transformer encoders on their own, the full forward, and the forward with the
+    depth map dropped (zero tokens + masked type embedding, model.py:503-507,527-535)."""
+    x, t, labels, views, prev = inputs(c)
+    pcd, depth = extra_inputs(c)
+    with torch.no_grad():
+        tok_p = ref.encoders["partial_pcd"](pcd)
+        tok_d = ref.encoders["depth"](depth)
+        y0, z0 = ref(x, t, class_labels=labels, viewpoints=views, partial_pcd=pcd, depth_maps=depth, prev_latent=prev)
+        y1, z1 = ref(x, t, class_labels=labels, viewpoints=views, partial_pcd=pcd, depth_maps=torch.zeros_like(depth))
+    torch.manual_seed(0)
+    fresh = type(ref.encoders["depth"])(in_channels=1, embed_dim=c["latent_dim"], num_tokens=c["num_tokens_depth"])
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"twostream_{name}.npz"),
+                        tok_p=tok_p.numpy(), tok_d=tok_d.numpy(), y0=y0.numpy(), z0=z0[:, ::4].numpy(),
+                        y1=y1.numpy(), z1=z1[:, ::4].numpy(), pos_embed=fresh.pos_embed[::5, ::3].numpy(),
+                        shapes_keys=np.array(list(shapes.keys())),
+                        shapes_vals=np.array([",".join(map(str, v)) for v in shapes.values()]))
+    print(name, tok_p.shape, tok_d.shape, y0.shape, z0.shape, float(tok_p.abs().mean()), float(tok_d.abs().mean()),
+          float(y0.abs().mean()), len(shapes), "tensors")
 
 
 def gen_sampler():
@@ -110,4 +151,3 @@ def gen_sampler():
 if __name__ == "__main__":
     main()
     gen_sampler()
-    main()

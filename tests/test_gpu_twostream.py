@@ -44,8 +44,43 @@ def test_twostream_state_dict_and_unsupported_modalities():
     assert set(out) == set(sd)
     for k, v in sd.items():
         assert torch.equal(out[k].cpu(), v), k
-    with pytest.raises(NotImplementedError):
-        P.TwoStreamDenoiser(active_modalities=["class", "view", "partial_pcd", "depth"], latent_dim=256, x_dim=256)
+    with pytest.raises(ValueError):  # the transformer encoders always have 8 heads: head dim 32 needs latent_dim 256
+        P.TwoStreamDenoiser(active_modalities=["class", "view", "partial_pcd", "depth"], latent_dim=128, x_dim=128, num_heads=4)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)])
+def test_twostream_all_four_modalities_match_reference(dtype, tol):
+    """Partial-cloud and depth-map encoders (model.py:262-434) on their own and inside the forward; dropped depth map;
+    the step-invariant encoders are evaluated once per input tensor."""
+    from oracle.make_golden_twostream import extra_inputs
+    from pcd_b200 import ops
+    model, c, g, sd = build("full4", dtype)
+    assert set(model.state_dict()) == set(sd)
+    x, t, labels, views, prev = (v.to(DEV) for v in inputs(c))
+    pcd, depth = (v.to(DEV) for v in extra_inputs(c))
+    tok_p = model._encode("partial_pcd", pcd, DEV)
+    tok_d = model._encode("depth", depth, DEV)
+    assert rel(tok_p, g["tok_p"]) < tol, describe(tok_p, g["tok_p"], "partial-cloud tokens")
+    assert rel(tok_d, g["tok_d"]) < tol, describe(tok_d, g["tok_d"], "depth tokens")
+    kw = dict(class_labels=labels, viewpoints=views, partial_pcd=pcd)
+    n0 = ops.launch_count()
+    y0, z0 = model(x, t, depth_maps=depth, prev_latent=prev, **kw)
+    n1 = ops.launch_count()
+    y0b, z0b = model(x, t, depth_maps=depth, prev_latent=prev, **kw)
+    n2 = ops.launch_count()
+    y1, z1 = model(x, t, depth_maps=torch.zeros_like(depth), **kw)
+    torch.cuda.synchronize()
+    for got, want, what in ((y0, g["y0"], "y0"), (z0[:, ::4], g["z0"], "z0"), (y1, g["y1"], "y1"), (z1[:, ::4], g["z1"], "z1")):
+        assert rel(got, want) < tol, describe(got, want, f"full4 {dtype} {what}")
+    assert torch.equal(y0, y0b) and torch.equal(z0, z0b)
+    assert n2 - n1 < (n1 - n0) // 4, (n0, n1, n2)  # second call reuses the cached condition tokens
+    model.cache_conditioning = False
+    y0c, _ = model(x, t, depth_maps=depth, prev_latent=prev, **kw)
+    assert torch.equal(y0, y0c)
+    depth.mul_(0.5)  # in-place edit of an input invalidates its cached tokens
+    model.cache_conditioning = True
+    y2, _ = model(x, t, depth_maps=depth, prev_latent=prev, **kw)
+    assert not torch.equal(y2, y0)
 
 
 def test_twostream_in_the_sampler_with_latent_self_conditioning():

@@ -48,3 +48,22 @@ def test_oracle_sampler_threads_the_latent_like_the_reference():
     got = torch.stack(ys)
     assert got.shape == want.shape
     assert float((got - want).norm() / want.norm()) < 1e-4
+
+
+def test_oracle_partial_cloud_and_depth_encoders_match_reference():
+    """PartialPointCloudEncoder / DepthMapEncoder (model.py:262-434: nn.TransformerEncoder / Decoder stacks) on their
+    own, inside the full four-modality forward, and with the depth map dropped."""
+    from oracle.make_golden_twostream import extra_inputs
+    c = CASES["full4"]
+    g, sd = golden_state("full4")
+    x, t, labels, views, prev = inputs(c)
+    pcd, depth = extra_inputs(c)
+    rel = lambda a, b: float((a - torch.from_numpy(b)).norm() / torch.from_numpy(b).norm())
+    with torch.no_grad():
+        assert rel(OT.partial_pcd_encoder(sd, pcd), g["tok_p"]) < 5e-6
+        assert rel(OT.depth_encoder(sd, depth), g["tok_d"]) < 5e-6
+        y0, z0 = OT.twostream_forward(sd, c, x, t, labels, views, prev_latent=prev, partial_pcd=pcd, depth_maps=depth)
+        y1, z1 = OT.twostream_forward(sd, c, x, t, labels, views, partial_pcd=pcd, depth_maps=torch.zeros_like(depth))
+    assert rel(y0, g["y0"]) < 5e-6 and rel(z0[:, ::4], g["z0"]) < 5e-6
+    assert rel(y1, g["y1"]) < 5e-6 and rel(z1[:, ::4], g["z1"]) < 5e-6
+    assert rel(OT.sincos_2d(16, 16, c["latent_dim"])[::5, ::3], g["pos_embed"]) < 1e-6
