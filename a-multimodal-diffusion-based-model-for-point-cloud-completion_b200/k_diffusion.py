@@ -269,6 +269,9 @@ def make_denoiser_eval(model, model_kwargs: Dict[str, Any], B: int, guided: bool
     with ``prev_latent`` threaded per branch when the model returns a tuple."""
     model_kwargs = model_kwargs or {}
     if _native(model):
+        if hasattr(model, "begin_trajectory"):  # models that carry a latent between evaluations (TwoStreamDenoiser)
+            model.begin_trajectory(2 * B if guided else B)
+
         def eval_native(model_in, t):
             return model.forward_cfg(model_in, t, model_kwargs, doubled=guided, out_channels=eps_channels)
         return eval_native

@@ -238,6 +238,20 @@ def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int) -> torch.Tens
     return attention_packed(qo, ko, vo, out, B, heads, Lq, Lkv, s, s)
 
 
+def attention_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, q_scale: float,
+                    k_scale: float) -> torch.Tensor:
+    """softmax((q_scale q) (k_scale k)^T) v per 64-wide head over strided views: q [B, Lq, H*64], k / v [B, Lkv, H*64]
+    (any batch / row strides, unit last stride; e.g. column blocks of one fused projection output)."""
+    B, Lq, W = q.shape
+    Lkv = k.shape[1]
+    assert W == heads * 64 and k.shape == v.shape == (B, Lkv, W) and q.dtype == k.dtype == v.dtype
+    for t in (q, k, v):
+        assert t.stride(2) == 1
+    out = torch.empty(B, Lq, W, device=q.device, dtype=q.dtype)
+    opnd = lambda t: _operand(t, 0, t.stride(0), t.stride(1), 64)
+    return attention_packed(opnd(q), opnd(k), opnd(v), out, B, heads, Lq, Lkv, q_scale, k_scale)
+
+
 def rotary_attention(qkv: torch.Tensor, coords: torch.Tensor, heads: int) -> torch.Tensor:
     """RotarySelfAttention core (reference models/rotaryencoderpcd.py:68-84): qkv [B, N, 3*D]
     laid out [3][H][64]; 3-axis RoPE on head dims 0..5 of q and k; logits * D**-0.5."""

@@ -43,6 +43,8 @@ class _GraphedStage:
         st, plan = self.state, self.plan
         B = self.shape[0]
         torch.mul(self.noise[0], plan.sigma_max, out=st.x)
+        if hasattr(self.model, "begin_trajectory"):
+            self.model.begin_trajectory(B * (2 if st.guided else 1))
         st.begin(self.noise[1])
         for i, step in enumerate(plan.steps):
             out = self.model.forward_cfg(st.model_in, step.first.t, self.kwargs, st.guided, self.eps_channels)
@@ -62,7 +64,10 @@ class _GraphedStage:
             else:
                 self.noise[k].copy_(noise_fn(self.shape))
         self.kwargs = {k: v for k, v in kwargs.items() if k != "prev_latent"}
-        self.model.prepare_cond(seqs, self.kwargs)
+        if getattr(self.model, "cfg_halves", False):
+            self.model.prepare_cond(seqs, self.kwargs, self.state.guided)
+        else:
+            self.model.prepare_cond(seqs, self.kwargs)
         self.model.prepare_time_tokens(self.plan.eval_timesteps())
         if self.graph is None:
             # warm-up on a side stream (populates every cache), then capture

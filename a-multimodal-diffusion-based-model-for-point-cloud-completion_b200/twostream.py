@@ -243,6 +243,7 @@ class TwoStreamDenoiser(nn.Module):
         self._bf16 = {}
         self.cache_conditioning = True
         self._cond_cache = {}
+        self._cfg, self._time_tok = {}, {}
         if device is not None:
             self.to(device)
         self.eval()
@@ -268,8 +269,64 @@ class TwoStreamDenoiser(nn.Module):
         epi = EPI_BIAS_GELU if gelu else EPI_BIAS
         if a2.dtype == torch.float32:
             return ops.linear(a2, weight.detach().float(), bias, epilogue=epi, residual=residual)
-        return ops.linear(a2, self._wb(weight), bias, epilogue=epi, residual=residual,
+        w = weight if weight.dtype == torch.bfloat16 else self._wb(weight)
+        return ops.linear(a2, w, bias, epilogue=epi, residual=residual,
                           out_dtype=torch.float32 if (out_fp32 or residual is not None) else torch.bfloat16)
+
+    # ---- bf16 mode: 32-wide heads on the 64-wide tensor-core attention kernel -------------------------------
+    # Each head's 32 output rows of Wq / Wk / Wv are followed by 32 zero rows (zero bias), so the projection GEMM
+    # writes q, k, v directly in a [.., H, 64] layout whose upper halves are exact zeros: q.k is unchanged, the upper
+    # half of every output head is zero, and the output projection gets matching zero columns.  The padding doubles
+    # the (small) projection and the MMA work but not the exponentials, which bound the attention kernel; the
+    # alternative -- fp32 CUDA-core attention -- was 85 % of the model's time.
+    def _padded(self, tag: str, owner, mats, biases, cols: bool = False):
+        """bf16 weight (+ fp32 bias) with every 32-row (or, cols=True, 32-column) head group zero-padded to 64; several
+        matrices are stacked on the output axis (one fused projection).  Cached per parameter versions."""
+        key = tuple(m._version for m in mats) + tuple(m.data_ptr() for m in mats)
+        hit = self._bf16.get((tag, id(owner)))
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        if cols:
+            (m,) = mats
+            w = torch.zeros(m.shape[0], m.shape[1] // 32, 64, device=m.device)
+            w[..., :32] = m.detach().view(m.shape[0], -1, 32)
+            w, b = w.view(m.shape[0], -1), biases[0]
+        else:
+            w = torch.cat([m.detach() for m in mats], dim=0)
+            K = w.shape[1]
+            wp = torch.zeros(w.shape[0] // 32, 64, K, device=w.device)
+            wp[:, :32] = w.view(-1, 32, K)
+            w = wp.view(-1, K)
+            if any(x is not None for x in biases):
+                bb = torch.cat([(x.detach().float() if x is not None else torch.zeros(m.shape[0], device=w.device))
+                                for x, m in zip(biases, mats)])
+                b = torch.zeros(bb.shape[0] // 32, 64, device=w.device)
+                b[:, :32] = bb.view(-1, 32)
+                b = b.view(-1)
+            else:
+                b = None
+        w = w.to(torch.bfloat16).contiguous()
+        self._bf16[(tag, id(owner))] = (key, w, b)
+        return w, b
+
+    def _attention_tc(self, q_in, kv_in, B, heads, owner, wq, wk, wv, bq, bk, bv, wo, bo, residual):
+        """bf16 path of both attention flavours: fused zero-padded projections -> tensor-core attention -> padded
+        output projection with the residual in its epilogue."""
+        P = heads * 64
+        s = 32.0 ** -0.25
+        if q_in is kv_in:
+            w, b = self._padded("qkv", owner, (wq, wk, wv), (bq, bk, bv))
+            qkv = self._proj(q_in, w, b, out_fp32=False).view(B, -1, 3 * P)
+            q, k, v = qkv[..., :P], qkv[..., P:2 * P], qkv[..., 2 * P:]
+        else:
+            w, b = self._padded("q", owner, (wq,), (bq,))
+            q = self._proj(q_in, w, b, out_fp32=False).view(B, -1, P)
+            w, b = self._padded("kv", owner, (wk, wv), (bk, bv))
+            kv = self._proj(kv_in, w, b, out_fp32=False).view(B, -1, 2 * P)
+            k, v = kv[..., :P], kv[..., P:]
+        a = ops.attention_views(q, k, v, heads, s, s).view(-1, P)
+        w, _ = self._padded("o", owner, (wo,), (bo,), cols=True)
+        return self._proj(a, w, bo, residual=residual)
 
     def _ln(self, x2: torch.Tensor, norm: nn.LayerNorm, act: bool = True) -> torch.Tensor:
         """LayerNorm of an fp32 [M, d] stream; act=True -> in the dtype the next projection consumes."""
@@ -304,6 +361,9 @@ class TwoStreamDenoiser(nn.Module):
                 residual: torch.Tensor) -> torch.Tensor:
         """residual + proj(softmax(q k^T / sqrt(32)) v) with q from q_stream, k / v from kv_stream (modules.py:40-63)."""
         heads, d = self.denoiser_backbone.num_heads, residual.shape[1]
+        if q_stream.dtype == torch.bfloat16:
+            return self._attention_tc(q_stream, kv_stream, B, heads, attn, attn.wq.weight, attn.wk.weight, attn.wv.weight,
+                                      attn.wq.bias, attn.wk.bias, attn.wv.bias, attn.proj.weight, attn.proj.bias, residual)
         q = self._lin(q_stream, attn.wq).view(B, -1, d)
         k = self._lin(kv_stream, attn.wk).view(B, -1, d)
         v = self._lin(kv_stream, attn.wv).view(B, -1, d)
@@ -318,6 +378,9 @@ class TwoStreamDenoiser(nn.Module):
         blocks the attention kernel reads in place, cross-attention one projection per stream."""
         d = residual.shape[1]
         W, b = mha.in_proj_weight, mha.in_proj_bias
+        if q_in.dtype == torch.bfloat16:
+            return self._attention_tc(q_in, kv_in, B, ENC_HEADS, mha, W[:d], W[d:2 * d], W[2 * d:], b[:d], b[d:2 * d],
+                                      b[2 * d:], mha.out_proj.weight, mha.out_proj.bias, residual)
         if q_in is kv_in:
             qkv = self._proj(q_in, W, b).view(B, -1, 3 * d)
             q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
@@ -426,53 +489,128 @@ class TwoStreamDenoiser(nn.Module):
         return cond
 
     # ---- forward ---------------------------------------------------------------------------------
+    def _time_rows(self, t: torch.Tensor) -> torch.Tensor:
+        """timestep token (modules.py:220): Mlp(timestep_embedding(t)) -- two tiny fp32 projections; t [S] -> [S, d]."""
+        bb = self.denoiser_backbone
+        te = ops.timestep_embedding(t, self.latent_dim)
+        te = ops.linear(te, bb.time_embed.fc1.weight.detach(), bb.time_embed.fc1.bias.detach(), epilogue=EPI_BIAS_GELU)
+        return ops.linear(te, bb.time_embed.fc2.weight.detach(), bb.time_embed.fc2.bias.detach())
+
+    def _backbone_forward(self, x: torch.Tensor, te: torch.Tensor, cond: torch.Tensor, prev: Optional[torch.Tensor]):
+        """Denoiser_backbone.forward (modules.py:198-244) for S sequences: x [S, C, N], time rows te [S, d] (or [1, d]
+        shared), condition tokens [S, n_cond, d], prev [S * n_lat, d] fp32 or None -> ([S, C_out, N], z [S, n_lat, d])."""
+        bb = self.denoiser_backbone
+        S, dev = x.shape[0], x.device
+        d, n_cond = self.latent_dim, cond.shape[1]
+        n_lat = bb.num_z + n_cond + 1
+
+        # x stream: input_proj + ln_pre (modules.py:223-224); K = 3 -> CUDA-core GEMM
+        pts = x.float().permute(0, 2, 1).contiguous().view(S * self.num_points, -1)
+        xs = self._lin_k3(pts, bb.input_proj)
+        xs = self._ln(xs, bb.ln_pre, act=False)
+
+        # latent stream with self-conditioning (modules.py:226-229)
+        z = torch.empty(S, n_lat, d, device=dev)
+        z[:, :bb.num_z].copy_(bb.z_init.detach().expand(S, -1, -1))
+        z[:, bb.num_z:bb.num_z + n_cond].copy_(cond)
+        z[:, -1].copy_(te.expand(S, d))
+        z = z.view(S * n_lat, d)
+        if prev is None:
+            prev = torch.zeros(S * n_lat, d, device=dev)
+        hid = self._lin(self._act(prev), bb.latent_mlp.fc1, gelu=True, out_fp32=False)
+        prev = self._lin(hid, bb.latent_mlp.fc2, residual=prev)
+        z = ops.add(z, self._ln(prev, bb.ln_latent, act=False))
+
+        for blk in bb.blocks:
+            z = self._attend(self._ln(z, blk.read.norm_z1), self._ln(xs, blk.read.norm_x), S, blk.read.attn, z)
+            z = self._mlp(z, blk.read.norm_z2, blk.read.mlp)
+            for cb in blk.compute:
+                zn = self._ln(z, cb.norm_z1)
+                z = self._attend(zn, zn, S, cb.attn, z)
+                z = self._mlp(z, cb.norm_z2, cb.mlp)
+            xs = self._attend(self._ln(xs, blk.write.norm_x1), self._ln(z, blk.write.norm_z), S, blk.write.attn, xs)
+            xs = self._mlp(xs, blk.write.norm_x2, blk.write.mlp)
+
+        out = ops.linear(self._ln(xs, bb.ln_post, act=False), bb.output_proj.weight.detach(), bb.output_proj.bias.detach())
+        return out.view(S, self.num_points, -1).permute(0, 2, 1).contiguous(), z.view(S, n_lat, d)
+
     @torch.no_grad()
     def forward(self, x, t, class_labels=None, viewpoints=None, partial_pcd=None, depth_maps=None, prev_latent=None):
         assert x.shape[-1] == self.num_points, \
             f"Input point cloud must have {self.num_points} points, got {x.shape[-1]} points."
         if self.training:
             raise NotImplementedError("inference path only (the reference's training branch draws dropout masks)")
-        bb = self.denoiser_backbone
-        B, dev = x.shape[0], x.device
-        d, n_cond = self.latent_dim, sum(self._cond_sizes)
-        n_lat = bb.num_z + n_cond + 1
+        B, dev, d = x.shape[0], x.device, self.latent_dim
+        n_lat = self.denoiser_backbone.num_z + sum(self._cond_sizes) + 1
         cond = self._cond_tokens(B, dev, {"class": class_labels, "view": viewpoints, "partial_pcd": partial_pcd,
                                           "depth": depth_maps})
-
-        # timestep token (modules.py:220): Mlp(timestep_embedding(t)) -- two tiny fp32 projections
-        te = ops.timestep_embedding(t, d)
-        te = ops.linear(te, bb.time_embed.fc1.weight.detach(), bb.time_embed.fc1.bias.detach(), epilogue=EPI_BIAS_GELU)
-        te = ops.linear(te, bb.time_embed.fc2.weight.detach(), bb.time_embed.fc2.bias.detach())
-
-        # x stream: input_proj + ln_pre (modules.py:223-224); K = 3 -> CUDA-core GEMM
-        pts = x.float().permute(0, 2, 1).contiguous().view(B * self.num_points, -1)
-        xs = self._lin_k3(pts, bb.input_proj)
-        xs = self._ln(xs, bb.ln_pre, act=False)
-
-        # latent stream with self-conditioning (modules.py:226-229)
-        z = torch.empty(B, n_lat, d, device=dev)
-        z[:, :bb.num_z].copy_(bb.z_init.detach().expand(B, -1, -1))
-        z[:, bb.num_z:bb.num_z + n_cond].copy_(cond)
-        z[:, -1].copy_(te)
-        z = z.view(B * n_lat, d)
-        if prev_latent is None:
-            prev = torch.zeros(B * n_lat, d, device=dev)
-        else:
+        prev = None
+        if prev_latent is not None:
             assert prev_latent.shape == (B, n_lat, d)
             prev = prev_latent.float().contiguous().view(B * n_lat, d)
-        hid = self._lin(self._act(prev), bb.latent_mlp.fc1, gelu=True, out_fp32=False)
-        prev = self._lin(hid, bb.latent_mlp.fc2, residual=prev)
-        z = ops.add(z, self._ln(prev, bb.ln_latent, act=False))
+        return self._backbone_forward(x, self._time_rows(t), cond, prev)
 
-        for blk in bb.blocks:
-            z = self._attend(self._ln(z, blk.read.norm_z1), self._ln(xs, blk.read.norm_x), B, blk.read.attn, z)
-            z = self._mlp(z, blk.read.norm_z2, blk.read.mlp)
-            for cb in blk.compute:
-                zn = self._ln(z, cb.norm_z1)
-                z = self._attend(zn, zn, B, cb.attn, z)
-                z = self._mlp(z, cb.norm_z2, cb.mlp)
-            xs = self._attend(self._ln(xs, blk.write.norm_x1), self._ln(z, blk.write.norm_z), B, blk.write.attn, xs)
-            xs = self._mlp(xs, blk.write.norm_x2, blk.write.mlp)
+    # ---- sampler fast path (same protocol as PointDiffusionTransformer.forward_cfg) ----------------------------
+    pcd_native = True
+    cfg_halves = True  # prepare_cond wants to know whether the kwargs hold [conditional ; unconditional] halves
 
-        out = ops.linear(self._ln(xs, bb.ln_post, act=False), bb.output_proj.weight.detach(), bb.output_proj.bias.detach())
-        return out.view(B, self.num_points, -1).permute(0, 2, 1).contiguous(), z.view(B, n_lat, d)
+    _KW = {"class_labels": "class", "viewpoints": "view", "partial_pcd": "partial_pcd", "depth_maps": "depth"}
+
+    def _cfg_state(self, seqs: int, dev) -> dict:
+        st = self._cfg.get(seqs)
+        if st is None:
+            n_cond = sum(self._cond_sizes)
+            n_lat = self.denoiser_backbone.num_z + n_cond + 1
+            st = dict(cond=torch.zeros(seqs, n_cond, self.latent_dim, device=dev),
+                      latent=torch.zeros(seqs * n_lat, self.latent_dim, device=dev),
+                      out=torch.empty(seqs, self.denoiser_backbone.output_proj.weight.shape[0], self.num_points, device=dev))
+            self._cfg[seqs] = st
+        return st
+
+    def prepare_cond(self, seqs: int, kw, doubled: bool = False) -> None:
+        """Condition tokens of a sampling run into the persistent [seqs, n_cond, d] buffer.  With classifier-free
+        guidance the kwargs rows are [conditional ; unconditional] (sampler.py:133-136) and the reference evaluates the
+        halves as separate calls (k_diffusion.py:182-207), each with its own all-zero test per modality."""
+        unknown = set(kw) - set(self._KW) - {"prev_latent"}
+        if unknown:
+            raise TypeError(f"forward() got an unexpected keyword argument '{sorted(unknown)[0]}'")
+        dev = self.token_type_embeddings.weight.device
+        st = self._cfg_state(seqs, dev)
+        B = seqs // 2 if doubled else seqs
+        for h in range(2 if doubled else 1):
+            vals = {m: None for m in _TOKEN_TYPE}
+            for k, m in self._KW.items():
+                v = kw.get(k)
+                if v is not None:
+                    assert v.shape[0] == seqs, f"{k}: expected {seqs} rows"
+                    vals[m] = v[h * B:(h + 1) * B]
+            st["cond"][h * B:(h + 1) * B].copy_(self._cond_tokens(B, dev, vals))
+
+    def prepare_time_tokens(self, timesteps) -> None:
+        todo = sorted({float(t) for t in timesteps} - set(self._time_tok))
+        if todo:
+            dev = self.token_type_embeddings.weight.device
+            rows = self._time_rows(torch.tensor(todo, device=dev, dtype=torch.float32))
+            for i, k in enumerate(todo):
+                self._time_tok[k] = rows[i:i + 1].clone()
+
+    def begin_trajectory(self, seqs: int) -> None:
+        """Start of a sampling run: no previous latent (zeros == prev_latent=None, modules.py:211-212)."""
+        self._cfg_state(seqs, self.token_type_embeddings.weight.device)["latent"].zero_()
+
+    @torch.no_grad()
+    def forward_cfg(self, x: torch.Tensor, t, model_kwargs, doubled: bool, out_channels: Optional[int] = None):
+        """One evaluation of B (or, with guidance, 2B = [conditional ; unconditional]) sequences sharing the B inputs
+        ``x`` and the integer timestep ``t``; each sequence's latent of the previous evaluation is fed back as its
+        ``prev_latent`` (guided_denoiser, k_diffusion.py:182-207).  Returns a persistent [seqs, C_out, N] buffer."""
+        B = x.shape[0]
+        seqs = 2 * B if doubled else B
+        st = self._cfg_state(seqs, x.device)
+        if not torch.cuda.is_current_stream_capturing():
+            self.prepare_cond(seqs, model_kwargs or {}, doubled)
+            self.prepare_time_tokens([t])
+        out, z = self._backbone_forward(torch.cat([x, x], dim=0) if doubled else x, self._time_tok[float(t)],
+                                        st["cond"], st["latent"])
+        st["latent"].copy_(z.view(st["latent"].shape))
+        st["out"].copy_(out)
+        return st["out"]

@@ -35,7 +35,13 @@ WORKLOADS = {
     "upsample-4096pt-b16": ("upsample", "upsample", 16, 160.0, 0.0, 0.0),
     # configs[4]: 300M denoiser (width 1024, 24 layers) with image grid + partial-cloud conditioning
     "base300M-upsample-4096pt-b8": ("base300M-upsample", "upsample", 8, 160.0, 0.0, 3.0),
+    # the TwoStreamDenoiser of the reference's config.yaml (all four modalities, 57.5 M parameters)
+    # under its own sampling settings (config.yaml:40-58: 32 samples, guidance 3, 64 steps, s_churn 0)
+    "twostream-config-1024pt-b32": ("twostream", "linear-1000", 32, 120.0, 0.0, 3.0),
 }
+TWOSTREAM_CONFIG = dict(num_points=1024, num_latents=256, input_channels=3, output_channels=3, latent_dim=256, x_dim=256,
+                        num_blocks=6, num_compute_layers=4, num_heads=8, num_classes=10, num_tokens_ppcd=256,
+                        num_tokens_depth=128, active_modalities=["class", "view", "partial_pcd", "depth"])
 
 
 def peaks():
@@ -206,6 +212,116 @@ def run_eager_gpu(args):
                                  "note": f"reference algorithm as plain PyTorch ops on cuda:0 (oracle port; [B,H,L,L] attention "
                                          f"materialised, fp32 softmax); {heun_steps} of 64 Heun steps timed by wall clock "
                                          f"around synchronize, scaled to 64"}}))
+
+
+# ---------------------------------------------------------------------------
+# TwoStreamDenoiser (config.yaml shapes) under the sampler, single GPU
+# ---------------------------------------------------------------------------
+def twostream_flops_per_forward(c):
+    """Multiply-add = 2 FLOP, one sequence, backbone only (the condition encoders run once per batch)."""
+    d, N = c["latent_dim"], c["num_points"]
+    nl = c["num_latents"] + 2 + c["num_tokens_ppcd"] + c["num_tokens_depth"] + 1
+    attn = lambda lq, lk: 4 * lq * d * d + 4 * lk * d * d + 4 * lq * lk * d
+    mlp = lambda l: 16 * l * d * d
+    block = attn(nl, N) + mlp(nl) + c["num_compute_layers"] * (attn(nl, nl) + mlp(nl)) + attn(N, nl) + mlp(N)
+    return c["num_blocks"] * block + mlp(nl)
+
+
+def run_twostream(args):
+    import torch
+
+    import pcd_b200 as P
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    assert int(os.environ.get("WORLD_SIZE", "1")) == 1, "single-GPU workload"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    lib = P._lib.load()
+    _, _, B, smax, churn, guidance = WORKLOADS[args.workload]
+    B = args.batch or B
+    c = TWOSTREAM_CONFIG
+    torch.manual_seed(1234)
+    model = P.TwoStreamDenoiser(**c, device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():  # the reference zero-initialises ln_latent; a trained model does not keep it there
+        model.denoiser_backbone.ln_latent.weight.fill_(1.0)
+    diffusion = P.GaussianDiffusion(betas=P.get_named_beta_schedule("linear", 1000), model_mean_type="epsilon",
+                                    model_var_type="fixed_small", loss_type="mse")
+    mk = lambda m, graph: P.PointCloudSampler(dev, [m], [diffusion], [c["num_points"]], [], guidance_scale=[guidance],
+                                              use_karras=[True], karras_steps=[64], sigma_min=[1e-3], sigma_max=[smax],
+                                              s_churn=[churn], use_cuda_graph=graph)
+    sampler = mk(model, True)
+    host_kw = dict(class_labels=torch.randint(1, c["num_classes"], (B,)), viewpoints=torch.rand(B, 3),
+                   partial_pcd=torch.rand(B, 1024, 3) - 0.5, depth_maps=torch.rand(B, 1, 512, 512))
+    host_kw = {k: v.pin_memory() for k, v in host_kw.items()}
+    dev_kw = {k: v.to(dev) for k, v in host_kw.items()}
+    out_host = torch.empty(B, 3, c["num_points"]).pin_memory()
+
+    def step_device():
+        model._cond_cache.clear()  # every batch pays for its condition encoders once
+        return sampler.sample_batch(B, dict(dev_kw))
+
+    def step_e2e():
+        kw = {k: v.to(dev, non_blocking=True) for k, v in host_kw.items()}
+        out_host.copy_(sampler.sample_batch(B, kw))
+        return out_host
+
+    def timed(fn, k):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    for _ in range(max(1, args.warmup)):
+        step_device()
+    clocks = ClockSampler(0)
+    clocks.start()
+    ms = timed(step_device, args.steps)
+    clk = clocks.stop()
+    stage = next(iter(sampler._graphs.values()))
+    c0 = lib.pcd_launch_count()
+    stage._enqueue()
+    torch.cuda.synchronize()
+    launches = int(lib.pcd_launch_count() - c0)
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    class Opaque(torch.nn.Module):  # public forward only: two B-sized calls per evaluation, no graph
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, x, t, **kw):
+            return self.inner(x, t, **kw)
+    plain = mk(Opaque(model), False)
+    plain.sample_batch(2, {k: v[:2] for k, v in dev_kw.items()})
+    ms_plain = timed(lambda: plain.sample_batch(B, dict(dev_kw)), 1)
+
+    pk = peaks()
+    evals = 127 * 2
+    flops = twostream_flops_per_forward(c) * evals * B
+    tf = flops / (ms * 1e-3) / 1e12
+    h2d = sum(v.numel() * v.element_size() for v in host_kw.values())
+    print(json.dumps({
+        "metric": METRIC, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "batch": B, "model": "TwoStreamDenoiser, reference config.yaml:24-38",
+                   "sampler": "64-step Heun, guidance 3, s_churn 0, one CUDA graph per stage",
+                   "l2": "activations of one evaluation (>1 GB) exceed L2"},
+        "e2e": {"value": B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launches * args.steps, "launches_per_step": launches,
+        "public_forward_two_calls_no_graph": {"value": B / (ms_plain * 1e-3), "unit": UNIT},
+        "roofline": {"kernel": "whole step (backbone projections + attention)", "bound": "tensor", "achieved": tf,
+                     "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"], "traffic": None,
+                     "peak_source": pk["source"] + ", sustained",
+                     "note": "useful FLOP only (the zero-padded halves of the 32-wide heads are not counted); ~290 "
+                             "launches per evaluation: d = 256 projections at M = 2B x 1024 / 2B x 643 rows, "
+                             "tensor-core attention, separate LayerNorm kernels"},
+        "clocks": clk}))
 
 
 # ---------------------------------------------------------------------------
@@ -490,6 +606,8 @@ def main():
         run_reference(args)
     elif args.impl == "eager-gpu":
         run_eager_gpu(args)
+    elif args.workload.startswith("twostream"):
+        run_twostream(args)
     else:
         run_b200(args)
 
