@@ -171,6 +171,8 @@ def run_eager_gpu(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     mcfg, dcfg, B, smax, churn, guidance = WORKLOADS[args.workload]
+    if mcfg == "twostream":
+        return run_eager_gpu_twostream(args)
     assert mcfg.startswith("base40M-"), "the eager comparator covers the base40M vector-conditioned workloads"
     B = args.batch or B
     dev = torch.device("cuda:0")
@@ -212,6 +214,58 @@ def run_eager_gpu(args):
                                  "note": f"reference algorithm as plain PyTorch ops on cuda:0 (oracle port; [B,H,L,L] attention "
                                          f"materialised, fp32 softmax); {heun_steps} of 64 Heun steps timed by wall clock "
                                          f"around synchronize, scaled to 64"}}))
+
+
+def run_eager_gpu_twostream(args):
+    """The reference's TwoStreamDenoiser algorithm (oracle restatement, plain PyTorch ops, condition encoders re-run
+    in every forward like model.py:498-509) under the oracle's guided Heun loop on cuda:0, fp32 and bf16 autocast."""
+    import torch
+
+    import pcd_b200 as P
+    from oracle import sampler as S
+    from oracle import twostream as OT
+    _, _, B, smax, churn, guidance = WORKLOADS[args.workload]
+    B = args.batch or B
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    c = TWOSTREAM_CONFIG
+    torch.manual_seed(1234)
+    shell = P.TwoStreamDenoiser(**c, device=dev, dtype=torch.float32)  # parameter container only: reference-shaped state_dict
+    sd = {k: v.detach() for k, v in shell.state_dict().items()}
+    tab = S.Tables(schedule="linear", timesteps=1000)
+    kw = dict(class_labels=torch.randint(1, c["num_classes"], (B,), device=dev), viewpoints=torch.rand(B, 3, device=dev),
+              partial_pcd=torch.rand(B, 1024, 3, device=dev) - 0.5, depth_maps=torch.rand(B, 1, 512, 512, device=dev))
+    kw = {k: torch.cat([v, torch.zeros_like(v)]) for k, v in kw.items()}
+    g = torch.Generator(device=dev).manual_seed(1)
+    heun_steps = max(1, args.steps)
+    out = {}
+    for mode in ("fp32", "bf16-autocast"):
+        def fn(x, t, _m=mode, **k):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(_m != "fp32")):
+                y, z = OT.twostream_forward(sd, c, x, t, k.get("class_labels"), k.get("viewpoints"), k.get("prev_latent"),
+                                            partial_pcd=k.get("partial_pcd"), depth_maps=k.get("depth_maps"))
+            return y.float(), z.float()
+        gen = S.heun_progressive(fn, tab, (B, 3, c["num_points"]), steps=64, sigma_min=1e-3, sigma_max=smax, s_churn=churn,
+                                 guidance_scale=guidance, model_kwargs=kw,
+                                 noise_fn=lambda shp: torch.randn(*shp, device=dev, generator=g))
+        with torch.no_grad():
+            for _ in range(1 + args.warmup):
+                next(gen)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(heun_steps):
+                next(gen)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out[mode] = B / (dt / heun_steps * 64.0)
+        del gen
+        torch.cuda.empty_cache()
+    print(json.dumps({"impl": "eager-gpu", "metric": METRIC, "unit": UNIT, "value": out["bf16-autocast"],
+                      "fp32": out["fp32"], "bf16_autocast": out["bf16-autocast"], "n_gpus": 1,
+                      "config": {"workload": args.workload, "batch": B,
+                                 "note": f"reference algorithm as plain PyTorch ops on cuda:0 (oracle port, condition encoders "
+                                         f"re-run every forward as in the reference); {heun_steps} of 64 Heun steps timed by "
+                                         f"wall clock around synchronize, scaled to 64"}}))
 
 
 # ---------------------------------------------------------------------------

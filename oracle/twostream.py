@@ -46,7 +46,7 @@ def backbone_forward(sd, cfg, x, t, cond, prev_latent, p="denoiser_backbone"):
     zd, heads = cfg["latent_dim"], cfg["num_heads"]
     n_lat = cfg["num_latents"] + cond.shape[1] + 1
     if prev_latent is None:
-        prev_latent = torch.zeros(B, n_lat, zd)
+        prev_latent = torch.zeros(B, n_lat, zd, device=x.device)
     t_embed = _mlp(sd, p + ".time_embed", timestep_embedding(t, zd)).unsqueeze(1)
     x = _ln(sd, p + ".ln_pre", _lin(sd, p + ".input_proj", x))
     z = torch.cat([sd[p + ".z_init"].repeat(B, 1, 1), cond, t_embed], dim=1)
@@ -153,12 +153,13 @@ def cond_tokens(sd, cfg, B, class_labels=None, viewpoints=None, extra_cond=None,
     cfg["active_modalities"]: encoder tokens (zeros when the input is None or all zero) + masked token-type
     embeddings."""
     zd = cfg["latent_dim"]
+    dev = sd["token_type_embeddings.weight"].device
     toks, types, masks = [], [], []
     for m in cfg["active_modalities"]:
         if m == "class":
             use = class_labels is not None and not bool(torch.all(class_labels == 0))
             tk = (_ln(sd, "encoders.class.norm", sd["encoders.class.embedding.weight"][class_labels]).unsqueeze(1)
-                  if use else torch.zeros(B, 1, zd))
+                  if use else torch.zeros(B, 1, zd, device=dev))
             tid = 0
         elif m == "view":
             use = viewpoints is not None and not bool(torch.all(viewpoints == 0))
@@ -167,7 +168,7 @@ def cond_tokens(sd, cfg, B, class_labels=None, viewpoints=None, extra_cond=None,
                 h = F.gelu(_lin(sd, "encoders.view.mlp.2", h))
                 tk = _ln(sd, "encoders.view.mlp.5", _lin(sd, "encoders.view.mlp.4", h)).unsqueeze(1)
             else:
-                tk = torch.zeros(B, 1, zd)
+                tk = torch.zeros(B, 1, zd, device=dev)
             tid = 1
         elif extra_cond is not None and m in extra_cond:
             tk, use = extra_cond[m]
@@ -176,11 +177,11 @@ def cond_tokens(sd, cfg, B, class_labels=None, viewpoints=None, extra_cond=None,
             value, enc, tid = ((partial_pcd, partial_pcd_encoder, 2) if m == "partial_pcd" else (depth_maps, depth_encoder, 3))
             use = value is not None and not bool(torch.all(value == 0))
             n_tok = sd[f"encoders.{m}.token_queries"].shape[1] + 1
-            tk = enc(sd, value) if use else torch.zeros(B, n_tok, zd)
+            tk = enc(sd, value) if use else torch.zeros(B, n_tok, zd, device=dev)
         toks.append(tk)
         types += [tid] * tk.shape[1]
-        masks.append(torch.full((B, tk.shape[1], 1), 1.0 if use else 0.0))
-    te = sd["token_type_embeddings.weight"][torch.tensor(types)].unsqueeze(0).expand(B, -1, -1)
+        masks.append(torch.full((B, tk.shape[1], 1), 1.0 if use else 0.0, device=dev))
+    te = sd["token_type_embeddings.weight"][torch.tensor(types, device=dev)].unsqueeze(0).expand(B, -1, -1)
     return torch.cat(toks, dim=1) + te * torch.cat(masks, dim=1)
 
 

@@ -1,6 +1,7 @@
 """One guided evaluation (2B sequences) of the config.yaml TwoStreamDenoiser, for ncu launch lists:
-    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_twostream.csv \
-        python tools/twostream_forward.py"""
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+        --log-file gpurun_out/launches_twostream.csv python tools/twostream_forward.py
+(only the last, steady-state evaluation is inside the cudaProfilerStart/Stop range)"""
 import os
 import sys
 
@@ -23,8 +24,12 @@ for i in range(3):  # evaluation 0 also runs the condition encoders; 1 and 2 are
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = P.ops.launch_count()
+    if i == 2:
+        torch.cuda.profiler.start()
     e0.record()
     model.forward_cfg(x, 500 - i, kw, True)
     e1.record()
     torch.cuda.synchronize()
+    if i == 2:
+        torch.cuda.profiler.stop()
     print(f"evaluation {i}: {e0.elapsed_time(e1):.2f} ms, {P.ops.launch_count() - n0} launches")
