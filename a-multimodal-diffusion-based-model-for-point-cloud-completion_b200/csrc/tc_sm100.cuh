@@ -289,19 +289,21 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// gelu_fast (common.cuh) on a pair: seven packed FMA-pipe instructions, two clamps and two tanh.approx
-// for two elements instead of 2 x 10 scalar ones
+// gelu_fast (common.cuh) on a pair: six packed FMA-pipe instructions, two clamps and two tanh.approx for two
+// elements.  z = x/sqrt(2) never appears: the polynomial runs in x^2 (clamped at 2 * 3.3^2, which bounds it exactly
+// like clamping z at +-3.3) with 1/sqrt(2) and the powers of 1/2 folded into its coefficients; beyond the clamp
+// u = x * P(clamp) keeps growing and tanh saturates.
 __device__ __forceinline__ uint64_t gelu_fast2(uint64_t x2) {
-  float z0, z1;
-  unpack2(mul2(x2, pack2(0.70710678118654752440f, 0.70710678118654752440f)), z0, z1);
-  z0 = fminf(fmaxf(z0, -3.3f), 3.3f);
-  z1 = fminf(fmaxf(z1, -3.3f), 3.3f);
-  const uint64_t z = pack2(z0, z1);
-  const uint64_t zz = mul2(z, z);
-  uint64_t p = fma2(pack2(-0.00204817f, -0.00204817f), zz, pack2(0.10449843f, 0.10449843f));
-  p = fma2(p, zz, pack2(1.12819195f, 1.12819195f));
+  constexpr float kA = -0.00204817f * 0.70710678118654752440f * 0.25f;
+  constexpr float kB = 0.10449843f * 0.70710678118654752440f * 0.5f;
+  constexpr float kC = 1.12819195f * 0.70710678118654752440f;
+  float q0, q1;
+  unpack2(mul2(x2, x2), q0, q1);
+  const uint64_t xx = pack2(fminf(q0, 21.78f), fminf(q1, 21.78f));
+  uint64_t p = fma2(pack2(kA, kA), xx, pack2(kB, kB));
+  p = fma2(p, xx, pack2(kC, kC));
   float u0, u1, t0, t1;
-  unpack2(mul2(z, p), u0, u1);
+  unpack2(mul2(x2, p), u0, u1);
   asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
   const uint64_t hx = mul2(x2, pack2(0.5f, 0.5f));
