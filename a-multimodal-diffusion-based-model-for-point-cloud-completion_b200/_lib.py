@@ -44,6 +44,17 @@ class GemmArgs(C.Structure):
                 ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int)]
 
 
+class DdpmArgs(C.Structure):  # include/pcd_b200.h: pcd_ddpm_args
+    _fields_ = ([(n, vp) for n in ("x", "model_out", "noise", "t", "table", "ch_scale", "ch_bias", "x_next",
+                                   "pred_xstart", "sample_unscaled", "mean", "log_variance")]
+                + [(n, C.c_int) for n in ("batch", "channels", "n_points", "out_channels", "var_mode",
+                                          "clip_denoised", "unscale")])
+
+
+DDPM_COLS = 8
+VAR_FIXED, VAR_LEARNED_RANGE, VAR_LEARNED = 0, 1, 2
+
+
 class ModelDesc(C.Structure):
     _fields_ = ([(n, C.c_int) for n in ("precision", "width", "heads", "layers", "c_in", "c_out",
                                          "n_points", "n_prefix", "time_slot")]
@@ -91,6 +102,7 @@ _SIGS = {
                                         C.POINTER(StepScalars), C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "pcd_sampler_corrector": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.POINTER(StepScalars),
                                         C.c_int, C.c_int, C.c_int, vp]),
+    "pcd_ddpm_step": (C.c_int, [C.POINTER(DdpmArgs), vp]),
     "pcd_chamfer": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "pcd_model_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(vp)]),
     "pcd_model_destroy": (C.c_int, [vp]),

@@ -207,6 +207,84 @@ __global__ void chamfer_reduce_kernel(const float* __restrict__ d1, int n1,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Ancestral (DDPM) step: GaussianDiffusion.p_mean_variance + p_sample (reference
+// gaussian_diffusion.py:257-350, 407-449) fused into one pass.  Per sample b the step index t[b] selects a row of
+// the schedule table (PCD_DDPM_* columns, float32 copies of the reference's float64 arrays like
+// _extract_into_tensor(...).float()):
+//   x0   = clamp(a_t x - b_t eps)                          (_predict_xstart_from_eps, clip_denoised)
+//   mean = c1_t x0 + c2_t x                                (q_posterior_mean_variance)
+//   logv = fixed_t | frac max_t + (1 - frac) min_t, frac = (v + 1) / 2 | v        (fixed_* | learned_range | learned)
+//   x'   = mean + [t != 0] exp(0.5 logv) noise
+// Optional outputs: unscaled pred_xstart / sample (unscale_out_dict), mean, log-variance.
+// ---------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) ddpm_step_kernel(pcd_ddpm_args a) {
+  const int nv = a.n_points / VEC;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)a.batch * a.channels * nv;
+  if (i >= total) return;
+  const int n = (int)(i % nv) * VEC;
+  const int c = (int)((i / nv) % a.channels);
+  const int b = (int)(i / ((int64_t)nv * a.channels));
+  const int64_t xi = ((int64_t)b * a.channels + c) * a.n_points + n;
+  const int64_t oe = ((int64_t)b * a.out_channels + c) * a.n_points + n;
+  const int64_t ov = oe + (int64_t)a.channels * a.n_points;
+  const int64_t t = a.t[b];
+  const float* row = a.table + t * PCD_DDPM_COLS;
+  const float ca = row[PCD_DDPM_RECIP], cb = row[PCD_DDPM_RECIPM1], c1 = row[PCD_DDPM_MEAN_X0], c2 = row[PCD_DDPM_MEAN_XT];
+  const float min_log = row[PCD_DDPM_MIN_LOG], max_log = row[PCD_DDPM_MAX_LOG], fixed_log = row[PCD_DDPM_FIXED_LOG];
+  const float sc = a.ch_scale ? a.ch_scale[c] : 1.f, bi = a.ch_bias ? a.ch_bias[c] : 0.f;
+  float xv[4], ev[4], vv[4], nz[4], sv[4], pv[4], mv[4], lv[4];
+  load<VEC>(a.x + xi, xv);
+  load<VEC>(a.model_out + oe, ev);
+  if (a.var_mode != PCD_VAR_FIXED) load<VEC>(a.model_out + ov, vv);
+  const bool noisy = a.noise != nullptr && t != 0;
+  if (noisy) load<VEC>(a.noise + xi, nz);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    float x0 = __fsub_rn(__fmul_rn(ca, xv[j]), __fmul_rn(cb, ev[j]));
+    if (a.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv[j]));
+    float logv = fixed_log;
+    if (a.var_mode == PCD_VAR_LEARNED_RANGE) {
+      const float frac = __fmul_rn(__fadd_rn(vv[j], 1.f), 0.5f);
+      logv = __fadd_rn(__fmul_rn(frac, max_log), __fmul_rn(__fsub_rn(1.f, frac), min_log));
+    } else if (a.var_mode == PCD_VAR_LEARNED) {
+      logv = vv[j];
+    }
+    pv[j] = x0;
+    mv[j] = mean;
+    lv[j] = logv;
+    sv[j] = noisy ? __fadd_rn(mean, __fmul_rn(expf(__fmul_rn(0.5f, logv)), nz[j])) : mean;
+  }
+  if (a.x_next) store<VEC>(a.x_next + xi, sv);
+  if (a.mean) store<VEC>(a.mean + xi, mv);
+  if (a.log_variance) store<VEC>(a.log_variance + xi, lv);
+  if (a.pred_xstart) {
+    float q[4];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float u = pv[j];
+      if (a.unscale && a.ch_bias) u = __fsub_rn(u, bi);
+      if (a.unscale && a.ch_scale) u = __fdiv_rn(u, sc);
+      q[j] = u;
+    }
+    store<VEC>(a.pred_xstart + xi, q);
+  }
+  if (a.sample_unscaled) {
+    float q[4];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float u = sv[j];
+      if (a.ch_bias) u = __fsub_rn(u, bi);
+      if (a.ch_scale) u = __fdiv_rn(u, sc);
+      q[j] = u;
+    }
+    store<VEC>(a.sample_unscaled + xi, q);
+  }
+}
+
 }  // namespace pcd
 
 using namespace pcd;
@@ -265,6 +343,27 @@ extern "C" int pcd_sampler_corrector(float* x, const float* model_out, int c_out
         x, model_out, c_out, guided, d, noise, model_in, *s, batch, channels, n_points);
   }
   PCD_CHECK_LAUNCH("sampler_corrector");
+  return PCD_OK;
+}
+
+extern "C" int pcd_ddpm_step(const pcd_ddpm_args* a, void* stream) {
+  PCD_CHECK_ARG(a != nullptr, "ddpm_step: null argument block");
+  PCD_CHECK_ARG(a->batch > 0 && a->channels > 0 && a->n_points > 0, "ddpm_step: bad shape");
+  PCD_CHECK_ARG(a->x && a->model_out && a->t && a->table, "ddpm_step: x, model_out, t and table are required");
+  PCD_CHECK_ARG(a->var_mode == PCD_VAR_FIXED || a->var_mode == PCD_VAR_LEARNED_RANGE || a->var_mode == PCD_VAR_LEARNED,
+                "ddpm_step: unknown variance mode %d", a->var_mode);
+  PCD_CHECK_ARG(a->out_channels >= (a->var_mode == PCD_VAR_FIXED ? 1 : 2) * a->channels,
+                "ddpm_step: model output has %d channels, need %d", a->out_channels,
+                (a->var_mode == PCD_VAR_FIXED ? 1 : 2) * a->channels);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->n_points % 4 == 0) {
+    int64_t tot = (int64_t)a->batch * a->channels * (a->n_points / 4);
+    ddpm_step_kernel<4><<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(*a);
+  } else {
+    int64_t tot = (int64_t)a->batch * a->channels * a->n_points;
+    ddpm_step_kernel<1><<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(*a);
+  }
+  PCD_CHECK_LAUNCH("ddpm_step");
   return PCD_OK;
 }
 

@@ -1,15 +1,19 @@
-"""Host-side Gaussian diffusion tables (float64, numpy) for the Karras sampling path.
+"""Host-side Gaussian diffusion tables (float64, numpy) for the Karras sampling path, and the ancestral
+(DDPM) sampling loop on the fused ``pcd_ddpm_step`` kernel.
 
-Mirrors the pieces of the reference's ``GaussianDiffusion`` that the sampler touches
-(diffusion/gaussian_diffusion.py:26-72 schedules, :144-196 tables, :938-965 channel
-scaling).  Training losses, DDIM and the ancestral p_sample loop are out of scope
-(SURVEY.md 8a row a8).
+Mirrors the pieces of the reference's ``GaussianDiffusion`` that sampling touches
+(diffusion/gaussian_diffusion.py:26-72 schedules, :144-196 tables, :257-350 p_mean_variance, :407-548
+p_sample / p_sample_loop / p_sample_loop_progressive, :938-965 channel scaling).  Training losses and DDIM are
+out of scope.
 """
+import ctypes as C
 import math
-from typing import Any, Dict, Optional, Sequence, Union
+from typing import Any, Callable, Dict, Optional, Sequence, Union
 
 import numpy as np
 import torch as th
+
+from . import _lib
 
 
 def get_beta_schedule(beta_schedule, *, beta_start, beta_end, num_diffusion_timesteps):
@@ -65,6 +69,13 @@ class GaussianDiffusion:
         self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
         self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
         self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        # posterior q(x_{t-1} | x_t, x_0) (gaussian_diffusion.py:183-196); its variance is 0 at t = 0, hence the clip
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = (np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+                                               if len(betas) > 1 else np.zeros(1))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        self._ddpm_tables: Dict[Any, th.Tensor] = {}
 
     @property
     def eps_channels_doubled(self) -> bool:
@@ -92,3 +103,125 @@ class GaussianDiffusion:
     def unscale_out_dict(self, out: Dict[str, Union[th.Tensor, Any]]) -> Dict[str, Union[th.Tensor, Any]]:
         return {k: (self.unscale_channels(v) if isinstance(v, th.Tensor) and v.dim() >= 2 else v)
                 for k, v in out.items()}
+
+    # ------------------------------------------------------------------------------------------------
+    # Ancestral (DDPM) sampling: p_mean_variance / p_sample / p_sample_loop(_progressive)
+    # (gaussian_diffusion.py:257-350, 407-548) on the fused pcd_ddpm_step kernel.
+    # ------------------------------------------------------------------------------------------------
+    def _var_mode(self) -> int:
+        modes = {"fixed_small": _lib.VAR_FIXED, "fixed_large": _lib.VAR_FIXED, "learned_range": _lib.VAR_LEARNED_RANGE,
+                 "learned": _lib.VAR_LEARNED}
+        if self.model_var_type not in modes:
+            raise KeyError(self.model_var_type)
+        return modes[self.model_var_type]
+
+    def _ddpm_table(self, device) -> th.Tensor:
+        """[T, 8] float32 schedule rows for pcd_ddpm_step (columns PCD_DDPM_*, include/pcd_b200.h)."""
+        key = str(device)
+        if key not in self._ddpm_tables:
+            if self.model_var_type == "fixed_large":  # gaussian_diffusion.py:305-311
+                fixed = np.log(np.append(self.posterior_variance[1], self.betas[1:]))
+            else:
+                fixed = self.posterior_log_variance_clipped
+            tab = np.zeros((self.num_timesteps, _lib.DDPM_COLS), dtype=np.float64)
+            for col, arr in enumerate((self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod,
+                                       self.posterior_mean_coef1, self.posterior_mean_coef2,
+                                       self.posterior_log_variance_clipped, np.log(self.betas), fixed)):
+                tab[:, col] = arr
+            self._ddpm_tables[key] = th.from_numpy(tab).float().to(device).contiguous()
+        return self._ddpm_tables[key]
+
+    def _ddpm_step(self, model, x, t, clip_denoised, model_kwargs, noise, outputs):
+        """One fused p_mean_variance (+ p_sample when ``noise`` is given).  ``outputs``: names of the optional result
+        tensors to materialise among x_next / pred_xstart / sample_unscaled / mean / log_variance."""
+        _lib.require_cuda(x)
+        B, Cc = x.shape[:2]
+        assert t.shape == (B,)
+        assert x.dtype == th.float32, "the sampler state is fp32"
+        out = model(x, t, **(model_kwargs or {}))
+        extra = None
+        if isinstance(out, tuple):
+            out, extra = out
+        mode = self._var_mode()
+        need = Cc * (1 if mode == _lib.VAR_FIXED else 2)
+        assert out.shape[0] == B and out.shape[1] == need and out.shape[2:] == x.shape[2:], \
+            f"model output {tuple(out.shape)} does not match state {tuple(x.shape)} for model_var_type={self.model_var_type}"
+        x = x.contiguous()
+        out = out.float().contiguous()
+        n_points = int(np.prod(x.shape[2:]))
+        res = {k: th.empty_like(x) for k in outputs}
+        a = _lib.DdpmArgs()
+        a.x, a.model_out, a.noise = _lib.ptr(x), _lib.ptr(out), _lib.ptr(noise.contiguous() if noise is not None else None)
+        tt = t.to(device=x.device, dtype=th.int64).contiguous()
+        if bool(((tt < 0) | (tt >= self.num_timesteps)).any()):
+            raise IndexError("timestep out of range")
+        a.t, a.table = _lib.ptr(tt), _lib.ptr(self._ddpm_table(x.device))
+        f32 = dict(device=x.device, dtype=th.float32)
+        sc = None if self.channel_scales is None else th.tensor(self.channel_scales, **f32)
+        bi = None if self.channel_biases is None else th.tensor(self.channel_biases, **f32)
+        a.ch_scale, a.ch_bias = _lib.ptr(sc), _lib.ptr(bi)
+        for k in ("x_next", "pred_xstart", "sample_unscaled", "mean", "log_variance"):
+            setattr(a, k, _lib.ptr(res.get(k)))
+        a.batch, a.channels, a.n_points, a.out_channels = B, Cc, n_points, out.shape[1]
+        a.var_mode, a.clip_denoised, a.unscale = mode, int(bool(clip_denoised)), int("sample_unscaled" in outputs)
+        _lib.check(_lib.load().pcd_ddpm_step(C.byref(a), _lib.stream_ptr()), "ddpm_step")
+        res["extra"] = extra
+        return res
+
+    def p_mean_variance(self, model, x, t, clip_denoised=False, denoised_fn=None, model_kwargs=None):
+        """Same contract as the reference (:257-350): dict with mean / variance / log_variance / pred_xstart / extra."""
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not used by any caller of the reference's sampling path")
+        r = self._ddpm_step(model, x, t, clip_denoised, model_kwargs, None, ("mean", "log_variance", "pred_xstart"))
+        if self._var_mode() == _lib.VAR_FIXED:
+            # table lookup like the reference (:305-318): at t = 0 of fixed_small this is 0, not exp(clipped log)
+            tab = (np.append(self.posterior_variance[1], self.betas[1:]) if self.model_var_type == "fixed_large"
+                   else self.posterior_variance)
+            row = th.from_numpy(tab).float().to(x.device)[t.to(x.device).long()]
+            variance = row.view(-1, *([1] * (x.dim() - 1))).expand_as(x).contiguous()
+        else:
+            variance = th.exp(r["log_variance"])
+        return {"mean": r["mean"], "variance": variance, "log_variance": r["log_variance"],
+                "pred_xstart": r["pred_xstart"], "extra": r["extra"]}
+
+    def p_sample(self, model, x, t, clip_denoised=False, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                 noise: Optional[th.Tensor] = None):
+        """x_{t-1} ~ p(. | x_t) (:407-449).  ``noise`` optionally replaces the torch draw (tests)."""
+        if denoised_fn is not None or cond_fn is not None:
+            raise NotImplementedError("denoised_fn / cond_fn are not used by any caller of the reference's sampling path")
+        if noise is None:
+            noise = th.randn_like(x)
+        r = self._ddpm_step(model, x, t, clip_denoised, model_kwargs, noise.to(x), ("x_next", "pred_xstart"))
+        return {"sample": r["x_next"], "pred_xstart": r["pred_xstart"]}
+
+    def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=False, denoised_fn=None, cond_fn=None,
+                                  model_kwargs=None, device=None, progress=False, temp=1.0,
+                                  noise_fn: Optional[Callable] = None):
+        """Generator over the T ancestral steps (:499-548); every yield is the *unscaled* {"sample", "pred_xstart"}
+        dict like the reference's ``unscale_out_dict(out)``.  ``noise_fn(shape)`` optionally replaces the torch draws
+        (x_T first, then one per step, the reference's order)."""
+        if denoised_fn is not None or cond_fn is not None:
+            raise NotImplementedError("denoised_fn / cond_fn are not used by any caller of the reference's sampling path")
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        draw = noise_fn if noise_fn is not None else (lambda shp: th.randn(*shp, device=device))
+        img = noise if noise is not None else draw(tuple(shape)).to(device) * temp
+        img = img.to(device=device, dtype=th.float32).contiguous()
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        with th.no_grad():
+            for i in indices:
+                t = th.full((shape[0],), i, device=device, dtype=th.int64)
+                r = self._ddpm_step(model, img, t, clip_denoised, model_kwargs, draw(tuple(shape)).to(img),
+                                    ("x_next", "pred_xstart", "sample_unscaled"))
+                yield {"sample": r["sample_unscaled"], "pred_xstart": r["pred_xstart"]}
+                img = r["x_next"]
+
+    def p_sample_loop(self, model, shape, **kwargs):
+        final = None
+        for sample in self.p_sample_loop_progressive(model, shape, **kwargs):
+            final = sample
+        return final["sample"]

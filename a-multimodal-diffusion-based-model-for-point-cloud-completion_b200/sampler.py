@@ -216,13 +216,20 @@ class PointCloudSampler:
                     if k not in ["prev_latent"]:
                         stage_model_kwargs[k] = torch.cat([v, torch.zeros_like(v)], dim=0)
 
-            if not stage_use_karras:
-                raise NotImplementedError(
-                    "use_karras=False (ancestral DDPM loop) is outside the accelerated path; the "
-                    "reference's own branch for it is dead code (SURVEY.md appendix B)")
-
             low_res = stage_model_kwargs.get("low_res")
-            if self.use_cuda_graph and getattr(model, "pcd_native", False):
+            if not stage_use_karras:
+                # ancestral DDPM loop over all diffusion steps (reference sampler.py:153-165).  With a guidance scale the
+                # reference wraps the model in _uncond_guide_model, whose (x_t, ts, model_kwargs) signature does not
+                # match how p_mean_variance calls models (**model_kwargs): that call raises TypeError there, so there
+                # is no behaviour to reproduce.
+                if stage_guidance_scale:
+                    raise NotImplementedError(
+                        "use_karras=False with a guidance scale: the reference's own branch fails with a TypeError "
+                        "(diffusion/sampler.py:194-233 vs gaussian_diffusion.py:285); use guidance_scale=0 or use_karras=True")
+                outs = (o["pred_xstart"] for o in diffusion.p_sample_loop_progressive(
+                    model, shape=sample_shape, model_kwargs=stage_model_kwargs, device=self.device,
+                    clip_denoised=self.clip_denoised, noise_fn=self.noise_fn))
+            elif self.use_cuda_graph and getattr(model, "pcd_native", False):
                 stage = self._graphed_stage(idx, model, diffusion, sample_shape, stage_karras_steps,
                                             stage_sigma_min, stage_sigma_max, stage_s_churn,
                                             stage_guidance_scale)

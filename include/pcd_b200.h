@@ -258,6 +258,43 @@ PCD_API int pcd_sampler_corrector(float* x, const float* model_out, int c_out, i
                           const pcd_step_scalars* s, int batch, int channels, int n_points,
                           void* stream);
 
+/* Ancestral (DDPM) sampling step: GaussianDiffusion.p_mean_variance + p_sample
+ * (reference diffusion/gaussian_diffusion.py:257-350, 407-449; the loop of p_sample_loop_progressive, :499-548, calls
+ * it once per step) fused into one pass over the state.  `table` is [num_timesteps, PCD_DDPM_COLS] float32 (float64
+ * schedule arrays rounded like _extract_into_tensor(...).float()), `t` the per-sample int64 step indices [batch].
+ * model_out is [batch, out_channels, n_points]: channels [0, C) epsilon, [C, 2C) the variance channel of
+ * learned / learned_range models.  x is read, x_next written (may alias x); every other output pointer may be NULL.
+ * noise == NULL gives the mean (p_mean_variance only). */
+enum { PCD_DDPM_RECIP = 0,    /* sqrt(1 / alphas_cumprod)          gaussian_diffusion.py:180 */
+       PCD_DDPM_RECIPM1 = 1,  /* sqrt(1 / alphas_cumprod - 1)      :181 */
+       PCD_DDPM_MEAN_X0 = 2,  /* posterior_mean_coef1              :191-193 */
+       PCD_DDPM_MEAN_XT = 3,  /* posterior_mean_coef2              :194-196 */
+       PCD_DDPM_MIN_LOG = 4,  /* posterior_log_variance_clipped    :188-190 */
+       PCD_DDPM_MAX_LOG = 5,  /* log(betas)                        :299 */
+       PCD_DDPM_FIXED_LOG = 6,/* log-variance of fixed_small / fixed_large models  :305-318 */
+       PCD_DDPM_COLS = 8 };
+enum { PCD_VAR_FIXED = 0, PCD_VAR_LEARNED_RANGE = 1, PCD_VAR_LEARNED = 2 };
+typedef struct pcd_ddpm_args {
+  const float* x;           /* [batch, channels, n_points] state x_t */
+  const float* model_out;   /* [batch, out_channels, n_points] */
+  const float* noise;       /* [batch, channels, n_points] or NULL */
+  const int64_t* t;         /* [batch] */
+  const float* table;       /* [num_timesteps, PCD_DDPM_COLS] */
+  const float* ch_scale;    /* [channels] or NULL (GaussianDiffusion.channel_scales) */
+  const float* ch_bias;     /* [channels] or NULL */
+  float* x_next;            /* sample x_{t-1} (scaled units) */
+  float* pred_xstart;       /* x0 prediction; unscaled when `unscale` != 0 */
+  float* sample_unscaled;   /* unscale_channels(x_next) */
+  float* mean;              /* posterior mean */
+  float* log_variance;
+  int batch, channels, n_points, out_channels;
+  int var_mode;             /* PCD_VAR_* */
+  int clip_denoised;
+  int unscale;
+} pcd_ddpm_args;
+PCD_API int pcd_ddpm_step(const pcd_ddpm_args* args, void* stream);
+
+
 /* Squared-L2 Chamfer distance on xyz (models/util.py:265-295): p1 [B,C1,N1],
  * p2 [B,C2,N2] -> out [B].  Tiled nearest-neighbour search, no [B,N1,N2] matrix. */
 PCD_API int pcd_chamfer(const float* p1, int c1, int n1, const float* p2, int c2, int n2,

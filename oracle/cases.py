@@ -165,3 +165,26 @@ SOLVER_CASES = {
     "heun_karras": dict(model="small_uncond_c6", diffusion="karras", sampler="heun", steps=12, s_churn=3.0,
                         sigma_max=80.0, B=2, noise_seed=9103),
 }
+
+
+# ancestral (DDPM) sampling, reference gaussian_diffusion.py:257-350,407-548: name -> model case, schedule,
+# number of diffusion steps, variance type, whether the diffusion carries the point-e channel scaling, and how the
+# reference is driven ("sampler": PointCloudSampler(use_karras=[False], guidance_scale=[0]), sampler.py:153-165;
+# "loop": GaussianDiffusion.p_sample_loop_progressive directly)
+DDPM_CASES = {
+    "learned_range_cosine": dict(model="small_imagevec", schedule="cosine", timesteps=40, var_type="learned_range",
+                                 scaled=True, via="sampler", B=2, noise_seed=9201),
+    "fixed_small_linear": dict(model="small_uncond_c6", schedule="linear", timesteps=24, var_type="fixed_small",
+                               scaled=False, via="loop", B=2, noise_seed=9202),
+    "fixed_large_cosine": dict(model="small_uncond_c6", schedule="cosine", timesteps=16, var_type="fixed_large",
+                               scaled=True, via="loop", B=3, noise_seed=9203),
+}
+
+
+def ddpm_kwargs(case):
+    dc = DDPM_CASES[case]
+    cfg, _, seed, _ = FORWARD_CASES[dc["model"]]
+    if cfg["name"] == "CLIPImagePointDiffusionTransformer":
+        e = det.normal((dc["B"], 768), seed * 10 + 7)
+        return dict(embeddings=e / e.norm(dim=1, keepdim=True))
+    return {}

@@ -212,6 +212,40 @@ def gen_solver(m, case):
     save("solver_" + case, x=xs, pred=preds)
 
 
+def gen_ddpm(m, case):
+    """Ancestral sampling over every diffusion step through the unmodified reference."""
+    print("ddpm", case)
+    dc = cases.DDPM_CASES[case]
+    model, cfg, _ = build_reference_model(m, dc["model"])
+    gd = m.gaussian_diffusion
+    scales = dict(channel_scales=np.array(cases._SCALES), channel_biases=np.array(cases._BIASES)) if dc["scaled"] else {}
+    diffusion = gd.GaussianDiffusion(betas=gd.get_named_beta_schedule(dc["schedule"], dc["timesteps"]),
+                                     model_mean_type="epsilon", model_var_type=dc["var_type"], loss_type="mse", **scales)
+    C, N, B = cfg["input_channels"], cfg["n_ctx"], dc["B"]
+    kw = cases.ddpm_kwargs(case)
+    with patched_noise(cases.DetNoise(dc["noise_seed"])), torch.no_grad():
+        if dc["via"] == "sampler":
+            sampler = m.sampler.PointCloudSampler(
+                device=torch.device("cpu"), models=[model], diffusions=[diffusion], num_points=[N],
+                aux_channels=["R", "G", "B"][: C - 3], guidance_scale=[0.0], use_karras=[False], karras_steps=[64],
+                sigma_min=[1e-3], sigma_max=[120.0], s_churn=[0.0])
+            preds = torch.stack([y.clone() for y in sampler.sample_batch_progressive(B, kw)])
+            arrays = dict(pred=preds)
+        else:
+            outs = list(diffusion.p_sample_loop_progressive(model, (B, C, N), clip_denoised=True, model_kwargs=kw,
+                                                            device=torch.device("cpu")))
+            arrays = dict(pred=torch.stack([o["pred_xstart"] for o in outs]),
+                          sample=torch.stack([o["sample"] for o in outs]))
+            # one p_mean_variance call (scaled units, no clipping) at a mixed batch of step indices
+            x = det.normal((B, C, N), dc["noise_seed"] + 5)
+            t = torch.tensor([(dc["timesteps"] - 1, 0, dc["timesteps"] // 2)[i % 3] for i in range(B)])
+            pmv = diffusion.p_mean_variance(model, x, t, clip_denoised=False, model_kwargs=kw)
+            arrays.update(pmv_mean=pmv["mean"], pmv_log_variance=pmv["log_variance"].expand_as(x).clone(),
+                          pmv_variance=pmv["variance"].expand_as(x).clone(), pmv_pred=pmv["pred_xstart"])
+    print("  ", {k: tuple(v.shape) for k, v in arrays.items()}, float(arrays["pred"].std()))
+    save("ddpm_" + case, **arrays)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also run the full-size (slow) cases")
@@ -233,6 +267,8 @@ def main():
     todo.append(("sampler_two_stage", lambda: gen_two_stage(m)))
     for c in cases.SOLVER_CASES:
         todo.append(("solver_" + c, lambda c=c: gen_solver(m, c)))
+    for c in cases.DDPM_CASES:
+        todo.append(("ddpm_" + c, lambda c=c: gen_ddpm(m, c)))
     for name, fn in todo:
         if args.only and args.only != name:
             continue

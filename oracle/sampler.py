@@ -40,6 +40,12 @@ class Tables:
         self.alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
         self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
         self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        # posterior q(x_{t-1} | x_t, x_0), reference gaussian_diffusion.py:183-196
+        prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.posterior_variance = betas * (1.0 - prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - prev) * np.sqrt(1.0 - betas) / (1.0 - self.alphas_cumprod)
         self.channel_scales = None if channel_scales is None else np.array(channel_scales)
         self.channel_biases = None if channel_biases is None else np.array(channel_biases)
         assert mean_type == "epsilon"
@@ -333,3 +339,56 @@ def karras_progressive(model_fn, diffusion, shape, steps, sampler="heun", sigma_
                 d_2 = to_d(x_2, sigmas[i + 1], den_2)
                 x = x + (d + d_2) / 2 * dt
     yield {"x": fin(x), "pred_xstart": fin(den)}
+
+
+# ---------------------------------------------------------------------------
+# Ancestral (DDPM) sampling of reference gaussian_diffusion.py (row f4 of SURVEY 8)
+# ---------------------------------------------------------------------------
+def p_mean_variance(tables: Tables, model_out: torch.Tensor, x: torch.Tensor, t: torch.Tensor, var_type: str,
+                    clip_denoised: bool):
+    """reference gaussian_diffusion.py:257-350 for epsilon-prediction models, given the model output."""
+    ex = lambda arr: torch.from_numpy(arr)[t.cpu()].float().to(x.device)[(...,) + (None,) * (x.dim() - 1)]
+    C = x.shape[1]
+    if var_type in ("learned", "learned_range"):
+        eps, v = model_out[:, :C], model_out[:, C:2 * C]
+        if var_type == "learned":
+            log_var = v
+        else:
+            frac = (v + 1) / 2
+            log_var = frac * ex(np.log(tables.betas)) + (1 - frac) * ex(tables.posterior_log_variance_clipped)
+        var = torch.exp(log_var)
+    else:
+        eps = model_out
+        # fixed variances come straight from the tables (:305-318): "variance" is NOT exp(log_variance) at t = 0 of
+        # fixed_small (posterior variance 0, log clipped to the t = 1 value)
+        if var_type == "fixed_large":
+            v_tab = np.append(tables.posterior_variance[1], tables.betas[1:])
+            var, log_var = ex(v_tab).expand_as(x), ex(np.log(v_tab)).expand_as(x)
+        else:
+            var = ex(tables.posterior_variance).expand_as(x)
+            log_var = ex(tables.posterior_log_variance_clipped).expand_as(x)
+    x0 = ex(tables.sqrt_recip_alphas_cumprod) * x - ex(tables.sqrt_recipm1_alphas_cumprod) * eps
+    if clip_denoised:
+        x0 = x0.clamp(-1, 1)
+    mean = ex(tables.posterior_mean_coef1) * x0 + ex(tables.posterior_mean_coef2) * x
+    return dict(mean=mean, log_variance=log_var, variance=var, pred_xstart=x0)
+
+
+def ddpm_progressive(model_fn, tables: Tables, shape, var_type: str, clip_denoised: bool = True, model_kwargs=None,
+                     noise_fn: Optional[Callable] = None):
+    """reference gaussian_diffusion.py:407-449 (p_sample) inside :499-548 (p_sample_loop_progressive): x_T ~ N(0, I);
+    for t = T-1 .. 0: x <- mean + [t != 0] exp(log_var / 2) noise.  Yields the unscaled dicts like the reference."""
+    model_kwargs = model_kwargs or {}
+    if noise_fn is None:
+        noise_fn = lambda shp: torch.randn(*shp)
+    x = noise_fn(tuple(shape))
+    for i in reversed(range(tables.num_timesteps)):
+        t = torch.full((shape[0],), i, dtype=torch.long)
+        out = model_fn(x, t, **model_kwargs)
+        if isinstance(out, tuple):
+            out = out[0]
+        r = p_mean_variance(tables, out, x, t, var_type, clip_denoised)
+        noise = noise_fn(tuple(shape))
+        sample = r["mean"] + (0.0 if i == 0 else 1.0) * torch.exp(0.5 * r["log_variance"]) * noise
+        yield {"sample": tables.unscale(sample), "pred_xstart": tables.unscale(r["pred_xstart"])}
+        x = sample

@@ -175,3 +175,35 @@ def test_solvers(case):
     assert xs.shape == g["x"].shape
     assert rel_l2(xs[:2], g["x"][:2]) < 1e-5 and rel_l2(preds[:2], g["pred"][:2]) < 1e-5
     assert rel_l2(preds, g["pred"]) < 1e-3
+
+
+def ddpm_tables(dc):
+    scales = dict(channel_scales=cases._SCALES, channel_biases=cases._BIASES) if dc["scaled"] else {}
+    return S.Tables(schedule=dc["schedule"], timesteps=dc["timesteps"], **scales)
+
+
+@pytest.mark.parametrize("case", list(cases.DDPM_CASES))
+def test_ddpm_ancestral_loop(case):
+    """p_mean_variance / p_sample / p_sample_loop_progressive (gaussian_diffusion.py:257-350,407-548): the oracle's
+    loop against the reference's, driven through PointCloudSampler(use_karras=[False]) or directly."""
+    g = load_golden("ddpm_" + case)
+    dc = cases.DDPM_CASES[case]
+    sd, cfg = case_weights(dc["model"])
+    tab = ddpm_tables(dc)
+    shape = (dc["B"], cfg["input_channels"], cfg["n_ctx"])
+    fn = S.make_model_fn(sd, cfg)
+    kw = cases.ddpm_kwargs(case)
+    with torch.no_grad():
+        outs = list(S.ddpm_progressive(fn, tab, shape, dc["var_type"], True, kw, cases.DetNoise(dc["noise_seed"])))
+    preds = torch.stack([o["pred_xstart"] for o in outs])
+    assert preds.shape == g["pred"].shape
+    assert rel_l2(preds[:2], g["pred"][:2]) < 1e-5 and rel_l2(preds, g["pred"]) < 1e-3
+    if "sample" in g:
+        assert rel_l2(torch.stack([o["sample"] for o in outs]), g["sample"]) < 1e-3
+        x = det.normal(shape, dc["noise_seed"] + 5)
+        t = torch.tensor([(dc["timesteps"] - 1, 0, dc["timesteps"] // 2)[i % 3] for i in range(dc["B"])])
+        with torch.no_grad():
+            r = S.p_mean_variance(tab, fn(x, t, **kw), x, t, dc["var_type"], False)
+        for k in ("mean", "log_variance", "variance"):
+            assert rel_l2(r[k], g["pmv_" + k]) < 1e-5, k
+        assert rel_l2(r["pred_xstart"], g["pmv_pred"]) < 1e-5

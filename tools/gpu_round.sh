@@ -21,6 +21,7 @@ run pointcloud 300 $PYT tests/test_gpu_point_cloud.py
 run forward    900 $PYT tests/test_gpu_forward.py
 run sampler    900 $PYT tests/test_gpu_sampler.py -s
 run twostream  400 $PYT tests/test_gpu_twostream.py
+run ddpm       300 $PYT tests/test_gpu_ddpm.py
 run smoke      600 python __graft_entry__.py --smoke
 TAILN=3 run bench 900 python bench.py --steps 2 --warmup 3
 grep -h '^{' $OUT/bench.log | tail -1 > $OUT/bench.json
