@@ -282,7 +282,8 @@ class TwoStreamDenoiser(nn.Module):
     def _padded(self, tag: str, owner, mats, biases, cols: bool = False):
         """bf16 weight (+ fp32 bias) with every 32-row (or, cols=True, 32-column) head group zero-padded to 64; several
         matrices are stacked on the output axis (one fused projection).  Cached per parameter versions."""
-        key = tuple(m._version for m in mats) + tuple(m.data_ptr() for m in mats)
+        key = (tuple(m._version for m in mats) + tuple(m.data_ptr() for m in mats)
+               + tuple(-1 if x is None else x._version for x in biases))
         hit = self._bf16.get((tag, id(owner)))
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
