@@ -125,3 +125,68 @@ def test_twostream_in_the_sampler_with_latent_self_conditioning(mode):
         noise.__init__(777)
         again = torch.stack([y.clone() for y in sampler.sample_batch_progressive(B, kw)])
         assert torch.equal(again, got)
+
+
+class _Traced(_Opaque):
+    """Public-forward wrapper that records chosen evaluations (inputs incl. prev_latent, outputs)."""
+    def __init__(self, inner, keep):
+        super().__init__(inner)
+        self.keep, self.count, self.trace = set(keep), 0, []
+
+    def forward(self, x, t, **kw):
+        y, z = self.inner(x, t, **kw)
+        if self.count in self.keep:
+            self.trace.append((x.clone(), t.clone(), {k: (v.clone() if torch.is_tensor(v) else v) for k, v in kw.items()},
+                               y.clone(), z.clone()))
+        self.count += 1
+        return y, z
+
+
+def test_twostream_run_py_flow_at_config_shapes():
+    """The reference's run.py:114-161 at its config.yaml shapes (all four modalities, 1024 points, 64 Heun steps,
+    guidance 3).  (1) fp32 parity mode driven through the public forward the way the reference's guided_denoiser
+    drives it gives the trajectory; (2) on that trajectory's own inputs (state, step, prev_latent of either branch) the
+    tensor-core mode stays within the north-star per-step tolerance; (3) tensor-core mode under one CUDA graph equals its
+    eager batched execution.  Final clouds of (1) and (3) are not compared: a randomly initialised model with latent
+    feedback is chaotic over 254 evaluations (bf16 rounding flips clamped coordinates)."""
+    from oracle import cases
+    cfgm = dict(num_points=1024, num_latents=256, input_channels=3, output_channels=3, latent_dim=256, x_dim=256,
+                num_blocks=6, num_compute_layers=4, num_heads=8, num_classes=10, num_tokens_ppcd=256,
+                num_tokens_depth=128, active_modalities=["class", "view", "partial_pcd", "depth"])
+    B = 2
+    torch.manual_seed(4242)
+    ref = P.TwoStreamDenoiser(**cfgm, device=DEV, dtype=torch.float32)
+    with torch.no_grad():
+        ref.denoiser_backbone.ln_latent.weight.fill_(1.0)  # zero-initialised in the reference: would hide prev_latent
+    fast = P.TwoStreamDenoiser(**cfgm, device=DEV, dtype=torch.bfloat16)
+    fast.load_state_dict(ref.state_dict())
+    diffusion = P.GaussianDiffusion(betas=P.get_named_beta_schedule("linear", 1000), model_mean_type="epsilon",
+                                    model_var_type="fixed_small", loss_type="mse")
+    g = torch.Generator().manual_seed(7)
+    kw = dict(class_labels=torch.randint(1, 10, (B,), generator=g), viewpoints=torch.rand(B, 3, generator=g),
+              partial_pcd=torch.rand(B, 1024, 3, generator=g) - 0.5, depth_maps=torch.rand(B, 1, 512, 512, generator=g))
+    kw = {k: v.to(DEV) for k, v in kw.items()}
+
+    def run(model, graph):
+        noise = cases.DetNoise(991)
+        sampler = P.PointCloudSampler(DEV, [model], [diffusion], [1024], [], guidance_scale=[3.0], clip_denoised=True,
+                                      use_karras=[True], karras_steps=[64], sigma_min=[1e-3], sigma_max=[120], s_churn=[0.0],
+                                      noise_fn=lambda shp: noise(shp).to(DEV), use_cuda_graph=graph)
+        ys = [y.clone() for y in sampler.sample_batch_progressive(B, kw, x_target=None)]
+        assert len(ys) == 65 and ys[-1].shape == (B, 3, 1024)
+        clouds = sampler.output_to_point_clouds(ys[-1])
+        assert len(clouds) == B and clouds[0].coords.shape == (1024, 3)
+        return torch.stack(ys)
+
+    traced = _Traced(ref, keep=[0, 1, 2, 3, 100, 101, 252, 253])  # even: conditional branch, odd: unconditional
+    y32 = run(traced, False)
+    assert traced.count == 254 and torch.isfinite(y32).all()
+    for x, t, k, y, z in traced.trace:
+        yb, zb = fast(x, t, **k)
+        assert rel(yb, y) < TOL_BF16, describe(yb, y, f"denoiser output at t={int(t[0])}")
+        assert rel(zb, z) < TOL_BF16, describe(zb, z, f"latent at t={int(t[0])}")
+    yg = run(fast, True)
+    ye = run(fast, False)
+    assert torch.equal(yg, ye), describe(yg, ye, "graph vs eager")
+    print("bf16 vs fp32 trajectories: first yield rel", rel(yg[0], y32[0]), "final Chamfer",
+          P.ops.chamfer_distance_xyz(yg[-1], y32[-1]).tolist())
