@@ -16,7 +16,7 @@ def ref(nb=2):
     w = torch.einsum("bthc,bshc->bhts", q, k) / 8.0
     return torch.einsum("bhts,bshc->bthc", torch.softmax(w, -1), v).reshape(nb, L, -1)
 want = ref()
-def t(fn, it=10):
+def t(fn, it=int(os.environ.get('ATTN_IT', '10'))):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
