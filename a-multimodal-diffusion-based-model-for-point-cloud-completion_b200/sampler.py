@@ -11,6 +11,7 @@ Same constructor, attributes and methods as the reference's
   finishes.  Noise is drawn by torch in the reference's order before the replay, so a
   fixed seed gives the same trajectory as the eager mode.
 """
+import dataclasses
 from typing import Any, Callable, Dict, Iterator, List, Optional, Sequence, Tuple
 
 import torch
@@ -84,256 +85,196 @@ class _GraphedStage:
         return self.preds
 
 
+# Per-stage options of the sampler, in constructor order, with the value a stage after the first gets when the
+# caller passed a single entry (reference diffusion/sampler.py:45-62: everything repeats, except that upsampler
+# stages are not guided unless asked).
+_STAGE_OPTIONS = ("model_kwargs_key_filter", "guidance_scale", "use_karras", "karras_steps", "sigma_min", "sigma_max",
+                  "s_churn")
+_COLOUR_CHANNELS = frozenset("RGBA")
+
+
+@dataclasses.dataclass
+class _Stage:
+    index: int
+    model: Any
+    diffusion: Any
+    num_points: int
+    key_filter: str
+    guidance: float
+    karras: bool
+    steps: int
+    sigma_min: float
+    sigma_max: float
+    churn: float
+
+    @property
+    def guided(self) -> bool:
+        return self.guidance not in (0, 1)
+
+
 class PointCloudSampler:
-    """
-    A wrapper around a model or stack of models that produces conditional or
-    unconditional sample tensors (reference diffusion/sampler.py:16-41).
-    """
+    """Runs a cascade of point-cloud diffusion models (e.g. base 1024 points -> upsampler 4096) and yields the clouds.
 
-    def __init__(
-        self,
-        device: torch.device,
-        models: Sequence[nn.Module],
-        diffusions: Sequence[GaussianDiffusion],
-        num_points: Sequence[int],
-        aux_channels: Sequence[str],
-        model_kwargs_key_filter: Sequence[str] = ("*",),
-        guidance_scale: Sequence[float] = (3.0, 3.0),
-        clip_denoised: bool = True,
-        use_karras: Sequence[bool] = (True, True),
-        karras_steps: Sequence[int] = (64, 64),
-        sigma_min: Sequence[float] = (1e-3, 1e-3),
-        sigma_max: Sequence[float] = (120, 160),
-        s_churn: Sequence[float] = (3, 0),
-        use_cuda_graph: bool = False,
-        noise_fn: Optional[Callable] = None,
-    ):
-        n = len(models)
-        assert n > 0
+    Drop-in for the reference's ``diffusion/sampler.py`` ``PointCloudSampler`` (:16-291): same constructor keywords and
+    defaults, the same public attributes (``models``, ``diffusions``, ``num_points``, ``guidance_scale``, ...) and methods
+    (``sample_batch``, ``sample_batch_progressive``, ``combine``, ``with_options``, ``split_model_output``,
+    ``output_to_point_clouds``, ``num_stages``).  Extras: ``use_cuda_graph`` and ``noise_fn`` (deterministic draws)."""
 
-        if n > 1:
-            if len(guidance_scale) == 1:
-                # Don't guide the upsamplers by default.
-                guidance_scale = list(guidance_scale) + [1.0] * (n - 1)
-            if len(use_karras) == 1:
-                use_karras = use_karras * n
-            if len(karras_steps) == 1:
-                karras_steps = karras_steps * n
-            if len(sigma_min) == 1:
-                sigma_min = sigma_min * n
-            if len(sigma_max) == 1:
-                sigma_max = sigma_max * n
-            if len(s_churn) == 1:
-                s_churn = s_churn * n
-            if len(model_kwargs_key_filter) == 1:
-                model_kwargs_key_filter = model_kwargs_key_filter * n
-        if len(model_kwargs_key_filter) == 0:
-            model_kwargs_key_filter = ["*"] * n
-        assert len(guidance_scale) == n
-        assert len(use_karras) == n
-        assert len(karras_steps) == n
-        assert len(sigma_min) == n
-        assert len(sigma_max) == n
-        assert len(s_churn) == n
-        assert len(model_kwargs_key_filter) == n
-
-        self.device = device
-        self.num_points = num_points
-        self.aux_channels = aux_channels
-        self.model_kwargs_key_filter = model_kwargs_key_filter
-        self.guidance_scale = guidance_scale
-        self.clip_denoised = clip_denoised
-        self.use_karras = use_karras
-        self.karras_steps = karras_steps
-        self.sigma_min = sigma_min
-        self.sigma_max = sigma_max
-        self.s_churn = s_churn
-
-        self.models = models
-        self.diffusions = diffusions
-        self.use_cuda_graph = use_cuda_graph
-        self.noise_fn = noise_fn
+    def __init__(self, device: torch.device, models: Sequence[nn.Module], diffusions: Sequence[GaussianDiffusion],
+                 num_points: Sequence[int], aux_channels: Sequence[str],
+                 model_kwargs_key_filter: Sequence[str] = ("*",), guidance_scale: Sequence[float] = (3.0, 3.0),
+                 clip_denoised: bool = True, use_karras: Sequence[bool] = (True, True),
+                 karras_steps: Sequence[int] = (64, 64), sigma_min: Sequence[float] = (1e-3, 1e-3),
+                 sigma_max: Sequence[float] = (120, 160), s_churn: Sequence[float] = (3, 0),
+                 use_cuda_graph: bool = False, noise_fn: Optional[Callable] = None):
+        stages = len(models)
+        assert stages > 0
+        given = dict(model_kwargs_key_filter=model_kwargs_key_filter, guidance_scale=guidance_scale, use_karras=use_karras,
+                     karras_steps=karras_steps, sigma_min=sigma_min, sigma_max=sigma_max, s_churn=s_churn)
+        for name in _STAGE_OPTIONS:
+            value = given[name]
+            if stages > 1 and len(value) == 1:
+                # one entry for a cascade: later stages repeat it -- but are unguided (scale 1) by default
+                rest = [1.0] * (stages - 1) if name == "guidance_scale" else list(value) * (stages - 1)
+                value = list(value) + rest
+            if name == "model_kwargs_key_filter" and len(value) == 0:
+                value = ["*"] * stages
+            assert len(value) == stages, f"{name}: expected one entry per stage ({stages}), got {len(value)}"
+            setattr(self, name, value)
+        self.device, self.models, self.diffusions = device, models, diffusions
+        self.num_points, self.aux_channels, self.clip_denoised = num_points, aux_channels, clip_denoised
+        self.use_cuda_graph, self.noise_fn = use_cuda_graph, noise_fn
         self._graphs: Dict[Tuple, _GraphedStage] = {}
 
     @property
     def num_stages(self) -> int:
         return len(self.models)
 
-    def sample_batch(self, batch_size: int, model_kwargs: Dict[str, Any]) -> torch.Tensor:
-        samples = None
-        for x in self.sample_batch_progressive(batch_size, model_kwargs):
-            samples = x
-        return samples
+    def _stages(self) -> Iterator[_Stage]:
+        for i in range(self.num_stages):
+            yield _Stage(i, self.models[i], self.diffusions[i], self.num_points[i], self.model_kwargs_key_filter[i],
+                         self.guidance_scale[i], self.use_karras[i], self.karras_steps[i], self.sigma_min[i],
+                         self.sigma_max[i], self.s_churn[i])
 
-    def _graphed_stage(self, idx, model, diffusion, shape, steps, smin, smax, churn, guidance) -> _GraphedStage:
-        key = (idx, tuple(shape), steps, smin, smax, churn, guidance, self.clip_denoised)
+    def sample_batch(self, batch_size: int, model_kwargs: Dict[str, Any]) -> torch.Tensor:
+        """The final clouds only: the last yield of ``sample_batch_progressive``."""
+        last = None
+        for last in self.sample_batch_progressive(batch_size, model_kwargs):
+            pass
+        return last
+
+    def _graphed_stage(self, st: _Stage, shape) -> _GraphedStage:
+        key = (st.index, tuple(shape), st.steps, st.sigma_min, st.sigma_max, st.churn, st.guidance, self.clip_denoised)
         if key not in self._graphs:
-            plan = HeunPlan(diffusion, steps, smin, smax, 7.0, churn)
-            self._graphs[key] = _GraphedStage(model, diffusion, plan, shape, self.device, guidance,
+            plan = HeunPlan(st.diffusion, st.steps, st.sigma_min, st.sigma_max, 7.0, st.churn)
+            self._graphs[key] = _GraphedStage(st.model, st.diffusion, plan, shape, self.device, st.guidance,
                                               self.clip_denoised)
         return self._graphs[key]
 
-    def sample_batch_progressive(
-        self, batch_size: int, model_kwargs: Dict[str, Any], x_target: torch.Tensor = None,
-    ) -> Iterator[torch.Tensor]:
+    def _stage_conditioning(self, st: _Stage, batch_size: int, model_kwargs: Dict[str, Any], previous) -> Dict[str, Any]:
+        """kwargs of one stage (reference sampler.py:121-136): key filter, the previous stage's clouds as ``low_res``,
+        the model's ``cached_model_kwargs`` hook, then -- for classifier-free guidance -- every tensor doubled with an
+        all-zero unconditional half ([:B] conditional, [B:] unconditional)."""
+        kw = dict(model_kwargs)
+        if st.key_filter != "*":
+            wanted = set(st.key_filter.split(","))
+            kw = {name: v for name, v in kw.items() if name in wanted}
+        if previous is not None:
+            kw["low_res"] = previous
+        if hasattr(st.model, "cached_model_kwargs"):
+            kw = st.model.cached_model_kwargs(batch_size, kw)
+        if st.guided:
+            kw = {name: (v if name == "prev_latent" else torch.cat([v, torch.zeros_like(v)], dim=0))
+                  for name, v in kw.items()}
+        return kw
+
+    def _stage_predictions(self, st: _Stage, shape, kw: Dict[str, Any], x_target) -> Iterator[torch.Tensor]:
+        """The x0 predictions a stage yields, one per step (+ the final one repeated), [B or 2B, C, N]."""
+        if not st.karras:
+            # ancestral DDPM loop over all diffusion steps (reference sampler.py:153-165).  With a guidance scale the
+            # reference wraps the model in _uncond_guide_model, whose (x_t, ts, model_kwargs) signature does not
+            # match how p_mean_variance calls models (**model_kwargs): that call raises TypeError there, so there
+            # is no behaviour to reproduce (SURVEY.md appendix B).
+            if st.guidance:
+                raise NotImplementedError(
+                    "use_karras=False with a guidance scale: the reference's own branch fails with a TypeError "
+                    "(diffusion/sampler.py:194-233 vs gaussian_diffusion.py:285); use guidance_scale=0 or use_karras=True")
+            for out in st.diffusion.p_sample_loop_progressive(st.model, shape=shape, model_kwargs=kw, device=self.device,
+                                                              clip_denoised=self.clip_denoised, noise_fn=self.noise_fn):
+                yield out["pred_xstart"]
+        elif self.use_cuda_graph and getattr(st.model, "pcd_native", False):
+            # fresh tensors like the reference (the stage buffers are overwritten by the next replay)
+            preds = self._graphed_stage(st, shape).run(kw, self.noise_fn).clone()
+            yield from preds
+            yield preds[-1]
+        else:
+            for out in karras_sample_progressive(diffusion=st.diffusion, model=st.model, shape=shape, steps=st.steps,
+                                                 clip_denoised=self.clip_denoised, model_kwargs=kw, device=self.device,
+                                                 sigma_min=st.sigma_min, sigma_max=st.sigma_max, s_churn=st.churn,
+                                                 guidance_scale=st.guidance, x_target=x_target, noise_fn=self.noise_fn):
+                yield out["pred_xstart"]
+
+    def sample_batch_progressive(self, batch_size: int, model_kwargs: Dict[str, Any],
+                                 x_target: torch.Tensor = None) -> Iterator[torch.Tensor]:
+        """Yields [batch_size, 3 + len(aux_channels), N] after every sampling step of every stage; an upsampling
+        stage's yields carry its conditioning cloud in front of the new points (reference sampler.py:166-171)."""
         require_cuda()
-        samples = None
-        for idx, (
-            model,
-            diffusion,
-            stage_num_points,
-            stage_guidance_scale,
-            stage_use_karras,
-            stage_karras_steps,
-            stage_sigma_min,
-            stage_sigma_max,
-            stage_s_churn,
-            stage_key_filter,
-        ) in enumerate(zip(
-            self.models,
-            self.diffusions,
-            self.num_points,
-            self.guidance_scale,
-            self.use_karras,
-            self.karras_steps,
-            self.sigma_min,
-            self.sigma_max,
-            self.s_churn,
-            self.model_kwargs_key_filter,
-        )):
-            stage_model_kwargs = model_kwargs.copy()
-            if stage_key_filter != "*":
-                use_keys = set(stage_key_filter.split(","))
-                stage_model_kwargs = {k: v for k, v in stage_model_kwargs.items() if k in use_keys}
-            if samples is not None:
-                stage_model_kwargs["low_res"] = samples
-            if hasattr(model, "cached_model_kwargs"):
-                stage_model_kwargs = model.cached_model_kwargs(batch_size, stage_model_kwargs)
-            sample_shape = (batch_size, 3 + len(self.aux_channels), stage_num_points)
-
-            if stage_guidance_scale != 1 and stage_guidance_scale != 0:
-                for k, v in stage_model_kwargs.copy().items():
-                    if k not in ["prev_latent"]:
-                        stage_model_kwargs[k] = torch.cat([v, torch.zeros_like(v)], dim=0)
-
-            low_res = stage_model_kwargs.get("low_res")
-            if not stage_use_karras:
-                # ancestral DDPM loop over all diffusion steps (reference sampler.py:153-165).  With a guidance scale the
-                # reference wraps the model in _uncond_guide_model, whose (x_t, ts, model_kwargs) signature does not
-                # match how p_mean_variance calls models (**model_kwargs): that call raises TypeError there, so there
-                # is no behaviour to reproduce (SURVEY.md appendix B).
-                if stage_guidance_scale:
-                    raise NotImplementedError(
-                        "use_karras=False with a guidance scale: the reference's own branch fails with a TypeError "
-                        "(diffusion/sampler.py:194-233 vs gaussian_diffusion.py:285); use guidance_scale=0 or use_karras=True")
-                outs = (o["pred_xstart"] for o in diffusion.p_sample_loop_progressive(
-                    model, shape=sample_shape, model_kwargs=stage_model_kwargs, device=self.device,
-                    clip_denoised=self.clip_denoised, noise_fn=self.noise_fn))
-            elif self.use_cuda_graph and getattr(model, "pcd_native", False):
-                stage = self._graphed_stage(idx, model, diffusion, sample_shape, stage_karras_steps,
-                                            stage_sigma_min, stage_sigma_max, stage_s_churn,
-                                            stage_guidance_scale)
-                # fresh tensors like the reference (the stage buffers are overwritten by the next replay)
-                preds = stage.run(stage_model_kwargs, self.noise_fn).clone()
-                outs = [preds[i] for i in range(preds.shape[0])] + [preds[-1]]
-            else:
-                outs = (o["pred_xstart"] for o in karras_sample_progressive(
-                    diffusion=diffusion,
-                    model=model,
-                    shape=sample_shape,
-                    steps=stage_karras_steps,
-                    clip_denoised=self.clip_denoised,
-                    model_kwargs=stage_model_kwargs,
-                    device=self.device,
-                    sigma_min=stage_sigma_min,
-                    sigma_max=stage_sigma_max,
-                    s_churn=stage_s_churn,
-                    guidance_scale=stage_guidance_scale,
-                    x_target=x_target,
-                    noise_fn=self.noise_fn,
-                ))
-            for x in outs:
-                samples = x[:batch_size]
+        clouds = None
+        for st in self._stages():
+            kw = self._stage_conditioning(st, batch_size, model_kwargs, clouds)
+            shape = (batch_size, 3 + len(self.aux_channels), st.num_points)
+            low_res = kw.get("low_res")
+            for pred in self._stage_predictions(st, shape, kw, x_target):
+                clouds = pred[:batch_size]
                 if low_res is not None:
-                    samples = torch.cat([low_res[: len(samples)], samples], dim=-1)
-                yield samples
+                    clouds = torch.cat([low_res[:len(clouds)], clouds], dim=-1)
+                yield clouds
+
+    def _options(self) -> Dict[str, Any]:
+        return dict({name: getattr(self, name) for name in _STAGE_OPTIONS}, device=self.device, models=self.models,
+                    diffusions=self.diffusions, num_points=self.num_points, aux_channels=self.aux_channels,
+                    clip_denoised=self.clip_denoised, use_cuda_graph=self.use_cuda_graph, noise_fn=self.noise_fn)
 
     @classmethod
     def combine(cls, *samplers: "PointCloudSampler") -> "PointCloudSampler":
-        assert all(x.device == samplers[0].device for x in samplers[1:])
-        assert all(x.aux_channels == samplers[0].aux_channels for x in samplers[1:])
-        assert all(x.clip_denoised == samplers[0].clip_denoised for x in samplers[1:])
-        return cls(
-            device=samplers[0].device,
-            models=[x for y in samplers for x in y.models],
-            diffusions=[x for y in samplers for x in y.diffusions],
-            num_points=[x for y in samplers for x in y.num_points],
-            aux_channels=samplers[0].aux_channels,
-            model_kwargs_key_filter=[x for y in samplers for x in y.model_kwargs_key_filter],
-            guidance_scale=[x for y in samplers for x in y.guidance_scale],
-            clip_denoised=samplers[0].clip_denoised,
-            use_karras=[x for y in samplers for x in y.use_karras],
-            karras_steps=[x for y in samplers for x in y.karras_steps],
-            sigma_min=[x for y in samplers for x in y.sigma_min],
-            sigma_max=[x for y in samplers for x in y.sigma_max],
-            s_churn=[x for y in samplers for x in y.s_churn],
-            use_cuda_graph=samplers[0].use_cuda_graph,
-            noise_fn=samplers[0].noise_fn,
-        )
+        """One cascade out of several samplers, stages in argument order (reference sampler.py:173-192)."""
+        first = samplers[0]
+        for other in samplers[1:]:
+            assert other.device == first.device
+            assert other.aux_channels == first.aux_channels
+            assert other.clip_denoised == first.clip_denoised
+        merged = first._options()
+        for name in ("models", "diffusions", "num_points") + _STAGE_OPTIONS:
+            merged[name] = [entry for smp in samplers for entry in getattr(smp, name)]
+        return cls(**merged)
 
-    def split_model_output(
-        self,
-        output: torch.Tensor,
-        rescale_colors: bool = False,
-    ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-        assert (
-            len(self.aux_channels) + 3 == output.shape[1]
-        ), "there must be three spatial channels before aux"
-        pos, joined_aux = output[:, :3], output[:, 3:]
+    def with_options(self, guidance_scale: float, clip_denoised: bool, use_karras: Sequence[bool] = (True, True),
+                     karras_steps: Sequence[int] = (64, 64), sigma_min: Sequence[float] = (1e-3, 1e-3),
+                     sigma_max: Sequence[float] = (120, 160), s_churn: Sequence[float] = (3, 0)) -> "PointCloudSampler":
+        """A sampler over the same models with other sampling options (reference sampler.py:267-291)."""
+        opts = self._options()
+        opts.update(guidance_scale=guidance_scale, clip_denoised=clip_denoised, use_karras=use_karras,
+                    karras_steps=karras_steps, sigma_min=sigma_min, sigma_max=sigma_max, s_churn=s_churn)
+        return PointCloudSampler(**opts)
 
-        aux = {}
-        for i, name in enumerate(self.aux_channels):
-            v = joined_aux[:, i]
-            if name in {"R", "G", "B", "A"}:
-                v = v.clamp(0, 255).round()
-                if rescale_colors:
-                    v = v / 255.0
-            aux[name] = v
-        return pos, aux
+    def split_model_output(self, output: torch.Tensor,
+                           rescale_colors: bool = False) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+        """[B, 3 + aux, N] -> (xyz [B, 3, N], {channel name: [B, N]}); colour channels are clamped to [0, 255] and
+        rounded, optionally rescaled to [0, 1] (reference sampler.py:235-253)."""
+        assert output.shape[1] == 3 + len(self.aux_channels), "there must be three spatial channels before aux"
+        named = {}
+        for offset, name in enumerate(self.aux_channels):
+            values = output[:, 3 + offset]
+            if name in _COLOUR_CHANNELS:
+                values = values.clamp(0, 255).round()
+                values = values / 255.0 if rescale_colors else values
+            named[name] = values
+        return output[:, :3], named
 
     def output_to_point_clouds(self, output: torch.Tensor) -> List[PointCloud]:
         """One ``PointCloud`` per sample, colours rescaled to [0, 1] (reference sampler.py:255-265)."""
-        res = []
-        for sample in output:
-            xyz, aux = self.split_model_output(sample[None], rescale_colors=True)
-            res.append(PointCloud(coords=xyz[0].t().cpu().numpy(),
-                                  channels={k: v[0].cpu().numpy() for k, v in aux.items()}))
-        return res
-
-    def with_options(
-        self,
-        guidance_scale: float,
-        clip_denoised: bool,
-        use_karras: Sequence[bool] = (True, True),
-        karras_steps: Sequence[int] = (64, 64),
-        sigma_min: Sequence[float] = (1e-3, 1e-3),
-        sigma_max: Sequence[float] = (120, 160),
-        s_churn: Sequence[float] = (3, 0),
-    ) -> "PointCloudSampler":
-        return PointCloudSampler(
-            device=self.device,
-            models=self.models,
-            diffusions=self.diffusions,
-            num_points=self.num_points,
-            aux_channels=self.aux_channels,
-            model_kwargs_key_filter=self.model_kwargs_key_filter,
-            guidance_scale=guidance_scale,
-            clip_denoised=clip_denoised,
-            use_karras=use_karras,
-            karras_steps=karras_steps,
-            sigma_min=sigma_min,
-            sigma_max=sigma_max,
-            s_churn=s_churn,
-            use_cuda_graph=self.use_cuda_graph,
-            noise_fn=self.noise_fn,
-        )
+        xyz, named = self.split_model_output(output, rescale_colors=True)
+        xyz = xyz.permute(0, 2, 1).cpu().numpy()
+        named = {name: v.cpu().numpy() for name, v in named.items()}
+        return [PointCloud(coords=xyz[b], channels={name: v[b] for name, v in named.items()})
+                for b in range(output.shape[0])]
