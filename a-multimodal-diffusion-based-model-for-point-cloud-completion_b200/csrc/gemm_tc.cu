@@ -572,7 +572,16 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           __syncwarp();
         }
         tmem_ld_wait();
-        if (c + 1 < NCH) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);
+        if (c + 1 < NCH) {
+          tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);
+        } else {
+          // the last chunk of this warp's accumulator slice is in registers: hand the TMEM buffer back to the MMA
+          // issuer now, a quarter of an epilogue earlier than after the math and stores of this chunk (the MMA
+          // stream and the epilogue are nearly balanced at K = 512, so slack on the hand-off is what absorbs jitter)
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_acc_empty);
+        }
         const float* sbc = sb + half * HALF_N + c * 32;
         float v[32];
         {
@@ -690,9 +699,6 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int row = row0 + lane;
         if (row < M) stats_out[(size_t)row * (N / HALF_N) + n_blk * 2 + half] = make_float2(st_mean, st_m2);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_acc_empty);
     }
     if (elect_one()) tma_store_wait_all<0>();
   }
