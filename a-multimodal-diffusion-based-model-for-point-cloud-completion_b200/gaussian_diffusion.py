@@ -131,6 +131,15 @@ class GaussianDiffusion:
             self._ddpm_tables[key] = th.from_numpy(tab).float().to(device).contiguous()
         return self._ddpm_tables[key]
 
+    def _channel_tensors(self, device):
+        """channel_scales / channel_biases on the device (cached; None when the diffusion has none)."""
+        key = ("channels", str(device))
+        if key not in self._ddpm_tables:
+            f32 = dict(device=device, dtype=th.float32)
+            self._ddpm_tables[key] = (None if self.channel_scales is None else th.tensor(self.channel_scales, **f32),
+                                      None if self.channel_biases is None else th.tensor(self.channel_biases, **f32))
+        return self._ddpm_tables[key]
+
     def _ddpm_step(self, model, x, t, clip_denoised, model_kwargs, noise, outputs):
         """One fused p_mean_variance (+ p_sample when ``noise`` is given).  ``outputs``: names of the optional result
         tensors to materialise among x_next / pred_xstart / sample_unscaled / mean / log_variance."""
@@ -152,13 +161,11 @@ class GaussianDiffusion:
         res = {k: th.empty_like(x) for k in outputs}
         a = _lib.DdpmArgs()
         a.x, a.model_out, a.noise = _lib.ptr(x), _lib.ptr(out), _lib.ptr(noise.contiguous() if noise is not None else None)
+        if not t.is_cuda and bool(((t < 0) | (t >= self.num_timesteps)).any()):
+            raise IndexError("timestep out of range")  # (device-side indices are trusted: checking them would sync)
         tt = t.to(device=x.device, dtype=th.int64).contiguous()
-        if bool(((tt < 0) | (tt >= self.num_timesteps)).any()):
-            raise IndexError("timestep out of range")
         a.t, a.table = _lib.ptr(tt), _lib.ptr(self._ddpm_table(x.device))
-        f32 = dict(device=x.device, dtype=th.float32)
-        sc = None if self.channel_scales is None else th.tensor(self.channel_scales, **f32)
-        bi = None if self.channel_biases is None else th.tensor(self.channel_biases, **f32)
+        sc, bi = self._channel_tensors(x.device)
         a.ch_scale, a.ch_bias = _lib.ptr(sc), _lib.ptr(bi)
         for k in ("x_next", "pred_xstart", "sample_unscaled", "mean", "log_variance"):
             setattr(a, k, _lib.ptr(res.get(k)))
