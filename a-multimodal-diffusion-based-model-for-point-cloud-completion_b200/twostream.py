@@ -24,6 +24,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import EPI_BIAS, EPI_BIAS_GELU
+from .transformer import fold_layernorm_into_linear
 
 LN_EPS = 1e-5
 
@@ -242,6 +243,7 @@ class TwoStreamDenoiser(nn.Module):
         self.register_buffer("token_types_template", torch.tensor(types, dtype=torch.long))
         self._bf16 = {}
         self.cache_conditioning = True
+        self.fold_layernorm = True  # bf16 mode: LayerNorms applied inside the projection epilogues (False: LN kernels)
         self._cond_cache = {}
         self._cfg, self._time_tok = {}, {}
         if device is not None:
@@ -328,6 +330,61 @@ class TwoStreamDenoiser(nn.Module):
         a = ops.attention_views(q, k, v, heads, s, s).view(-1, P)
         w, _ = self._padded("o", owner, (wo,), (bo,), cols=True)
         return self._proj(a, w, bo, residual=residual)
+
+    # ---- bf16 mode, >= 512 rows per stream: LayerNorm folded into the projections ----------------
+    # Every LayerNorm of the backbone feeds a projection, so with W' = bf16(gamma o W), s = rowsum(W'), c = W beta + b
+    #   LN(x) W^T + b = rstd (x W'^T - mu s) + c
+    # is evaluated by the projection's epilogue from the bf16 copy of the stream and its row statistics, which the
+    # residual projections (out_proj / fc2) emit next to the updated fp32 stream: no LayerNorm or cast kernels.
+    def _folded(self, tag: str, owner, norm: nn.LayerNorm, mats, biases, pad: bool):
+        """(W', colsum, const) of LN(norm) followed by the stacked projections ``mats``; pad=True additionally
+        zero-pads every 32-row head group to 64 rows (tensor-core attention layout)."""
+        params = tuple(mats) + tuple(x for x in biases if x is not None) + (norm.weight, norm.bias)
+        key = tuple(x._version for x in params) + tuple(x.data_ptr() for x in params)
+        hit = self._bf16.get((tag, id(owner)))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        w = torch.cat([m.detach().float() for m in mats], dim=0)
+        b = torch.cat([(x.detach().float() if x is not None else torch.zeros(m.shape[0], device=w.device))
+                       for x, m in zip(biases, mats)])
+        wf, colsum, const = fold_layernorm_into_linear(w, b, norm.weight.detach(), norm.bias.detach())
+        if pad:
+            K = wf.shape[1]
+            wp = torch.zeros(wf.shape[0] // 32, 64, K, device=wf.device, dtype=wf.dtype)
+            wp[:, :32] = wf.view(-1, 32, K)
+            cp, kp = torch.zeros(wf.shape[0] // 32, 64, device=wf.device), torch.zeros(wf.shape[0] // 32, 64, device=wf.device)
+            cp[:, :32], kp[:, :32] = colsum.view(-1, 32), const.view(-1, 32)
+            wf, colsum, const = wp.view(-1, K).contiguous(), cp.view(-1).contiguous(), kp.view(-1).contiguous()
+        out = (wf, colsum, const)
+        self._bf16[(tag, id(owner))] = (key, out)
+        return out
+
+    def _attend_fold(self, q_src, q_norm, kv_src, kv_norm, B, attn: _CrossAttention, stream: torch.Tensor):
+        """``stream`` (fp32, updated IN PLACE) += proj(attention(LN_q(q stream), LN_kv(kv stream))); q_src / kv_src are
+        (bf16 copy, row statistics) pairs.  Returns the new (bf16 copy, statistics) of ``stream``."""
+        heads = self.denoiser_backbone.num_heads
+        P = heads * 64
+        s = 32.0 ** -0.25
+        wq, wk, wv = attn.wq, attn.wk, attn.wv
+        if q_src is kv_src:
+            w, cs, c = self._folded("f_qkv", attn, q_norm, (wq.weight, wk.weight, wv.weight), (wq.bias, wk.bias, wv.bias), True)
+            qkv = ops.linear_layernorm_folded(q_src[0], q_src[1], w, cs, c, eps=LN_EPS).view(B, -1, 3 * P)
+            q, k, v = qkv[..., :P], qkv[..., P:2 * P], qkv[..., 2 * P:]
+        else:
+            w, cs, c = self._folded("f_q", attn, q_norm, (wq.weight,), (wq.bias,), True)
+            q = ops.linear_layernorm_folded(q_src[0], q_src[1], w, cs, c, eps=LN_EPS).view(B, -1, P)
+            w, cs, c = self._folded("f_kv", attn, kv_norm, (wk.weight, wv.weight), (wk.bias, wv.bias), True)
+            kv = ops.linear_layernorm_folded(kv_src[0], kv_src[1], w, cs, c, eps=LN_EPS).view(B, -1, 2 * P)
+            k, v = kv[..., :P], kv[..., P:]
+        a = ops.attention_views(q, k, v, heads, s, s).view(-1, P)
+        wo, _ = self._padded("o", attn, (attn.proj.weight,), (attn.proj.bias,), cols=True)
+        return ops.linear_residual_stats(a, wo, attn.proj.bias.detach().float(), stream)
+
+    def _mlp_fold(self, src, norm: nn.LayerNorm, mlp: _Mlp, stream: torch.Tensor):
+        """``stream`` += fc2(gelu(fc1(LN(stream)))) in place; returns its new (bf16 copy, statistics)."""
+        w, cs, c = self._folded("f_fc1", mlp, norm, (mlp.fc1.weight,), (mlp.fc1.bias,), False)
+        hid = ops.linear_layernorm_folded(src[0], src[1], w, cs, c, eps=LN_EPS, gelu=True)
+        return ops.linear_residual_stats(hid, self._wb(mlp.fc2.weight), mlp.fc2.bias.detach().float(), stream)
 
     def _ln(self, x2: torch.Tensor, norm: nn.LayerNorm, act: bool = True) -> torch.Tensor:
         """LayerNorm of an fp32 [M, d] stream; act=True -> in the dtype the next projection consumes."""
@@ -522,7 +579,19 @@ class TwoStreamDenoiser(nn.Module):
         prev = self._lin(hid, bb.latent_mlp.fc2, residual=prev)
         z = ops.add(z, self._ln(prev, bb.ln_latent, act=False))
 
-        for blk in bb.blocks:
+        fold = (self.compute_dtype == torch.bfloat16 and d % 256 == 0 and z.shape[0] >= 512 and xs.shape[0] >= 512
+                and self.fold_layernorm)
+        if fold:
+            zs, xsrc = ops.cast_rowstats(z), ops.cast_rowstats(xs)  # (bf16 copy, row statistics) of either stream
+            for blk in bb.blocks:
+                zs = self._attend_fold(zs, blk.read.norm_z1, xsrc, blk.read.norm_x, S, blk.read.attn, z)
+                zs = self._mlp_fold(zs, blk.read.norm_z2, blk.read.mlp, z)
+                for cb in blk.compute:
+                    zs = self._attend_fold(zs, cb.norm_z1, zs, cb.norm_z1, S, cb.attn, z)
+                    zs = self._mlp_fold(zs, cb.norm_z2, cb.mlp, z)
+                xsrc = self._attend_fold(xsrc, blk.write.norm_x1, zs, blk.write.norm_z, S, blk.write.attn, xs)
+                xsrc = self._mlp_fold(xsrc, blk.write.norm_x2, blk.write.mlp, xs)
+        for blk in (() if fold else bb.blocks):
             z = self._attend(self._ln(z, blk.read.norm_z1), self._ln(xs, blk.read.norm_x), S, blk.read.attn, z)
             z = self._mlp(z, blk.read.norm_z2, blk.read.mlp)
             for cb in blk.compute:
