@@ -36,6 +36,18 @@ def test_twostream_forward_matches_reference(name, dtype, tol):
     for got, want, what in ((y0, g["y0"], "y0"), (z0, g["z0"], "z0"), (y1, g["y1"], "y1"), (z1[:, ::8], g["z1"], "z1"),
                             (y2, g["y2"], "y2"), (z2[:, ::8], g["z2"], "z2")):
         assert rel(got, want) < tol, describe(got, want, f"{name} {dtype} {what}")
+    if dtype == torch.bfloat16:
+        # >= 512 rows per stream: the default path folds the LayerNorms into the projection epilogues; the LayerNorm-kernel
+        # path must agree with it (and with the reference) on the same inputs
+        launches = []
+        for fold in (True, False):
+            model.fold_layernorm = fold
+            n0 = P.ops.launch_count()
+            yf, zf = model(x, t, class_labels=labels, viewpoints=views, prev_latent=prev)
+            launches.append(P.ops.launch_count() - n0)
+            assert rel(yf, g["y1"]) < tol and rel(zf[:, ::8], g["z1"]) < tol, f"fold={fold}"
+            assert rel(yf, y1) < (1e-6 if fold else 1e-2)
+        assert launches[0] < launches[1], launches  # no LayerNorm / cast launches on the folded path
 
 
 def test_twostream_state_dict_and_unsupported_modalities():
