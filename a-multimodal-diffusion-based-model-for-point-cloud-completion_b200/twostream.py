@@ -554,6 +554,33 @@ class TwoStreamDenoiser(nn.Module):
         te = ops.linear(te, bb.time_embed.fc1.weight.detach(), bb.time_embed.fc1.bias.detach(), epilogue=EPI_BIAS_GELU)
         return ops.linear(te, bb.time_embed.fc2.weight.detach(), bb.time_embed.fc2.bias.detach())
 
+    def _blocks_plain(self, z: torch.Tensor, xs: torch.Tensor, S: int):
+        """read / compute / write blocks (modules.py:76-146) with LayerNorm kernels in front of the projections."""
+        for blk in self.denoiser_backbone.blocks:
+            z = self._attend(self._ln(z, blk.read.norm_z1), self._ln(xs, blk.read.norm_x), S, blk.read.attn, z)
+            z = self._mlp(z, blk.read.norm_z2, blk.read.mlp)
+            for cb in blk.compute:
+                zn = self._ln(z, cb.norm_z1)
+                z = self._attend(zn, zn, S, cb.attn, z)
+                z = self._mlp(z, cb.norm_z2, cb.mlp)
+            xs = self._attend(self._ln(xs, blk.write.norm_x1), self._ln(z, blk.write.norm_z), S, blk.write.attn, xs)
+            xs = self._mlp(xs, blk.write.norm_x2, blk.write.mlp)
+        return z, xs
+
+    def _blocks_folded(self, z: torch.Tensor, xs: torch.Tensor, S: int):
+        """The same blocks with every LayerNorm folded into the projection that consumes it; z and xs (fp32 [rows, d])
+        are updated in place, ``zs`` / ``xsrc`` carry the (bf16 copy, row statistics) of either stream."""
+        zs, xsrc = ops.cast_rowstats(z), ops.cast_rowstats(xs)
+        for blk in self.denoiser_backbone.blocks:
+            zs = self._attend_fold(zs, blk.read.norm_z1, xsrc, blk.read.norm_x, S, blk.read.attn, z)
+            zs = self._mlp_fold(zs, blk.read.norm_z2, blk.read.mlp, z)
+            for cb in blk.compute:
+                zs = self._attend_fold(zs, cb.norm_z1, zs, cb.norm_z1, S, cb.attn, z)
+                zs = self._mlp_fold(zs, cb.norm_z2, cb.mlp, z)
+            xsrc = self._attend_fold(xsrc, blk.write.norm_x1, zs, blk.write.norm_z, S, blk.write.attn, xs)
+            xsrc = self._mlp_fold(xsrc, blk.write.norm_x2, blk.write.mlp, xs)
+        return z, xs
+
     def _backbone_forward(self, x: torch.Tensor, te: torch.Tensor, cond: torch.Tensor, prev: Optional[torch.Tensor]):
         """Denoiser_backbone.forward (modules.py:198-244) for S sequences: x [S, C, N], time rows te [S, d] (or [1, d]
         shared), condition tokens [S, n_cond, d], prev [S * n_lat, d] fp32 or None -> ([S, C_out, N], z [S, n_lat, d])."""
@@ -579,27 +606,9 @@ class TwoStreamDenoiser(nn.Module):
         prev = self._lin(hid, bb.latent_mlp.fc2, residual=prev)
         z = ops.add(z, self._ln(prev, bb.ln_latent, act=False))
 
-        fold = (self.compute_dtype == torch.bfloat16 and d % 256 == 0 and z.shape[0] >= 512 and xs.shape[0] >= 512
-                and self.fold_layernorm)
-        if fold:
-            zs, xsrc = ops.cast_rowstats(z), ops.cast_rowstats(xs)  # (bf16 copy, row statistics) of either stream
-            for blk in bb.blocks:
-                zs = self._attend_fold(zs, blk.read.norm_z1, xsrc, blk.read.norm_x, S, blk.read.attn, z)
-                zs = self._mlp_fold(zs, blk.read.norm_z2, blk.read.mlp, z)
-                for cb in blk.compute:
-                    zs = self._attend_fold(zs, cb.norm_z1, zs, cb.norm_z1, S, cb.attn, z)
-                    zs = self._mlp_fold(zs, cb.norm_z2, cb.mlp, z)
-                xsrc = self._attend_fold(xsrc, blk.write.norm_x1, zs, blk.write.norm_z, S, blk.write.attn, xs)
-                xsrc = self._mlp_fold(xsrc, blk.write.norm_x2, blk.write.mlp, xs)
-        for blk in (() if fold else bb.blocks):
-            z = self._attend(self._ln(z, blk.read.norm_z1), self._ln(xs, blk.read.norm_x), S, blk.read.attn, z)
-            z = self._mlp(z, blk.read.norm_z2, blk.read.mlp)
-            for cb in blk.compute:
-                zn = self._ln(z, cb.norm_z1)
-                z = self._attend(zn, zn, S, cb.attn, z)
-                z = self._mlp(z, cb.norm_z2, cb.mlp)
-            xs = self._attend(self._ln(xs, blk.write.norm_x1), self._ln(z, blk.write.norm_z), S, blk.write.attn, xs)
-            xs = self._mlp(xs, blk.write.norm_x2, blk.write.mlp)
+        fold = (self.fold_layernorm and self.compute_dtype == torch.bfloat16 and d % 256 == 0
+                and min(z.shape[0], xs.shape[0]) >= 512)
+        z, xs = (self._blocks_folded if fold else self._blocks_plain)(z, xs, S)
 
         out = ops.linear(self._ln(xs, bb.ln_post, act=False), bb.output_proj.weight.detach(), bb.output_proj.bias.detach())
         return out.view(S, self.num_points, -1).permute(0, 2, 1).contiguous(), z.view(S, n_lat, d)
