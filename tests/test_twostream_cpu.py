@@ -67,3 +67,19 @@ def test_oracle_partial_cloud_and_depth_encoders_match_reference():
     assert rel(y0, g["y0"]) < 5e-6 and rel(z0[:, ::4], g["z0"]) < 5e-6
     assert rel(y1, g["y1"]) < 5e-6 and rel(z1[:, ::4], g["z1"]) < 5e-6
     assert rel(OT.sincos_2d(16, 16, c["latent_dim"])[::5, ::3], g["pos_embed"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_product_state_dict_has_the_reference_keys_and_shapes(name):
+    """Drop-in weights: the product's parameter containers (no GPU needed to build them) expose exactly the keys and
+    shapes of the reference's TwoStreamDenoiser.state_dict() recorded in the goldens."""
+    import pcd_b200 as P
+    from oracle.make_golden_twostream import ctor_kwargs
+    g = load_golden("twostream_" + name)
+    want = {k: tuple(int(x) for x in v.split(",")) if v else () for k, v in zip(g["shapes_keys"], g["shapes_vals"])}
+    model = P.TwoStreamDenoiser(**ctor_kwargs(CASES[name]))
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == want
+    if "depth" in CASES[name]["active_modalities"]:  # the fixed positional table is built like the reference's
+        pe = model.encoders["depth"].pos_embed
+        assert float((pe[::5, ::3] - torch.from_numpy(g["pos_embed"])).abs().max()) < 1e-6
