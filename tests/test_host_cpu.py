@@ -100,8 +100,15 @@ def test_sampler_constructor_semantics():
     assert torch.allclose(aux["G"], torch.tensor([[127.0 / 255, 128.0 / 255]]))
     c = P.PointCloudSampler.combine(s, s)
     assert c.num_stages == 4
-    w = s.with_options(2.0, False, use_karras=[True, True], karras_steps=[8, 8], sigma_min=[1e-3, 1e-3],
-                       sigma_max=[120, 160], s_churn=[0, 0]) if False else None
+    assert list(c.num_points) == [1024, 3072, 1024, 3072] and list(c.guidance_scale) == [3.0, 1.0, 3.0, 1.0]
+    # like the reference, with_options forwards guidance_scale as given: callers pass per-stage lists
+    w = s.with_options([2.0, 1.0], False, use_karras=[True, True], karras_steps=[8, 8], sigma_min=[1e-3, 1e-3],
+                       sigma_max=[120, 160], s_churn=[0, 0])
+    assert list(w.karras_steps) == [8, 8] and w.clip_denoised is False and w.models is s.models
+    assert list(w.model_kwargs_key_filter) == list(s.model_kwargs_key_filter)
+    clouds = s.output_to_point_clouds(out.repeat(2, 1, 1))
+    assert len(clouds) == 2 and clouds[0].coords.shape == (2, 3) and set(clouds[0].channels) == {"R", "G", "B"}
+    assert abs(float(clouds[1].channels["G"][1]) - 128.0 / 255) < 1e-6
 
 
 def test_configs_mirror_reference_registry():
