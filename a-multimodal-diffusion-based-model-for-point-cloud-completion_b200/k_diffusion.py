@@ -270,7 +270,10 @@ def make_denoiser_eval(model, model_kwargs: Dict[str, Any], B: int, guided: bool
     model_kwargs = model_kwargs or {}
     if _native(model):
         if hasattr(model, "begin_trajectory"):  # models that carry a latent between evaluations (TwoStreamDenoiser)
-            model.begin_trajectory(2 * B if guided else B)
+            seqs = 2 * B if guided else B
+            if hasattr(model, "stage_prev_latent"):  # only an unguided run keeps the caller's prev_latent
+                model.stage_prev_latent(seqs, None if guided else model_kwargs.get("prev_latent"))
+            model.begin_trajectory(seqs)
 
         def eval_native(model_in, t):
             return model.forward_cfg(model_in, t, model_kwargs, doubled=guided, out_channels=eps_channels)
@@ -291,8 +294,12 @@ def make_denoiser_eval(model, model_kwargs: Dict[str, Any], B: int, guided: bool
         tt = (th.full((B,), int(t), dtype=th.long, device=device) if float(t).is_integer() and not karras
               else th.full((B,), float(t), dtype=th.float32, device=device))
         if not guided:
-            kw = {k: v for k, v in model_kwargs.items() if k != "prev_latent"}
-            return call(model_in, tt, kw, "cond").contiguous()
+            # the reference's unguided `denoiser` passes model_kwargs through unchanged on every call and drops the
+            # returned latent (k_diffusion.py:150-166): only guided_denoiser threads prev_latent (:171-203)
+            out = model(model_in, tt, **model_kwargs)
+            if isinstance(out, tuple):
+                out = out[0]
+            return out.float().contiguous()
         cond = {k: v[:B] for k, v in model_kwargs.items() if k != "prev_latent"}
         uncond = {k: v[B:] for k, v in model_kwargs.items() if k != "prev_latent"}
         return th.cat([call(model_in, tt, cond, "cond"), call(model_in, tt, uncond, "uncond")], dim=0).contiguous()

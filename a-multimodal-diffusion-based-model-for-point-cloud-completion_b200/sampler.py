@@ -45,7 +45,7 @@ class _GraphedStage:
         B = self.shape[0]
         torch.mul(self.noise[0], plan.sigma_max, out=st.x)
         if hasattr(self.model, "begin_trajectory"):
-            self.model.begin_trajectory(B * (2 if st.guided else 1))
+            self.model.begin_trajectory(B * (2 if st.guided else 1))  # an unguided run's prev_latent was staged by run()
         st.begin(self.noise[1])
         for i, step in enumerate(plan.steps):
             out = self.model.forward_cfg(st.model_in, step.first.t, self.kwargs, st.guided, self.eps_channels)
@@ -65,6 +65,8 @@ class _GraphedStage:
             else:
                 self.noise[k].copy_(noise_fn(self.shape))
         self.kwargs = {k: v for k, v in kwargs.items() if k != "prev_latent"}
+        if hasattr(self.model, "stage_prev_latent"):  # only an unguided run keeps the caller's prev_latent
+            self.model.stage_prev_latent(seqs, None if self.state.guided else kwargs.get("prev_latent"))
         if getattr(self.model, "cfg_halves", False):
             self.model.prepare_cond(seqs, self.kwargs, self.state.guided)
         else:
@@ -164,7 +166,12 @@ class PointCloudSampler:
         return last
 
     def _graphed_stage(self, st: _Stage, shape) -> _GraphedStage:
-        key = (st.index, tuple(shape), st.steps, st.sigma_min, st.sigma_max, st.churn, st.guidance, self.clip_denoised)
+        base = (st.index, tuple(shape), st.steps, st.sigma_min, st.sigma_max, st.churn, st.guidance, self.clip_denoised)
+        # a graph bakes in the addresses of the packed weights / time tokens: re-capture when the model re-packs them
+        # (load_state_dict, an optimiser step) and drop the stale capture
+        key = base + (st.model.graph_key() if hasattr(st.model, "graph_key") else None,)
+        for old in [k for k in self._graphs if k[:len(base)] == base and k != key]:
+            del self._graphs[old]
         if key not in self._graphs:
             plan = HeunPlan(st.diffusion, st.steps, st.sigma_min, st.sigma_max, 7.0, st.churn)
             self._graphs[key] = _GraphedStage(st.model, st.diffusion, plan, shape, self.device, st.guidance,

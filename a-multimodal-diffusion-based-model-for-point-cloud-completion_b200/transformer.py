@@ -167,6 +167,7 @@ class PointDiffusionTransformer(nn.Module):
         self._cond_key: Dict[int, Any] = {}
         self._cond_refs: Dict[int, Any] = {}
         self._addc: Dict[int, Optional[torch.Tensor]] = {}
+        self._pack_version = 0   # bumped whenever the packed weights move (CUDA graphs captured before are stale)
         self._time_tok: Dict[float, torch.Tensor] = {}
         self._tcond: Dict[int, torch.Tensor] = {}
         self._out: Dict[Tuple[int, int], torch.Tensor] = {}
@@ -247,9 +248,15 @@ class PointDiffusionTransformer(nn.Module):
         handle = C.c_void_p()
         check(lib.pcd_model_create(C.byref(d), C.byref(handle)), "model_create")
         self._handle, self._packed_key, self._keep = handle, key, keep
+        self._pack_version += 1
         self._n_prefix, self._time_slot = n_prefix, time_slot
         self._cond_key.clear()
         self._time_tok.clear()
+
+    def graph_key(self):
+        """Changes whenever a CUDA graph captured over this model would read freed / repacked memory."""
+        self._ensure_handle()
+        return self._pack_version
 
     def _destroy_handle(self):
         if getattr(self, "_handle", None) is not None:
@@ -303,7 +310,16 @@ class PointDiffusionTransformer(nn.Module):
         tensors = {k: v for k, v in kw.items() if torch.is_tensor(v)}
         ckey = tuple(sorted((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in tensors.items()))
         if self._cond_key.get(seqs) != ckey or len(tensors) != len(kw):
-            self._addc[seqs] = self._fill_cond(seqs, kw, prefix)
+            addc = self._fill_cond(seqs, kw, prefix)
+            if addc is not None:
+                # persistent per-seqs buffer: a captured CUDA graph holds this address, so new conditioning is
+                # copied INTO it (like the prefix tokens), never swapped for a fresh tensor
+                buf = self._addc.get(seqs)
+                if buf is None or buf.shape != addc.shape:
+                    buf = torch.empty_like(addc)
+                buf.copy_(addc)
+                addc = buf
+            self._addc[seqs] = addc
             self._cond_key[seqs] = ckey
             self._cond_refs[seqs] = list(tensors.values())
         return self._addc.get(seqs)

@@ -673,15 +673,40 @@ class TwoStreamDenoiser(nn.Module):
             for i, k in enumerate(todo):
                 self._time_tok[k] = rows[i:i + 1].clone()
 
+    def graph_key(self):
+        """Changes whenever a CUDA graph captured over this model would read freed / re-derived weight copies (the
+        bf16 / folded / head-padded copies are re-made per parameter version)."""
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def stage_prev_latent(self, seqs: int, prev_latent: Optional[torch.Tensor]) -> None:
+        """Copy a caller-supplied ``prev_latent`` of an UNGUIDED run into the persistent staging buffer that
+        ``begin_trajectory`` reads (called outside graph capture, so a replay never dereferences the caller's tensor)."""
+        st = self._cfg_state(seqs, self.token_type_embeddings.weight.device)
+        st["has_user_latent"] = prev_latent is not None
+        if prev_latent is not None:
+            if "user_latent" not in st:
+                st["user_latent"] = torch.empty_like(st["latent"])
+            assert prev_latent.numel() == st["latent"].numel(), "prev_latent: expected [B, num_latents + n_cond + 1, d]"
+            st["user_latent"].copy_(prev_latent.float().reshape(st["latent"].shape))
+
     def begin_trajectory(self, seqs: int) -> None:
-        """Start of a sampling run: no previous latent (zeros == prev_latent=None, modules.py:211-212)."""
-        self._cfg_state(seqs, self.token_type_embeddings.weight.device)["latent"].zero_()
+        """Start of a sampling run.  Guided runs start from no previous latent (zeros == prev_latent=None,
+        modules.py:211-218) and thread each evaluation's latent into the next (guided_denoiser,
+        k_diffusion.py:171-203).  Unguided runs keep whatever ``prev_latent`` the caller passed (or none) for EVERY
+        evaluation: the reference's plain ``denoiser`` hands model_kwargs through unchanged and drops the returned
+        latent (k_diffusion.py:150-166)."""
+        st = self._cfg_state(seqs, self.token_type_embeddings.weight.device)
+        if st.get("has_user_latent"):  # set by stage_prev_latent, which every sampler path calls first
+            st["latent"].copy_(st["user_latent"])
+        else:
+            st["latent"].zero_()
 
     @torch.no_grad()
     def forward_cfg(self, x: torch.Tensor, t, model_kwargs, doubled: bool, out_channels: Optional[int] = None):
         """One evaluation of B (or, with guidance, 2B = [conditional ; unconditional]) sequences sharing the B inputs
-        ``x`` and the integer timestep ``t``; each sequence's latent of the previous evaluation is fed back as its
-        ``prev_latent`` (guided_denoiser, k_diffusion.py:182-207).  Returns a persistent [seqs, C_out, N] buffer."""
+        ``x`` and the integer timestep ``t``.  With guidance each sequence's latent of the previous evaluation is fed
+        back as its ``prev_latent`` (guided_denoiser, k_diffusion.py:171-203); without, the latent buffer set by
+        ``begin_trajectory`` is left untouched.  Returns a persistent [seqs, C_out, N] buffer."""
         B = x.shape[0]
         seqs = 2 * B if doubled else B
         st = self._cfg_state(seqs, x.device)
@@ -690,6 +715,7 @@ class TwoStreamDenoiser(nn.Module):
             self.prepare_time_tokens([t])
         out, z = self._backbone_forward(torch.cat([x, x], dim=0) if doubled else x, self._time_tok[float(t)],
                                         st["cond"], st["latent"])
-        st["latent"].copy_(z.view(st["latent"].shape))
+        if doubled:
+            st["latent"].copy_(z.view(st["latent"].shape))
         st["out"].copy_(out)
         return st["out"]

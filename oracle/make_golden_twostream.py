@@ -121,9 +121,10 @@ def gen_full(ref, name, c, shapes):
           float(y0.abs().mean()), len(shapes), "tensors")
 
 
-def gen_sampler():
+def gen_sampler(guidance=3.0, out_name="twostream_sampler_small.npz"):
     """The reference's own sampling setup for this model (run.py:119-141, config.yaml:40-58): guided Heun with the
-    latent self-conditioning threaded by guided_denoiser, on the small case, deterministic noise."""
+    latent self-conditioning threaded by guided_denoiser, on the small case, deterministic noise.  ``guidance=0``
+    pins the UNGUIDED path, where the reference's plain ``denoiser`` never threads the latent (k_diffusion.py:150-166)."""
     from oracle import cases
     from oracle.make_golden import patched_noise
     load_reference()
@@ -139,15 +140,16 @@ def gen_sampler():
     diffusion = gd.GaussianDiffusion(betas=gd.get_named_beta_schedule("linear", 1000), model_mean_type="epsilon",
                                      model_var_type="fixed_small", loss_type="mse")
     sampler = smp.PointCloudSampler(device=torch.device("cpu"), models=[ref], diffusions=[diffusion], num_points=[c["num_points"]],
-                                    aux_channels=[], guidance_scale=[3.0], clip_denoised=True, use_karras=[True],
+                                    aux_channels=[], guidance_scale=[guidance], clip_denoised=True, use_karras=[True],
                                     karras_steps=[6], sigma_min=[1e-3], sigma_max=[120], s_churn=[0.0])
     _, _, labels, views, _ = inputs(c)
     with patched_noise(cases.DetNoise(777)), torch.no_grad():
         ys = [y.clone() for y in sampler.sample_batch_progressive(c["B"], dict(class_labels=labels, viewpoints=views))]
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "twostream_sampler_small.npz"), yields=torch.stack(ys).numpy())
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", out_name), yields=torch.stack(ys).numpy())
     print("sampler", len(ys), float(ys[-1].abs().mean()))
 
 
 if __name__ == "__main__":
     main()
     gen_sampler()
+    gen_sampler(0.0, "twostream_sampler_small_unguided.npz")

@@ -111,6 +111,47 @@ def test_graph_equals_eager_bitwise():
     assert torch.equal(ya, yb), describe(yb, ya, "graph vs eager")
 
 
+def test_graph_replay_follows_new_conditioning_and_new_weights():
+    """A captured stage must not read stale addresses (round-1 advisor finding): (a) new `embeddings` tensors
+    (token_cond=False -> the conditioning vector is added to every token) and (b) re-loaded weights both have to
+    show up in the next sample_batch of a CUDA-graph sampler, bit for bit like a fresh eager sampler."""
+    from oracle import det
+    from test_oracle_golden import shapes_of
+    case = "small_imagevec_guided"
+    graph, sc, cfg, sd = make_sampler(case, torch.bfloat16, True)
+    B = sc["B"]
+    kw1 = to_dev(cases.sampler_kwargs(case))
+    y1 = graph.sample_batch(B, kw1).clone()
+
+    # (a) fresh conditioning tensor at a different address, old one released
+    e2 = det.normal(tuple(kw1["embeddings"].shape), 4321)
+    kw2 = dict(embeddings=(e2 / e2.norm(dim=1, keepdim=True)).to(DEV))
+    del kw1
+    junk = [torch.full((B, 768), 7.0, device=DEV) for _ in range(8)]  # recycle the freed blocks with other data
+    def restart_noise():
+        fresh = cases.DetNoise(sc["noise_seed"])
+        graph.noise_fn = lambda shp: fresh(shp).to(DEV)
+
+    restart_noise()
+    y2 = graph.sample_batch(B, kw2).clone()
+    eager, _, _, _ = make_sampler(case, torch.bfloat16, False)
+    want2 = eager.sample_batch(B, kw2)
+    assert torch.equal(y2, want2), describe(y2, want2, "graph replay with new embeddings")
+    assert not torch.equal(y2, y1)
+
+    # (b) new weights loaded into the same module: the packed copies move, the graph has to be re-captured
+    cfgm = cases.FORWARD_CASES[sc["model"]][0]
+    sd3 = det.fill_state_dict(shapes_of(cfgm), 977, mode="unit", width=cfgm["width"])
+    graph.models[0].load_state_dict(sd3)
+    restart_noise()
+    y3 = graph.sample_batch(B, kw2).clone()
+    eager3, _, _, _ = make_sampler(case, torch.bfloat16, False)
+    eager3.models[0].load_state_dict(sd3)
+    want3 = eager3.sample_batch(B, kw2)
+    assert torch.equal(y3, want3), describe(y3, want3, "graph replay after load_state_dict")
+    del junk
+
+
 def test_two_stage_cascade():
     g = load_golden("sampler_two_stage")
     base, bcfg, _ = build_model("small_imagevec", torch.float32)

@@ -139,6 +139,31 @@ def test_twostream_in_the_sampler_with_latent_self_conditioning(mode):
         assert torch.equal(again, got)
 
 
+@pytest.mark.parametrize("mode", ["two-calls", "batched", "graph"])
+def test_twostream_unguided_sampler_does_not_thread_the_latent(mode):
+    """guidance_scale 0 (k_diffusion.py:150-166): the reference's plain `denoiser` passes model_kwargs through unchanged
+    and drops the returned latent, so every evaluation sees prev_latent=None.  ln_latent is non-trivial in these
+    weights, so threading the latent (the round-1 bug) changes the trajectory."""
+    from oracle import cases
+    model, c, g, sd = build("small", torch.float32)
+    x, t, labels, views, prev = inputs(c)
+    B, N = c["B"], c["num_points"]
+    diffusion = P.GaussianDiffusion(betas=P.get_named_beta_schedule("linear", 1000), model_mean_type="epsilon",
+                                    model_var_type="fixed_small", loss_type="mse")
+    noise = cases.DetNoise(777)
+    sampler = P.PointCloudSampler(DEV, [_Opaque(model) if mode == "two-calls" else model], [diffusion], [N], [],
+                                  guidance_scale=[0.0], clip_denoised=True,
+                                  use_karras=[True], karras_steps=[6], sigma_min=[1e-3], sigma_max=[120], s_churn=[0.0],
+                                  noise_fn=lambda shp: noise(shp).to(DEV), use_cuda_graph=(mode == "graph"))
+    kw = dict(class_labels=labels.to(DEV), viewpoints=views.to(DEV))
+    got = torch.stack([y.clone() for y in sampler.sample_batch_progressive(B, kw)])
+    torch.cuda.synchronize()
+    want = torch.from_numpy(load_golden("twostream_sampler_small_unguided")["yields"])
+    assert got.shape == want.shape
+    for i in range(want.shape[0]):
+        assert rel(got[i], want[i]) < 1e-3, describe(got[i], want[i], f"yield {i}")
+
+
 class _Traced(_Opaque):
     """Public-forward wrapper that records chosen evaluations (inputs incl. prev_latent, outputs)."""
     def __init__(self, inner, keep):

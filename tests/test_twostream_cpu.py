@@ -50,6 +50,26 @@ def test_oracle_sampler_threads_the_latent_like_the_reference():
     assert float((got - want).norm() / want.norm()) < 1e-4
 
 
+def test_oracle_unguided_sampler_does_not_thread_the_latent():
+    """guidance_scale 0: the reference's plain `denoiser` drops the returned latent (k_diffusion.py:150-166), so every
+    evaluation starts from prev_latent=None -- pinned by the reference's own PointCloudSampler run."""
+    from oracle import cases
+    from oracle import sampler as S
+    c = CASES["small"]
+    g, sd = golden_state("small")
+    want = torch.from_numpy(load_golden("twostream_sampler_small_unguided")["yields"])
+    _, _, labels, views, _ = inputs(c)
+    tab = S.Tables(schedule="linear", timesteps=1000)
+    fn = lambda xx, tt, **k: OT.twostream_forward(sd, c, xx, tt, k.get("class_labels"), k.get("viewpoints"), k.get("prev_latent"))
+    with torch.no_grad():
+        ys = list(S.sample_batch_progressive([fn], [lambda b, k: k], [tab], [c["num_points"]], [], c["B"],
+                                             dict(class_labels=labels, viewpoints=views), guidance_scale=[0.0], karras_steps=[6],
+                                             sigma_min=[1e-3], sigma_max=[120], s_churn=[0.0], noise_fn=cases.DetNoise(777)))
+    got = torch.stack(ys)
+    assert got.shape == want.shape
+    assert float((got - want).norm() / want.norm()) < 1e-4
+
+
 def test_oracle_partial_cloud_and_depth_encoders_match_reference():
     """PartialPointCloudEncoder / DepthMapEncoder (model.py:262-434: nn.TransformerEncoder / Decoder stacks) on their
     own, inside the full four-modality forward, and with the depth map dropped."""
