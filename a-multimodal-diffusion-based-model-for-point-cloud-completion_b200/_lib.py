@@ -13,9 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PCD_B200_LIB: A/B timing of two builds of the library in one process tree (tools/ab.sh); never a fallback
 LIB_PATH = os.environ.get("PCD_B200_LIB") or os.path.join(HERE, "libpcd_b200.so")
 
+ABI_VERSION = 3
 PCD_F32, PCD_BF16 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 EPI_RESIDUAL_STATS, EPI_LN_BIAS, EPI_LN_BIAS_GELU = 3, 4, 5
+# pcd_attn_variant (tensor-core attention kernels, per call) and pcd_model_desc.flags
+ATTN_DEFAULT, ATTN_GROUPED, ATTN_GROUPED_FREE, ATTN_PAIRED, ATTN_PAIRED_POLY4, ATTN_PAIRED_POLY2 = 0, 8, 9, 5, 6, 7
+MODEL_SEPARATE_LAYERNORM, MODEL_ATTN_VARIANT_SHIFT = 1, 8
 
 c_float_p = C.POINTER(C.c_float)
 vp = C.c_void_p
@@ -41,7 +45,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("A", vp), ("lda", C.c_int), ("W", vp), ("ldw", C.c_int), ("bias", vp), ("residual", vp),
                 ("ldr", C.c_int), ("C", vp), ("ldc", C.c_int), ("out_precision", C.c_int), ("C2", vp),
                 ("ldc2", C.c_int), ("stats_out", vp), ("stats_in", vp), ("colsum", vp), ("ln_eps", C.c_float),
-                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int)]
+                ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("epilogue", C.c_int), ("debug", C.c_int)]
 
 
 class DdpmArgs(C.Structure):  # include/pcd_b200.h: pcd_ddpm_args
@@ -58,7 +62,7 @@ VAR_FIXED, VAR_LEARNED_RANGE, VAR_LEARNED = 0, 1, 2
 class ModelDesc(C.Structure):
     _fields_ = ([(n, C.c_int) for n in ("precision", "width", "heads", "layers", "c_in", "c_out",
                                          "n_points", "n_prefix", "time_slot")]
-                + [("ln_eps", C.c_float)]
+                + [("ln_eps", C.c_float), ("flags", C.c_int)]
                 + [(n, vp) for n in ("time_fc_w", "time_fc_b", "time_proj_w", "time_proj_b", "freqs",
                                      "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b", "in_w", "in_b",
                                      "out_w", "out_b")]
@@ -70,9 +74,6 @@ _SIGS = {
     "pcd_last_error": (C.c_char_p, []),
     "pcd_launch_count": (C.c_ulonglong, []),
     "pcd_check_device": (C.c_int, []),
-    "pcd_set_attention_variant": (C.c_int, [C.c_int]),
-    "pcd_default_attention_variant": (C.c_int, []),
-    "pcd_set_debug_flags": (C.c_int, [C.c_int]),
     "pcd_timestep_embed": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "pcd_layernorm": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "pcd_embed_tokens": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
@@ -90,7 +91,7 @@ _SIGS = {
     "pcd_cast_rowstats": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp]),
     "pcd_attention": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                 C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                C.c_float, vp, C.c_int, vp]),
+                                C.c_float, vp, C.c_int, C.c_int, vp]),
     "pcd_attention_hd32": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                      C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
     "pcd_rope_bf16": (C.c_int, [C.POINTER(AttnOperand), vp, C.c_int, C.c_int, C.c_int, vp]),
@@ -127,13 +128,17 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        if not os.environ.get("PCD_B200_LIB"):
+            # rebuilds only when the sources' content hash differs from the one the .so was built from: a stale
+            # library would mis-read the ctypes structs below
             from . import build as _build
             _build.build()
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
             fn = getattr(lib, name)  # AttributeError if the ABI drifted from the header
             fn.restype, fn.argtypes = res, args
+        if lib.pcd_abi_version() != ABI_VERSION:
+            raise PcdError(f"{LIB_PATH}: ABI version {lib.pcd_abi_version()}, this binding expects {ABI_VERSION}")
         _lib = lib
     return _lib
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpcd_b200.so")
 SOURCES = ["pcd_api.cu", "elementwise.cu", "sampler.cu", "gemm_simt.cu", "attn_simt.cu",
-           "gemm_tc.cu", "attn_tc.cu", "attn_tc5.cu", "pointops.cu"]
+           "gemm_tc.cu", "attn_tc_launch.cu", "attn_tc5.cu", "attn_tc8.cu", "pointops.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -26,18 +26,43 @@ def _nvcc():
     return nvcc
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (sources, header, flags).  Content, not mtimes: the
+    snapshot that travels to the GPU box does not preserve them."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS + SOURCES).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "pcd_b200.h"))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(os.path.dirname(HERE), "include", "pcd_b200.h"), os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:  # several ranks may import at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():
+            return LIB
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -56,10 +81,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose and out:
             print(out)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC"]
+    tmp = LIB + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

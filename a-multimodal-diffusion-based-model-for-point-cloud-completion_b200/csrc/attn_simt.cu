@@ -206,15 +206,13 @@ template <int HD>
 static int launch_attention_f32_hd(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                                    float* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv,
                                    float q_scale, float k_scale, const float* rope, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device, not per process
     cudaError_t e = cudaFuncSetAttribute(attn_f32_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(AttnSmem<HD>));
     if (e != cudaSuccess) {
       set_error("attention_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return PCD_ERR_CUDA;
     }
-    attr_set = true;
   }
   dim3 grid(ceil_div(len_q, AQ), heads, batch);
   attn_f32_kernel<HD><<<grid, 256, sizeof(AttnSmem<HD>), st>>>(

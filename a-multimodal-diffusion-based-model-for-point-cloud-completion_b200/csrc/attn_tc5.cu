@@ -578,8 +578,7 @@ static int launch_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
                       int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2,
                       cudaStream_t st) {
   auto kern = a5::attn_bf16_tc5_kernel<POLY>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device, not per process
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -587,7 +586,6 @@ static int launch_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
       set_error("attention_bf16: kernel attribute setup (%d B smem): %s", a5::SMEM_BYTES, cudaGetErrorString(e));
       return PCD_ERR_CUDA;
     }
-    attr_set = true;
   }
   const int nq = ceil_div(len_q, a5::BQ);
   const int64_t n_items64 = (int64_t)nq * heads * batch;

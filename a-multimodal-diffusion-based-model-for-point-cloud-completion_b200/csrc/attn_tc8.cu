@@ -1,0 +1,565 @@
+// bf16 flash attention (head dim 64, non-causal) on tcgen05 -- three query tiles per CTA, MUFU hand-off ring.
+//
+// What bounds head-dim-64 attention on this chip is the special-function unit: one ex2 per logit against 256
+// tensor FLOP, 16 ex2/clk/SM.  Variant 5 (attn_tc5.cu: two CTAs per SM, one 128-query tile each) left that
+// unit 43 % idle for a reason its ncu capture shows directly (profiles/r01/prof_attn_v5.ncu-rep, stall
+// reasons of MUFU.EX2: `wait` 55 %, `mio_throttle` 23 %): the two softmax warps that share a scheduler drift
+// INTO phase -- while both exponentiate they split the pipe and finish together, then both do their
+// non-exponential work (row maximum, P hand-off, barrier and TMEM round trips, ~580 cycles) with the pipe
+// empty: 2 x 512 + 580 cycles per pair of tiles where 2 x 512 would do (measured 0.96 us per pair against
+// 0.64 us for a lone CTA).  This kernel removes the convoy instead of shortening the chain:
+//   * ONE CTA per SM with THREE query tiles ("slots") of the same (sequence, head): 12 softmax warps, three
+//     per scheduler, sharing every K / V tile (one TMA load and one shared-memory copy serve three S = Q K^T
+//     products);
+//   * a MUFU TOKEN per scheduler: the three warps of a scheduler pass an mbarrier token round-robin and
+//     exponentiate only while holding it, so the pipe always belongs to exactly one warp running at the
+//     full 8 cycles per instruction, while the other two do their non-exponential work; the token is passed
+//     on a few instructions before the last exponential so the wake-up latency of the next warp is hidden;
+//   * with three warps to cover for each other the per-warp chain may be 3 x 512 cycles long, so the
+//     softmax needs no software pipelining: one S tile in registers (about 110 registers per thread), S, P
+//     and O single-buffered per slot in TMEM (3 x (64 + 32 + 64) = 480 of 512 columns);
+//   * the ragged last KV tile costs only its real 16-key groups (exponentials and P columns of fully masked
+//     groups are skipped, the PV product stops at the last real group);
+//   * rotary point encoding (rotaryencoderpcd.py:6-27) inside the kernel: a dedicated warp rotates head dims
+//     0..5 of every Q / K tile in shared memory between the TMA arrival and the first MMA that reads it.
+// Warp roles (512 threads): 0 = TMA producer (Q, K, V), 1 = QK^T issuer, 2 = rotary warp, 3 = PV issuer,
+// 4..15 = softmax: slot = (warp - 4) / 4, TMEM lane quarter = warp % 4, thread = query row.
+#include "common.cuh"
+#include "tc_sm100.cuh"
+
+namespace pcd {
+
+using namespace tc;
+
+namespace a8 {
+
+constexpr int BQ = 128, BKV = 64, HD = 64, NT = 3;
+constexpr int Q_TILE = BQ * HD * 2;    // 16 KB
+constexpr int KV_TILE = BKV * HD * 2;  // 8 KB
+constexpr int KSK = 4, KSV = 4;
+constexpr int TILE_BYTES = 2 * NT * Q_TILE + (KSK + KSV) * KV_TILE;  // 160 KB
+constexpr int BAR_BYTES = 1024;
+constexpr int SMEM_BYTES = TILE_BYTES + 1024 + BAR_BYTES;
+constexpr int TMEM_COLS = 512;
+__host__ __device__ constexpr int s_col(int s) { return s * 64; }
+__host__ __device__ constexpr int p_col(int s) { return 192 + s * 32; }
+__host__ __device__ constexpr int o_col(int s) { return 288 + s * 64; }
+
+// barrier slots (8 bytes each)
+constexpr int B_Q_FULL = 0, B_Q_EMPTY = B_Q_FULL + 2 * NT, B_Q_ROT = B_Q_EMPTY + 2 * NT, B_K_FULL = B_Q_ROT + 2 * NT,
+              B_K_EMPTY = B_K_FULL + KSK, B_K_ROT = B_K_EMPTY + KSK, B_V_FULL = B_K_ROT + KSK,
+              B_V_EMPTY = B_V_FULL + KSV, B_S_FULL = B_V_EMPTY + KSV, B_S_FREE = B_S_FULL + NT,
+              B_P_READY = B_S_FREE + NT, B_PV_DONE = B_P_READY + NT, B_O_FREE = B_PV_DONE + NT,
+              B_TOK = B_O_FREE + NT, B_COUNT = B_TOK + 4 * NT;
+static_assert(B_COUNT * 8 + 16 <= BAR_BYTES, "barrier block too small");
+
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma4(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// exponential that stays where the source puts it (between the token acquire and release)
+__device__ __forceinline__ float ex2v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
+
+// work item = (group of NT consecutive query tiles, head, sequence); consecutive items share (sequence, head)
+struct Item {
+  int g, h, b, n_act;
+};
+__device__ __forceinline__ Item decode_item(int item, int ngroups, int heads, int nq) {
+  const int g = item % ngroups, bh = item / ngroups;
+  return Item{g, bh % heads, bh / heads, min(NT, nq - g * NT)};
+}
+
+// 3-axis rotation of head dims 0..5 of one 128-byte tile row held in 128B-swizzled shared memory
+// (apply_rotary_pos_emb, rotaryencoderpcd.py:6-27: out[0:3] = even * cos - odd * sin, out[3:6] = even * sin + odd * cos)
+__device__ __forceinline__ void rope_row(uint32_t tile, int r, const float* __restrict__ coord) {
+  const uint32_t addr = tile + r * 128 + ((r & 7) << 4);  // 16-byte chunk 0 of row r sits at chunk position r & 7
+  uint32_t w0, w1, w2, w3;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+  float s0, c0, s1, c1, s2, c2;
+  sincosf(coord[0] * 3.14159265358979323846f, &s0, &c0);
+  sincosf(coord[1] * 3.14159265358979323846f, &s1, &c1);
+  sincosf(coord[2] * 3.14159265358979323846f, &s2, &c2);
+  const float e0 = __uint_as_float(w0 << 16), o0 = __uint_as_float(w0 & 0xffff0000u);
+  const float e1 = __uint_as_float(w1 << 16), o1 = __uint_as_float(w1 & 0xffff0000u);
+  const float e2 = __uint_as_float(w2 << 16), o2 = __uint_as_float(w2 & 0xffff0000u);
+  w0 = pack_bf16x2(e0 * c0 - o0 * s0, e1 * c1 - o1 * s1);
+  w1 = pack_bf16x2(e2 * c2 - o2 * s2, e0 * s0 + o0 * c0);
+  w2 = pack_bf16x2(e1 * s1 + o1 * c1, e2 * s2 + o2 * c2);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+}
+
+constexpr float kRescaleThreshold = 8.f;  // log2 units: P <= 2^8, safe in bf16 / fp32
+
+// TOKEN = 1: MUFU hand-off ring; 0: warps exponentiate whenever they are ready (A/B of the ring itself)
+template <int TOKEN>
+__global__ void __launch_bounds__(512, 1)
+attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs, int64_t o_ls,
+                     int len_q, int len_kv, float scale_log2, int nq, int ngroups, int heads, int n_items,
+                     const float* __restrict__ rope) {
+  extern __shared__ unsigned char smem_raw[];
+  uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  pin(smem);
+  const uint32_t sQ = smem;                      // [NT][2] 16 KB
+  const uint32_t sK = sQ + 2 * NT * Q_TILE;      // [KSK] 8 KB
+  const uint32_t sV = sK + KSK * KV_TILE;        // [KSV] 8 KB
+  uint32_t bars = smem + TILE_BYTES;
+  pin(bars);
+  auto bar = [&](int slot) -> uint32_t { return bars + 8u * slot; };
+  const uint32_t tmem_slot = bars + 8 * B_COUNT;
+
+  uint32_t tid = threadIdx.x;
+  pin(tid);
+  const int warp = tid >> 5, lane = tid & 31;
+  const int num_kv = (len_kv + BKV - 1) / BKV;
+  const int last_valid = len_kv - (num_kv - 1) * BKV;  // keys in the last KV tile (1..64)
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmK);
+    prefetch_tensormap(&tmV);
+    for (int i = 0; i < 2 * NT; ++i) {
+      bar_init(bar(B_Q_FULL + i), 1);
+      bar_init(bar(B_Q_EMPTY + i), 1);
+      bar_init(bar(B_Q_ROT + i), 1);
+    }
+    for (int i = 0; i < KSK; ++i) {
+      bar_init(bar(B_K_FULL + i), 1);
+      bar_init(bar(B_K_EMPTY + i), 1);
+      bar_init(bar(B_K_ROT + i), 1);
+    }
+    for (int i = 0; i < KSV; ++i) {
+      bar_init(bar(B_V_FULL + i), 1);
+      bar_init(bar(B_V_EMPTY + i), 1);
+    }
+    for (int s = 0; s < NT; ++s) {
+      bar_init(bar(B_S_FULL + s), 1);
+      bar_init(bar(B_S_FREE + s), 4);  // one arrival per softmax warp of the slot
+      bar_init(bar(B_P_READY + s), 4);
+      bar_init(bar(B_PV_DONE + s), 1);
+      bar_init(bar(B_O_FREE + s), 4);
+    }
+    for (int i = 0; i < 4 * NT; ++i) bar_init(bar(B_TOK + i), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    setmaxnreg_dec<56>();
+    if (warp == 0) {
+      // ----------------------- TMA producer: Q tiles of the item, then K_j, V_j -----------------------
+      if (elect_one()) {
+        int kst = 0, vst = 0;
+        uint32_t kph = 1, vph = 1;  // "empty" barriers: the first pass over a ring does not block
+        uint32_t qcnt[NT] = {0, 0, 0};
+        for (int k = 0; k < my_items; ++k) {
+          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+#pragma unroll
+          for (int s = 0; s < NT; ++s) {
+            if (s < it.n_act) {
+              const int qi = s * 2 + (qcnt[s] & 1);
+              bar_wait(bar(B_Q_EMPTY + qi), ((qcnt[s] >> 1) & 1) ^ 1);
+              bar_expect_tx(bar(B_Q_FULL + qi), Q_TILE);
+              tma4(sQ + qi * Q_TILE, &tmQ, bar(B_Q_FULL + qi), 0, it.h, (it.g * NT + s) * BQ, it.b);
+              ++qcnt[s];
+            }
+          }
+          for (int j = 0; j < num_kv; ++j) {
+            bar_wait(bar(B_K_EMPTY + kst), kph);
+            bar_expect_tx(bar(B_K_FULL + kst), KV_TILE);
+            tma4(sK + kst * KV_TILE, &tmK, bar(B_K_FULL + kst), 0, it.h, j * BKV, it.b);
+            if (++kst == KSK) {
+              kst = 0;
+              kph ^= 1;
+            }
+            bar_wait(bar(B_V_EMPTY + vst), vph);
+            bar_expect_tx(bar(B_V_FULL + vst), KV_TILE);
+            tma4(sV + vst * KV_TILE, &tmV, bar(B_V_FULL + vst), 0, it.h, j * BKV, it.b);
+            if (++vst == KSV) {
+              vst = 0;
+              vph ^= 1;
+            }
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ------------- rotary warp: rotate head dims 0..5 of the landed Q / K tiles in place -------------
+      if (rope != nullptr) {
+        int kst = 0;
+        uint32_t kph = 0;
+        uint32_t qcnt[NT] = {0, 0, 0};
+        for (int k = 0; k < my_items; ++k) {
+          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+#pragma unroll
+          for (int s = 0; s < NT; ++s) {
+            if (s < it.n_act) {
+              const int qi = s * 2 + (qcnt[s] & 1);
+              bar_wait(bar(B_Q_FULL + qi), (qcnt[s] >> 1) & 1);
+              const int q0 = (it.g * NT + s) * BQ;
+              for (int r = lane; r < BQ; r += 32)
+                if (q0 + r < len_q) rope_row(sQ + qi * Q_TILE, r, rope + ((int64_t)it.b * len_q + q0 + r) * 3);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) bar_arrive(bar(B_Q_ROT + qi));
+              ++qcnt[s];
+            }
+          }
+          for (int j = 0; j < num_kv; ++j) {
+            bar_wait(bar(B_K_FULL + kst), kph);
+            for (int r = lane; r < BKV; r += 32)
+              if (j * BKV + r < len_kv) rope_row(sK + kst * KV_TILE, r, rope + ((int64_t)it.b * len_kv + j * BKV + r) * 3);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) bar_arrive(bar(B_K_ROT + kst));
+            if (++kst == KSK) {
+              kst = 0;
+              kph ^= 1;
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------ QK^T issuer: S[s] = Q[s] K_j^T for every active slot ------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_full = idesc_bf16_f32(BQ, BKV, 0);
+        const uint32_t idesc_last = idesc_bf16_f32(BQ, max(16, (last_valid + 15) & ~15), 0);
+        const int qbar = rope != nullptr ? B_Q_ROT : B_Q_FULL;
+        const int kbar = rope != nullptr ? B_K_ROT : B_K_FULL;
+        int kst = 0;
+        uint32_t kph = 0;
+        uint32_t qcnt[NT] = {0, 0, 0};
+        uint32_t su[NT] = {0, 0, 0};  // S products issued per slot
+        for (int k = 0; k < my_items; ++k) {
+          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+          uint64_t adesc[NT];
+          int qi[NT];
+#pragma unroll
+          for (int s = 0; s < NT; ++s) {
+            qi[s] = s * 2 + (qcnt[s] & 1);
+            adesc[s] = smem_desc_sw128(sQ + qi[s] * Q_TILE);
+            if (s < it.n_act) {
+              bar_wait(bar(qbar + qi[s]), (qcnt[s] >> 1) & 1);
+              ++qcnt[s];
+            }
+          }
+          for (int j = 0; j < num_kv; ++j) {
+            bar_wait(bar(kbar + kst), kph);
+            const bool last = (j == num_kv - 1);
+            const uint32_t idesc = last ? idesc_last : idesc_full;
+            const uint64_t bdesc = smem_desc_sw128(sK + kst * KV_TILE);
+#pragma unroll
+            for (int s = 0; s < NT; ++s) {
+              if (s < it.n_act) {
+                bar_wait(bar(B_S_FREE + s), (su[s] & 1) ^ 1);  // previous S of the slot sits in registers
+                ++su[s];
+                tcgen05_fence_after();
+                const uint32_t s_tmem = tmem_base + s_col(s);
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(s_tmem, adesc[s] + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
+                commit(bar(B_S_FULL + s));
+              }
+            }
+            commit(bar(B_K_EMPTY + kst));
+            if (last) {
+#pragma unroll
+              for (int s = 0; s < NT; ++s)
+                if (s < it.n_act) commit(bar(B_Q_EMPTY + qi[s]));
+            }
+            if (++kst == KSK) {
+              kst = 0;
+              kph ^= 1;
+            }
+          }
+        }
+      }
+    } else {
+      // -------------------------- PV issuer: O[s] += P[s] V_j --------------------------
+      if (elect_one()) {
+        constexpr uint32_t idesc_pv = idesc_bf16_f32(BQ, HD, /*B MN-major*/ 1);
+        const int nks_last = (last_valid + 15) >> 4;
+        int vst = 0;
+        uint32_t vph = 0;
+        uint32_t pu[NT] = {0, 0, 0};   // PV products issued per slot
+        uint32_t ni[NT] = {0, 0, 0};   // items the slot took part in
+        for (int k = 0; k < my_items; ++k) {
+          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+          for (int j = 0; j < num_kv; ++j) {
+            bar_wait(bar(B_V_FULL + vst), vph);
+            const int nks = (j == num_kv - 1) ? nks_last : BKV / 16;
+            const uint32_t v_addr = sV + vst * KV_TILE;
+#pragma unroll
+            for (int s = 0; s < NT; ++s) {
+              if (s < it.n_act) {
+                if (j == 0 && ni[s] > 0) bar_wait(bar(B_O_FREE + s), (ni[s] - 1) & 1);  // previous O read out
+                bar_wait(bar(B_P_READY + s), pu[s] & 1);
+                ++pu[s];
+                tcgen05_fence_after();
+                const uint32_t o_tmem = tmem_base + o_col(s), p_tmem = tmem_base + p_col(s);
+                for (int kk = 0; kk < nks; ++kk)
+                  umma_bf16_ts(o_tmem, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0);
+                commit(bar(B_PV_DONE + s));
+              }
+            }
+            commit(bar(B_V_EMPTY + vst));
+            if (++vst == KSV) {
+              vst = 0;
+              vph ^= 1;
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < NT; ++s)
+            if (s < it.n_act) ++ni[s];
+        }
+      }
+    }
+  } else {
+    setmaxnreg_inc<152>();
+    // --------------------------- softmax: thread = query row ----------------------------
+    const int slot = (warp - 4) >> 2, quarter = warp & 3;
+    uint32_t tm = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    pin(tm);
+    const uint32_t b_sfull = bars + 8 * (B_S_FULL + slot), b_sfree = bars + 8 * (B_S_FREE + slot),
+                   b_pready = bars + 8 * (B_P_READY + slot), b_pvdone = bars + 8 * (B_PV_DONE + slot),
+                   b_ofree = bars + 8 * (B_O_FREE + slot), b_tok = bars + 8 * (B_TOK + quarter * NT);
+    uint32_t u = 0;    // tiles this slot has processed (parity of S_FULL / P_READY / PV_DONE uses)
+    uint32_t tk = 0;   // token acquisitions of this warp
+    const uint64_t sc2 = pack2(scale_log2, scale_log2);
+
+    for (int k = 0; k < my_items; ++k) {
+      const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+      if (slot >= it.n_act) continue;
+      const int q0 = (it.g * NT + slot) * BQ;
+      if (q0 + quarter * 32 >= len_q) {
+        // no real query row in this warp (ragged last query tile): keep the slot's barrier counts in step
+        for (int j = 0; j < num_kv; ++j) {
+          if (lane == 0) {
+            bar_arrive(b_sfree);
+            bar_arrive(b_pready);
+          }
+          bar_wait(b_pready, u & 1);  // all four warps of the slot are past this tile
+          ++u;
+        }
+        if (lane == 0) bar_arrive(b_ofree);
+        continue;
+      }
+      // slots of this item whose quarter holds real rows (a prefix): the members of this scheduler's token ring
+      int ring = 0;
+#pragma unroll
+      for (int s = 0; s < NT; ++s) ring += (s < it.n_act && (it.g * NT + s) * BQ + quarter * 32 < len_q) ? 1 : 0;
+      const uint32_t tok_next = b_tok + 8 * ((slot + 1 < ring) ? slot + 1 : 0);
+
+      float m_used = 0.f, l_run = 0.f;
+      for (int j = 0; j < num_kv; ++j) {
+        uint32_t r[BKV];
+        bar_wait(b_sfull, u & 1);
+        tcgen05_fence_after();
+        tmem_ld_32x32b_x32(tm + s_col(slot), r);
+        tmem_ld_32x32b_x32(tm + s_col(slot) + 32, r + 32);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(b_sfree);  // S sits in registers: the next QK^T of the slot may overwrite it
+        const int nvalid = (j == num_kv - 1) ? last_valid : BKV;
+        if (nvalid < BKV) {
+#pragma unroll
+          for (int i = 0; i < BKV; ++i)
+            if (i >= nvalid) r[i] = 0xff800000u;  // -inf
+        }
+        float mx;
+        {
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < BKV; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+          }
+          mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+        }
+        // P buffer / O of the slot are free once the previous PV product has completed
+        bar_wait(b_pvdone, (u & 1) ^ 1);
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          // lazy rescale of O and l when the maximum grows by more than 2^8 (rare)
+          const bool grow = mx > m_used + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, grow)) {
+            tcgen05_fence_after();
+            const float alpha = grow ? ex2_approx(m_used - mx) : 1.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(tm + o_col(slot) + h * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x32b_x32(tm + o_col(slot) + h * 32, o);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+            if (grow) m_used = mx;
+          }
+        }
+        const uint64_t nm2 = pack2(-m_used, -m_used);
+        // ---- exponentials, under this scheduler's MUFU token ----
+        if (TOKEN) bar_wait(b_tok + 8 * slot, slot == 0 ? ((tk & 1) ^ 1) : (tk & 1));
+        ++tk;
+        tcgen05_fence_after();
+        uint64_t sum_a = 0ull, sum_b = 0ull;
+#pragma unroll
+        for (int c = 0; c < BKV / 16; ++c) {
+          if (c * 16 < nvalid) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const int e = c * 16 + i;
+              const uint64_t xa = fma2(pack2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), sc2, nm2);
+              const uint64_t xb = fma2(pack2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), sc2, nm2);
+              float a0, a1, b0, b1;
+              unpack2(xa, a0, a1);
+              unpack2(xb, b0, b1);
+              const float p0 = ex2v(a0), p1 = ex2v(a1), p2 = ex2v(b0), p3 = ex2v(b1);
+              sum_a = add2(sum_a, pack2(p0, p1));
+              sum_b = add2(sum_b, pack2(p2, p3));
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+              pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+            tmem_st_32x32b_x8(tm + p_col(slot) + c * 8, pk);
+          }
+          if (TOKEN && c == 2) {
+            // pass the token on one group early: the next warp's wake-up overlaps the last 16 exponentials
+            __syncwarp();
+            if (lane == 0) bar_arrive(tok_next);
+          }
+        }
+        {
+          float s0, s1, s2, s3;
+          unpack2(sum_a, s0, s1);
+          unpack2(sum_b, s2, s3);
+          l_run += (s0 + s1) + (s2 + s3);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(b_pready);  // P in TMEM -> PV may be issued
+        ++u;
+      }
+      // ---- epilogue: O / l -> global ----
+      bar_wait(b_pvdone, (u & 1) ^ 1);  // every PV product of the item has landed in O
+      tcgen05_fence_after();
+      uint32_t o[HD];
+      tmem_ld_32x32b_x32(tm + o_col(slot), o);
+      tmem_ld_32x32b_x32(tm + o_col(slot) + 32, o + 32);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(b_ofree);  // O is in registers: the slot's next item may overwrite it
+      const int row = q0 + quarter * 32 + lane;
+      if (row < len_q) {
+        uint16_t* orow = out + it.b * o_bs + (int64_t)row * o_ls + it.h * HD;
+        const float inv = 1.f / l_run;
+#pragma unroll
+        for (int i = 0; i < HD; i += 8) {
+          float v[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(o[i + t]) * inv;
+          *reinterpret_cast<uint4*>(orow + i) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace a8
+
+template <int TOKEN>
+static int launch_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out, int64_t o_bs,
+                      int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
+                      cudaStream_t st) {
+  auto kern = a8::attn_bf16_tc8_kernel<TOKEN>;
+  // the attribute is per device: set it on every launch (cheap) rather than caching a per-process flag
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a8::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    set_error("attention_bf16: kernel attribute setup (%d B smem): %s", a8::SMEM_BYTES, cudaGetErrorString(e));
+    return PCD_ERR_CUDA;
+  }
+  const int nq = ceil_div(len_q, a8::BQ);
+  const int ngroups = ceil_div(nq, a8::NT);
+  const int64_t n_items64 = (int64_t)ngroups * heads * batch;
+  if (n_items64 > 0x7fffffff) {
+    set_error("attention_bf16: too many (query group, head, sequence) items");
+    return PCD_ERR_INVALID;
+  }
+  const int n_items = (int)n_items64;
+  const int grid = min(n_items, num_sms());  // one CTA per SM: 162 KB shared memory, all 512 TMEM columns
+  kern<<<grid, 512, a8::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2, nq, ngroups, heads,
+                                          n_items, rope);
+  PCD_CHECK_LAUNCH("attention_bf16");
+  return PCD_OK;
+}
+
+// token: 1 = MUFU hand-off ring (default), 0 = free-running softmax warps (A/B measurement of the ring)
+int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out, int64_t o_bs,
+                    int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
+                    int token, cudaStream_t st) {
+  if (token) return launch_tc8<1>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  return launch_tc8<0>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, rope, st);
+}
+
+}  // namespace pcd

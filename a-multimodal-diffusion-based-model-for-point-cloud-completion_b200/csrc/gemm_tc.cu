@@ -279,8 +279,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-extern int g_gemm_debug;
-
 // ---------------------------------------------------------------------------
 // CTA-pair kernel (cta_group::2): two CTAs of a cluster compute one 256 x 256 tile.  Each CTA
 // stages its own 128 rows of A and HALF of the W tile (128 of the 256 N rows); the leader's MMA
@@ -724,17 +722,15 @@ struct LnArgs {  // extra operands of the residual+statistics and LayerNorm-fold
 template <int EPI, bool OUT_BF16, bool DEEPK = false>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC,
                         const CUtensorMap& tmR, const float* bias, int M, int N, int K, cudaStream_t st,
-                        const LnArgs* ln = nullptr) {
+                        const LnArgs* ln, int dbg) {
   using Cfg = Gemm2Cfg<EPI, DEEPK>;
   auto kern = gemm_bf16_tc2_kernel<EPI, OUT_BF16, DEEPK>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device, not per process: set on every launch (a host-side table lookup)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_bf16(pair): cudaFuncSetAttribute(%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return PCD_ERR_CUDA;
     }
-    attr_set = true;
   }
   const int tiles = ceil_div(M, 2 * G_BM) * ceil_div(N, Cfg::BN);
   int pairs = num_sms() / 2;
@@ -742,77 +738,73 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmW, const CU
   static const LnArgs none = {};
   const LnArgs& x = ln ? *ln : none;
   kern<<<2 * pairs, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, ln ? x.tmC2 : tmC, bias, x.colsum, x.stats_in,
-                                                       x.stats_in_slots, x.stats_out, x.ln_eps, M, N, K, g_gemm_debug);
+                                                       x.stats_in_slots, x.stats_out, x.ln_eps, M, N, K, dbg);
   PCD_CHECK_LAUNCH("gemm_bf16(pair)");
   return PCD_OK;
 }
 
 static int dispatch_epi2(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& c, const CUtensorMap& r,
                          const float* bias, int out_prec, int M, int N, int K, int epi, cudaStream_t st,
-                         const LnArgs* ln = nullptr) {
+                         const LnArgs* ln, int dbg) {
   const bool ob = out_prec == PCD_BF16;
   switch (epi) {
     case PCD_EPI_RESIDUAL_STATS:
       if (ob || ln == nullptr) break;
-      if (K >= 1024) return launch_gemm2<PCD_EPI_RESIDUAL_STATS, false, true>(a, w, c, r, bias, M, N, K, st, ln);
-      return launch_gemm2<PCD_EPI_RESIDUAL_STATS, false>(a, w, c, r, bias, M, N, K, st, ln);
+      if (K >= 1024) return launch_gemm2<PCD_EPI_RESIDUAL_STATS, false, true>(a, w, c, r, bias, M, N, K, st, ln, dbg);
+      return launch_gemm2<PCD_EPI_RESIDUAL_STATS, false>(a, w, c, r, bias, M, N, K, st, ln, dbg);
     case PCD_EPI_LN_BIAS:
       if (!ob || ln == nullptr) break;
-      return launch_gemm2<PCD_EPI_LN_BIAS, true>(a, w, c, r, bias, M, N, K, st, ln);
+      return launch_gemm2<PCD_EPI_LN_BIAS, true>(a, w, c, r, bias, M, N, K, st, ln, dbg);
     case PCD_EPI_LN_BIAS_GELU:
       if (!ob || ln == nullptr) break;
-      return launch_gemm2<PCD_EPI_LN_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st, ln);
+      return launch_gemm2<PCD_EPI_LN_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st, ln, dbg);
     case PCD_EPI_BIAS:
-      return ob ? launch_gemm2<PCD_EPI_BIAS, true>(a, w, c, r, bias, M, N, K, st)
-                : launch_gemm2<PCD_EPI_BIAS, false>(a, w, c, r, bias, M, N, K, st);
+      return ob ? launch_gemm2<PCD_EPI_BIAS, true>(a, w, c, r, bias, M, N, K, st, nullptr, dbg)
+                : launch_gemm2<PCD_EPI_BIAS, false>(a, w, c, r, bias, M, N, K, st, nullptr, dbg);
     case PCD_EPI_BIAS_GELU:
-      return ob ? launch_gemm2<PCD_EPI_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st)
-                : launch_gemm2<PCD_EPI_BIAS_GELU, false>(a, w, c, r, bias, M, N, K, st);
+      return ob ? launch_gemm2<PCD_EPI_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st, nullptr, dbg)
+                : launch_gemm2<PCD_EPI_BIAS_GELU, false>(a, w, c, r, bias, M, N, K, st, nullptr, dbg);
     case PCD_EPI_BIAS_RESIDUAL:
       if (ob) break;
-      return launch_gemm2<PCD_EPI_BIAS_RESIDUAL, false>(a, w, c, r, bias, M, N, K, st);
+      return launch_gemm2<PCD_EPI_BIAS_RESIDUAL, false>(a, w, c, r, bias, M, N, K, st, nullptr, dbg);
   }
   set_error("gemm_bf16: unsupported epilogue %d / output precision %d", epi, out_prec);
   return PCD_ERR_INVALID;
 }
 
-int g_gemm_debug = 0;  // profiling aid, see pcd_set_debug_flags (bit 2: force the single-CTA kernel)
-
 template <int BN, int EPI, bool OUT_BF16>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmC,
-                       const CUtensorMap& tmR, const float* bias, int M, int N, int K, cudaStream_t st) {
+                       const CUtensorMap& tmR, const float* bias, int M, int N, int K, cudaStream_t st, int dbg) {
   using Cfg = GemmCfg<BN, EPI>;
   auto kern = gemm_bf16_tc_kernel<BN, EPI, OUT_BF16>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_bf16: cudaFuncSetAttribute(%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return PCD_ERR_CUDA;
     }
-    attr_set = true;
   }
   int tiles = ceil_div(M, G_BM) * ceil_div(N, BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, bias, M, N, K, g_gemm_debug);
+  kern<<<grid, G_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tmR, bias, M, N, K, dbg);
   PCD_CHECK_LAUNCH("gemm_bf16");
   return PCD_OK;
 }
 
 template <int BN>
 static int dispatch_epi(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& c, const CUtensorMap& r,
-                        const float* bias, int out_prec, int M, int N, int K, int epi, cudaStream_t st) {
+                        const float* bias, int out_prec, int M, int N, int K, int epi, cudaStream_t st, int dbg) {
   const bool ob = out_prec == PCD_BF16;
   switch (epi) {
     case PCD_EPI_BIAS:
-      return ob ? launch_gemm<BN, PCD_EPI_BIAS, true>(a, w, c, r, bias, M, N, K, st)
-                : launch_gemm<BN, PCD_EPI_BIAS, false>(a, w, c, r, bias, M, N, K, st);
+      return ob ? launch_gemm<BN, PCD_EPI_BIAS, true>(a, w, c, r, bias, M, N, K, st, dbg)
+                : launch_gemm<BN, PCD_EPI_BIAS, false>(a, w, c, r, bias, M, N, K, st, dbg);
     case PCD_EPI_BIAS_GELU:
-      return ob ? launch_gemm<BN, PCD_EPI_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st)
-                : launch_gemm<BN, PCD_EPI_BIAS_GELU, false>(a, w, c, r, bias, M, N, K, st);
+      return ob ? launch_gemm<BN, PCD_EPI_BIAS_GELU, true>(a, w, c, r, bias, M, N, K, st, dbg)
+                : launch_gemm<BN, PCD_EPI_BIAS_GELU, false>(a, w, c, r, bias, M, N, K, st, dbg);
     case PCD_EPI_BIAS_RESIDUAL:
       if (ob) break;
-      return launch_gemm<BN, PCD_EPI_BIAS_RESIDUAL, false>(a, w, c, r, bias, M, N, K, st);
+      return launch_gemm<BN, PCD_EPI_BIAS_RESIDUAL, false>(a, w, c, r, bias, M, N, K, st, dbg);
   }
   set_error("gemm_bf16: unsupported epilogue %d / output precision %d", epi, out_prec);
   return PCD_ERR_INVALID;
@@ -839,7 +831,8 @@ static int gemm_bf16_impl(const pcd_gemm_args& g, void* stream) {
   const bool lnfold = epilogue == PCD_EPI_LN_BIAS || epilogue == PCD_EPI_LN_BIAS_GELU;
   PCD_CHECK_ARG(!resid || (residual != nullptr && ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && !ob),
                 "gemm_bf16: residual epilogue needs an fp32, 16-byte aligned residual and fp32 output");
-  const bool use_pair = (N % 256 == 0) && M >= 512 && !(g_gemm_debug & 4);
+  const int dbg = g.debug;
+  const bool use_pair = (N % 256 == 0) && M >= 512 && !(dbg & 4);
   if (epilogue == PCD_EPI_RESIDUAL_STATS) {
     PCD_CHECK_ARG(use_pair, "gemm_bf16: the residual+statistics epilogue needs N %% 256 == 0 and M >= 512 (N=%d M=%d)", N, M);
     PCD_CHECK_ARG(g.C2 != nullptr && g.ldc2 % 8 == 0 && (reinterpret_cast<uintptr_t>(g.C2) & 15) == 0 && g.stats_out != nullptr,
@@ -889,11 +882,11 @@ static int gemm_bf16_impl(const pcd_gemm_args& g, void* stream) {
     ln.stats_in_slots = K / 128;
     ln.stats_out = reinterpret_cast<float2*>(g.stats_out);
     ln.ln_eps = g.ln_eps;
-    return dispatch_epi2(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st, &ln);
+    return dispatch_epi2(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st, &ln, dbg);
   }
-  if (use_pair) return dispatch_epi2(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st);
-  if (BN == 256) return dispatch_epi<256>(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st);
-  return dispatch_epi<128>(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st);
+  if (use_pair) return dispatch_epi2(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st, nullptr, dbg);
+  if (BN == 256) return dispatch_epi<256>(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st, dbg);
+  return dispatch_epi<128>(tmA, tmW, tmC, tmR, g.bias, out_precision, M, N, K, epilogue, st, dbg);
 }
 
 extern "C" int pcd_gemm_bf16_ex(const pcd_gemm_args* args, void* stream) {

@@ -19,15 +19,17 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+int num_sms() {  // of the CURRENT device (a process may drive more than one)
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -92,15 +94,13 @@ int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const floa
                      int len, cudaStream_t st);
 int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                           uint16_t* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
-                          int len_kv, float q_scale, float k_scale, cudaStream_t st);
-extern int g_attn_variant;
-extern int g_gemm_debug;
+                          int len_kv, float q_scale, float k_scale, const float* rope, int variant, cudaStream_t st);
 
 }  // namespace pcd
 
 using namespace pcd;
 
-extern "C" int pcd_abi_version(void) { return 2; }
+extern "C" int pcd_abi_version(void) { return 3; }
 extern "C" unsigned long long pcd_launch_count(void) { return g_launch_count; }
 extern "C" const char* pcd_last_error(void) { return g_err; }
 
@@ -121,26 +121,6 @@ extern "C" int pcd_check_device(void) {
   return PCD_OK;
 }
 
-// Tuning/testing knob (not part of the reference-facing surface): 1 = P kept in TMEM
-// (tcgen05.mma A-from-TMEM, 2 CTAs/SM), 0 = P staged in swizzled shared memory.
-// Profiling aid (results are WRONG when set): bit 0 = GEMM epilogue skipped, bit 1 = GEMM TMA
-// loads skipped.  Used by tools/ to separate main-loop from epilogue time.
-static int g_disable_ln_fold = 0;  // debug flag bit 4: run the forward with separate LayerNorm kernels
-extern "C" int pcd_set_debug_flags(int flags) {
-  g_gemm_debug = flags & 15;
-  g_disable_ln_fold = (flags >> 4) & 1;
-  return PCD_OK;
-}
-
-constexpr int kDefaultAttnVariant = 5;
-extern "C" int pcd_default_attention_variant(void) { return kDefaultAttnVariant; }
-
-extern "C" int pcd_set_attention_variant(int v) {
-  PCD_CHECK_ARG(v >= 0 && v <= 7, "attention variant must be 0..7");
-  g_attn_variant = v;
-  return PCD_OK;
-}
-
 static bool operand_ok(const pcd_attn_operand* o, int align_elems, size_t elem) {
   return o && o->ptr && (reinterpret_cast<uintptr_t>(o->ptr) % (align_elems * elem) == 0) &&
          o->row_stride % align_elems == 0 && o->head_stride % align_elems == 0 &&
@@ -150,7 +130,7 @@ static bool operand_ok(const pcd_attn_operand* o, int align_elems, size_t elem) 
 extern "C" int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                              void* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
                              int len_kv, float q_scale, float k_scale, const float* rope_coords,
-                             int precision, void* stream) {
+                             int precision, int variant, void* stream) {
   PCD_CHECK_ARG(batch > 0 && heads > 0 && len_q > 0 && len_kv > 0, "attention: empty problem");
   PCD_CHECK_ARG(batch <= 65535 && heads <= 65535, "attention: batch/heads exceed grid limits");
   PCD_CHECK_ARG(q_scale > 0.f && k_scale > 0.f, "attention: scales must be positive");
@@ -164,11 +144,8 @@ extern "C" int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* 
   if (precision == PCD_BF16) {
     PCD_CHECK_ARG(operand_ok(q, 8, 2) && operand_ok(k, 8, 2) && operand_ok(v, 8, 2), "attention(bf16): operands must be 16-byte aligned with strides %% 8 == 0");
     PCD_CHECK_ARG(o_ls % 8 == 0 && o_bs % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "attention(bf16): output must be 16-byte aligned with strides %% 8 == 0");
-    if (rope_coords != nullptr) {
-      set_error("attention(bf16): apply the rotation with pcd_rope_bf16 (in place on q and k) before the tensor-core kernel");
-      return PCD_ERR_UNSUPPORTED;
-    }
-    return launch_attention_bf16(q, k, v, (uint16_t*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, st);
+    return launch_attention_bf16(q, k, v, (uint16_t*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale,
+                                 rope_coords, variant, st);
   }
   PCD_CHECK_ARG(false, "attention: unknown precision %d", precision);
 }
@@ -324,7 +301,8 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
   // LayerNorm kernels at all.  The c_proj / mlp.c_proj GEMMs update the fp32 residual stream in their
   // epilogue and emit its bf16 copy + per-row statistics; c_qkv / c_fc consume that copy with
   // W' = gamma o W and apply mean / rstd algebraically in their epilogue (gemm_tc.cu).
-  bool fold = bf && W % 256 == 0 && M >= 512 && !g_disable_ln_fold;
+  bool fold = bf && W % 256 == 0 && M >= 512 && !(d.flags & PCD_MODEL_SEPARATE_LAYERNORM);
+  const int attn_variant = (d.flags >> PCD_MODEL_ATTN_VARIANT_SHIFT) & 0xff;
   for (int l = 0; l < d.layers && fold; ++l) {
     const pcd_block_weights& b = m->blocks[l];
     fold = b.w_qkv_ln && b.w_fc_ln && b.qkv_colsum && b.qkv_const && b.fc_colsum && b.fc_const;
@@ -350,7 +328,7 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
       pcd_attn_operand q = {w.qkv, (int64_t)L * 3 * W, 3 * W, 3 * 64};
       pcd_attn_operand k = {(const unsigned char*)w.qkv + 64 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
       pcd_attn_operand v = {(const unsigned char*)w.qkv + 128 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
-      PCD_TRY(pcd_attention(&q, &k, &v, w.att, (int64_t)L * W, W, seqs, d.heads, L, L, qk_scale, qk_scale, nullptr, prec, stream));
+      PCD_TRY(pcd_attention(&q, &k, &v, w.att, (int64_t)L * W, W, seqs, d.heads, L, L, qk_scale, qk_scale, nullptr, prec, attn_variant, stream));
       PCD_TRY(lin_res(w.att, W, b.w_proj, b.b_proj));
       PCD_TRY(lin_ln(b.w_fc_ln, b.fc_colsum, b.fc_const, w.hid, 4 * W, PCD_EPI_LN_BIAS_GELU));
       PCD_TRY(lin_res(w.hid, 4 * W, b.w_fc2, b.b_fc2));
@@ -370,7 +348,7 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
     pcd_attn_operand q = {w.qkv, (int64_t)L * 3 * W, 3 * W, 3 * 64};
     pcd_attn_operand k = {(const unsigned char*)w.qkv + 64 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
     pcd_attn_operand v = {(const unsigned char*)w.qkv + 128 * es, (int64_t)L * 3 * W, 3 * W, 3 * 64};
-    PCD_TRY(pcd_attention(&q, &k, &v, w.att, (int64_t)L * W, W, seqs, d.heads, L, L, qk_scale, qk_scale, nullptr, prec, stream));
+    PCD_TRY(pcd_attention(&q, &k, &v, w.att, (int64_t)L * W, W, seqs, d.heads, L, L, qk_scale, qk_scale, nullptr, prec, attn_variant, stream));
     PCD_TRY(gemm(w.att, W, b.w_proj, b.b_proj, w.y, W, W, PCD_EPI_BIAS));
     PCD_TRY(pcd_add_layernorm(w.h, W, w.y, W, prec, b.ln2_g, b.ln2_b, w.xn, W, prec, M, W, d.ln_eps, stream));
     PCD_TRY(gemm(w.xn, W, b.w_fc, b.b_fc, w.hid, 4 * W, W, PCD_EPI_BIAS_GELU));

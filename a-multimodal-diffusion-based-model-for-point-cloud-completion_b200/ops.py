@@ -95,6 +95,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     ldr = 0
     if residual is not None:
         assert residual.dtype == torch.float32
+        if epilogue == EPI_BIAS_GELU:
+            raise ValueError("linear: a residual cannot be combined with the GELU epilogue")
         r2 = residual.reshape(-1, N) if residual.dim() != 2 else residual
         ldr = _rowmajor2d(r2)
         epilogue = EPI_BIAS_RESIDUAL
@@ -200,16 +202,17 @@ def _operand(t: torch.Tensor, offset: int, batch_stride: int, row_stride: int, h
 
 
 def attention_packed(q_op, k_op, v_op, out: torch.Tensor, batch: int, heads: int, len_q: int, len_kv: int,
-                     q_scale: float, k_scale: float, rope_coords: Optional[torch.Tensor] = None):
-    """Low-level call: operands are ``AttnOperand`` views; ``out`` is [batch, len_q, heads*64]."""
+                     q_scale: float, k_scale: float, rope_coords: Optional[torch.Tensor] = None, variant: int = 0):
+    """Low-level call: operands are ``AttnOperand`` views; ``out`` is [batch, len_q, heads*64]; ``variant`` picks
+    the tensor-core kernel (``_lib.ATTN_*``, 0 = default) for this call."""
     require_cuda(out)
     check(_lib.load().pcd_attention(C.byref(q_op), C.byref(k_op), C.byref(v_op), ptr(out), out.stride(0),
                                     out.stride(1), batch, heads, len_q, len_kv, float(q_scale), float(k_scale),
-                                    ptr(rope_coords), _PREC[out.dtype], stream_ptr()), "attention")
+                                    ptr(rope_coords), _PREC[out.dtype], int(variant), stream_ptr()), "attention")
     return out
 
 
-def self_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+def self_attention(qkv: torch.Tensor, heads: int, variant: int = 0) -> torch.Tensor:
     """QKVMultiheadAttention (reference models/transformer.py:65-84): qkv [B, L, H*3*64]
     laid out [H][q|k|v][64]; q and k each scaled by 64**-0.25."""
     B, L, W3 = qkv.shape
@@ -219,10 +222,10 @@ def self_attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     out = torch.empty(B, L, heads * hd, device=qkv.device, dtype=qkv.dtype)
     s = 1.0 / math.sqrt(math.sqrt(hd))
     ops = [_operand(qkv, i * hd, L * W3, W3, 3 * hd) for i in range(3)]
-    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, L, L, s, s)
+    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, L, L, s, s, variant=variant)
 
 
-def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int) -> torch.Tensor:
+def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int, variant: int = 0) -> torch.Tensor:
     """QKVMultiheadCrossAttention (reference models/perceiver.py:46-67): q [B, Lq, H*64],
     kv [B, Lkv, H*2*64] laid out [H][k|v][64]."""
     B, Lq, W = q.shape
@@ -235,7 +238,7 @@ def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int) -> torch.Tens
     qo = _operand(q, 0, Lq * W, W, hd)
     ko = _operand(kv, 0, Lkv * W2, W2, 2 * hd)
     vo = _operand(kv, hd, Lkv * W2, W2, 2 * hd)
-    return attention_packed(qo, ko, vo, out, B, heads, Lq, Lkv, s, s)
+    return attention_packed(qo, ko, vo, out, B, heads, Lq, Lkv, s, s, variant=variant)
 
 
 def attention_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, q_scale: float,
@@ -254,25 +257,29 @@ def attention_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
 
 def rotary_attention(qkv: torch.Tensor, coords: torch.Tensor, heads: int) -> torch.Tensor:
     """RotarySelfAttention core (reference models/rotaryencoderpcd.py:68-84): qkv [B, N, 3*D]
-    laid out [3][H][64]; 3-axis RoPE on head dims 0..5 of q and k; logits * D**-0.5."""
+    laid out [3][H][64]; 3-axis RoPE on head dims 0..5 of q and k; logits * D**-0.5.  One launch in either
+    precision: the rotation happens inside the attention kernel (fp32: in registers while the tiles are loaded;
+    bf16: on the Q / K tiles in shared memory between their TMA arrival and the first MMA)."""
     B, N, D3 = qkv.shape
     D = D3 // 3
     assert D // heads == 64
     qkv = qkv.contiguous()
     coords = coords.to(torch.float32).contiguous()
+    assert coords.shape == (B, N, 3)
     out = torch.empty(B, N, D, device=qkv.device, dtype=qkv.dtype)
     ops = [_operand(qkv, i * D, N * D3, D3, 64) for i in range(3)]
-    if qkv.dtype == torch.float32:  # RoPE applied in registers while the tiles are loaded
-        return attention_packed(ops[0], ops[1], ops[2], out, B, heads, N, N, D ** -0.5, 1.0, coords)
-    # bf16: the tensor-core kernel takes its tiles straight from TMA -> rotate q and k in place first
-    # (qkv is this call's own projection output / contiguous copy, never the caller's tensor)
-    assert qkv.dtype == torch.bfloat16
-    qkv = qkv.clone()
-    ops = [_operand(qkv, i * D, N * D3, D3, 64) for i in range(3)]
-    lib = _lib.load()
-    for o in ops[:2]:
-        check(lib.pcd_rope_bf16(C.byref(o), ptr(coords), B, heads, N, stream_ptr()), "rope_bf16")
-    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, N, N, D ** -0.5, 1.0)
+    return attention_packed(ops[0], ops[1], ops[2], out, B, heads, N, N, D ** -0.5, 1.0, coords)
+
+
+def rope_bf16_(x: torch.Tensor, coords: torch.Tensor, heads: int) -> torch.Tensor:
+    """Stand-alone rotation (pcd_rope_bf16): rotate head dims 0..5 of a bf16 [B, N, H*64] view IN PLACE."""
+    require_cuda(x, coords)
+    assert x.dtype == torch.bfloat16 and x.stride(2) == 1
+    B, N, _ = x.shape
+    coords = coords.to(torch.float32).contiguous()
+    o = _operand(x, 0, x.stride(0), x.stride(1), 64)
+    check(_lib.load().pcd_rope_bf16(C.byref(o), ptr(coords), B, heads, N, stream_ptr()), "rope_bf16")
+    return x
 
 
 def chamfer_distance_xyz(p1: torch.Tensor, p2: torch.Tensor) -> torch.Tensor:

@@ -167,6 +167,10 @@ class PointDiffusionTransformer(nn.Module):
         self._cond_key: Dict[int, Any] = {}
         self._cond_refs: Dict[int, Any] = {}
         self._addc: Dict[int, Optional[torch.Tensor]] = {}
+        # per-handle options (pcd_model_desc.flags): LayerNorm folded into the projections (bf16 mode) and the
+        # tensor-core attention kernel of the forward (_lib.ATTN_*, 0 = default)
+        self.fold_layernorm = True
+        self.attention_variant = 0
         self._pack_version = 0   # bumped whenever the packed weights move (CUDA graphs captured before are stale)
         self._time_tok: Dict[float, torch.Tensor] = {}
         self._tcond: Dict[int, torch.Tensor] = {}
@@ -185,7 +189,7 @@ class PointDiffusionTransformer(nn.Module):
     # ---- packing ----
     def _version_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple(
-            (b.data_ptr(), b._version) for b in self.buffers())
+            (b.data_ptr(), b._version) for b in self.buffers()) + (bool(self.fold_layernorm), int(self.attention_variant))
 
     def _ensure_handle(self):
         key = self._version_key()
@@ -237,6 +241,8 @@ class PointDiffusionTransformer(nn.Module):
         d.precision, d.width, d.heads, d.layers = prec, width, self.heads, len(self.backbone.resblocks)
         d.c_in, d.c_out, d.n_points = self.input_channels, self.output_channels, self.n_ctx
         d.n_prefix, d.time_slot, d.ln_eps = n_prefix, time_slot, LN_EPS
+        d.flags = ((0 if self.fold_layernorm else _lib.MODEL_SEPARATE_LAYERNORM)
+                   | (int(self.attention_variant) << _lib.MODEL_ATTN_VARIANT_SHIFT))
         d.time_fc_w, d.time_fc_b = f32(self.time_embed.c_fc.weight), f32(self.time_embed.c_fc.bias)
         d.time_proj_w, d.time_proj_b = f32(self.time_embed.c_proj.weight), f32(self.time_embed.c_proj.bias)
         d.freqs = ptr(freqs)

@@ -63,22 +63,8 @@ PCD_API unsigned long long pcd_launch_count(void);
 /* Device capability probe: 0 if the current device is sm_100 (B200). */
 PCD_API int pcd_check_device(void);
 
-/* Tuning / testing knob (no reference counterpart): tensor-core attention kernel variant,
- * 5 = persistent CTAs over (query tile, head, sequence) items, softmax software-pipelined over KV
- *     tiles (S_{j+1} loaded before the exponentials of S_j), separate K / V rings, packed f32x2 math,
- * 3 = one query tile per CTA, 64-key tiles, S and P double-buffered in TMEM, two CTAs per SM (default),
- * 4 = as 3, with every query row split over two softmax threads (16 softmax warps per SM),
- * 2 = ping-pong over two query tiles per CTA, P in TMEM,
- * 1 = one query tile per CTA, P in TMEM (tcgen05.mma with A from TMEM), two CTAs per SM,
- * 0 = one query tile per CTA, P staged through 128B-swizzled shared memory. */
-PCD_API int pcd_set_attention_variant(int variant);
-/* The variant the library starts with (what pcd_model_forward uses unless overridden). */
-PCD_API int pcd_default_attention_variant(void);
-/* Profiling aid -- results are INVALID while non-zero: bit 0 skips the GEMM epilogue, bit 1 skips
- * the GEMM TMA loads (separates main-loop, load and epilogue time in tools/gemm_probe.py).
- * Bit 4 (results stay valid): pcd_model_forward runs with separate LayerNorm kernels even when the
- * LayerNorm-folded weights are present (A/B timing and parity of the two paths). */
-PCD_API int pcd_set_debug_flags(int flags);
+/* There is no process-global state behind this ABI: kernel variants and profiling switches are per-call
+ * arguments (pcd_attention `variant`, pcd_gemm_args.debug) or per-handle options (pcd_model_desc.flags). */
 
 /* ------------------------------------------------------------------ */
 /* Elementwise / normalisation kernels                                 */
@@ -160,6 +146,9 @@ typedef struct {
   const float* colsum;             /* fp32 [N] (LN_*) */
   float ln_eps;
   int M, N, K, epilogue;
+  int debug;                       /* profiling aid (tools/gemm_probe.py): bit 0 skips the epilogue, bit 1 the TMA
+                                      operand loads, bit 3 the MMAs -- results INVALID; bit 2 (results valid)
+                                      forces the single-CTA kernel where the CTA-pair kernel would run */
 } pcd_gemm_args;
 PCD_API int pcd_gemm_bf16_ex(const pcd_gemm_args* args, void* stream);
 
@@ -186,19 +175,37 @@ typedef struct {
   int64_t head_stride;
 } pcd_attn_operand;
 
+/* Tensor-core attention kernels selectable per call (bf16 only; the fp32 kernel ignores `variant`):
+ *  GROUPED      one CTA per SM over three query tiles of one (sequence, head) that share every K / V tile; the
+ *               three softmax warps of a scheduler pass a MUFU token so that exactly one exponentiates at a
+ *               time (attn_tc8.cu) -- the default;
+ *  GROUPED_FREE the same kernel without the token (A/B measurement of the hand-off);
+ *  PAIRED       round-1 kernel: two CTAs per SM, one query tile each, softmax software-pipelined over KV tiles
+ *               (attn_tc5.cu); _POLY4 / _POLY2 evaluate 1/4 / 1/2 of the exponentials with an FMA-pipe polynomial. */
+typedef enum {
+  PCD_ATTN_DEFAULT = 0,
+  PCD_ATTN_GROUPED = 8,
+  PCD_ATTN_GROUPED_FREE = 9,
+  PCD_ATTN_PAIRED = 5,
+  PCD_ATTN_PAIRED_POLY4 = 6,
+  PCD_ATTN_PAIRED_POLY2 = 7
+} pcd_attn_variant;
+
 /* out[b, l, h*64 + c] = sum_s softmax_s((q_scale q[b,l,h]) . (k_scale k[b,s,h])) v[b,s,h,c]
  *  - self-attention   (transformer.py:65-84):   q,k,v views of qkv [B,L,H,3,64], scales 64^-1/4
  *  - cross-attention  (perceiver.py:46-67):     q [B,Lq,H,64], k,v views of kv [B,Lkv,H,2,64]
  *  - rotary attention (rotaryencoderpcd.py:6-27,68-84): rope_coords [B,L,3] != NULL applies
  *    theta = pi*coords to head dims 0..5 of q and k (requires Lq == Lkv);
- *    q_scale = width^-1/2, k_scale = 1.
+ *    q_scale = width^-1/2, k_scale = 1.  Both kernels rotate inside the attention kernel: the fp32 one in
+ *    registers while it loads the tiles, the tcgen05 one in shared memory between the TMA arrival of a Q / K
+ *    tile and the first MMA that reads it -- no rotated copy of q / k is ever written to HBM.
  * `precision` selects the operand/out dtype: PCD_F32 (CUDA-core kernel) or PCD_BF16
  * (tcgen05 flash kernel: QK^T and PV on tensor cores, accumulators in TMEM). */
 PCD_API int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                   void* out, int64_t out_batch_stride, int64_t out_row_stride,
                   int batch, int heads, int len_q, int len_kv,
                   float q_scale, float k_scale, const float* rope_coords,
-                  int precision, void* stream);
+                  int precision, int variant, void* stream);
 
 /* fp32 attention with head dim 32 (c in [0, 32) in the operand description): the cross-attention of the TwoStream
  * denoiser's read / compute / write blocks (models/modules.py:17-63: z_dim = x_dim = 256, 8 heads); CUDA-core kernel,
@@ -207,9 +214,10 @@ PCD_API int pcd_attention_hd32(const pcd_attn_operand* q, const pcd_attn_operand
                                float* out, int64_t out_batch_stride, int64_t out_row_stride, int batch, int heads,
                                int len_q, int len_kv, float q_scale, float k_scale, void* stream);
 
-/* bf16 mode of the rotary attention: rotate head dims 0..5 of a q or k operand IN PLACE with
- * theta = pi * coords[b, l, :] (apply_rotary_pos_emb, rotaryencoderpcd.py:6-27; fp32 arithmetic), then call
- * pcd_attention(..., rope_coords = NULL, PCD_BF16).  The fp32 kernel rotates in registers on load instead. */
+/* Stand-alone form of the rotation (apply_rotary_pos_emb, rotaryencoderpcd.py:6-27; fp32 arithmetic): rotate head
+ * dims 0..5 of a bf16 q or k operand IN PLACE with theta = pi * coords[b, l, :].  pcd_attention does this inside the
+ * kernel; this entry exists for callers that want rotated projections for something else (and as the test yardstick
+ * of the fused path). */
 PCD_API int pcd_rope_bf16(const pcd_attn_operand* x, const float* coords, int batch, int heads, int len,
                           void* stream);
 
@@ -346,6 +354,7 @@ typedef struct {
   int time_slot;            /* index of the time token in the prefix, or -1 when the
                                time embedding is ADDED to the point tokens instead  */
   float ln_eps;
+  int flags;                /* PCD_MODEL_* options of this handle                     */
   /* always fp32: */
   const float *time_fc_w, *time_fc_b, *time_proj_w, *time_proj_b;   /* time_embed MLP      */
   const float *freqs;                                                /* [width/2]          */
@@ -353,6 +362,9 @@ typedef struct {
   const float *in_w, *in_b, *out_w, *out_b;                          /* input/output_proj  */
   const pcd_block_weights* blocks;                                   /* HOST array [layers] */
 } pcd_model_desc;
+
+enum { PCD_MODEL_SEPARATE_LAYERNORM = 1,  /* run LayerNorm kernels even when the folded weights are present */
+       PCD_MODEL_ATTN_VARIANT_SHIFT = 8 };   /* bits 8..15: pcd_attn_variant of the forward (0 = default)      */
 
 typedef struct pcd_model pcd_model;
 

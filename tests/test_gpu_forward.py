@@ -45,7 +45,7 @@ def test_forward_full_size(case, dtype, tol):
 def test_forward_layernorm_folded_vs_separate(case):
     """The LayerNorm-folded bf16 forward (no LayerNorm kernels; residual update, bf16 copy and row
     statistics in the c_proj epilogues) against the same forward with separate LayerNorm kernels
-    (debug flag bit 4), and both against the reference golden."""
+    (per-handle option PCD_MODEL_SEPARATE_LAYERNORM), and both against the reference golden."""
     import pcd_b200 as P
     lib = P._lib.load()
     g = load_golden("forward_" + case)
@@ -55,14 +55,11 @@ def test_forward_layernorm_folded_vs_separate(case):
     with torch.no_grad():
         y_fold = model(x.to(DEV), t.to(DEV), **to_dev(kw)).clone()
     n_fold = lib.pcd_launch_count() - n0
-    lib.pcd_set_debug_flags(16)
-    try:
-        n0 = lib.pcd_launch_count()
-        with torch.no_grad():
-            y_sep = model(x.to(DEV), t.to(DEV), **to_dev(kw)).clone()
-        n_sep = lib.pcd_launch_count() - n0
-    finally:
-        lib.pcd_set_debug_flags(0)
+    model.fold_layernorm = False   # per-handle option (pcd_model_desc.flags): separate LayerNorm kernels
+    n0 = lib.pcd_launch_count()
+    with torch.no_grad():
+        y_sep = model(x.to(DEV), t.to(DEV), **to_dev(kw)).clone()
+    n_sep = lib.pcd_launch_count() - n0
     torch.cuda.synchronize()
     layers = cfg["layers"]
     assert n_sep - n_fold == 2 * layers - 1, (n_sep, n_fold)   # 2 LayerNorm launches per block vs one cast
@@ -87,11 +84,8 @@ def test_forward_width_2048_layernorm_folded():
     t = torch.tensor([900, 17], device=DEV)
     with torch.no_grad():
         y_fold = m16(x, t).clone()
-        lib.pcd_set_debug_flags(16)
-        try:
-            y_sep = m16(x, t).clone()
-        finally:
-            lib.pcd_set_debug_flags(0)
+        m16.fold_layernorm = False
+        y_sep = m16(x, t).clone()
         y32 = m32(x, t)
     torch.cuda.synchronize()
     assert rel(y_fold, y32) < TOL_BF16 and rel(y_sep, y32) < TOL_BF16, (rel(y_fold, y32), rel(y_sep, y32))

@@ -180,24 +180,20 @@ def test_gemm_layernorm_folded(M, N, K, gelu):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
-@pytest.mark.parametrize("variant", [5, 4, 3, 2, 1, 0])
+@pytest.mark.parametrize("variant", [0, 8, 9, 5])
 def test_self_attention_golden(dtype, tol, variant):
-    if dtype == torch.float32 and variant != 3:
+    if dtype == torch.float32 and variant != 0:
         pytest.skip("variant only affects the tensor-core kernel")
-    P._lib.load().pcd_set_attention_variant(variant)
-    try:
-        g = load_golden("ops")
-        for name, shape, seed, std, heads in (("self_attn", (2, 70, 384), 301, 1.0, 2),
-                                              ("self_attn_h8", (1, 300, 1536), 302, 2.0, 8)):
-            qkv = det.normal(shape, seed, std=std)
-            want = torch.from_numpy(g[name])
-            if dtype == torch.bfloat16:
-                want = D.qkv_attention(bf16_round(qkv), heads)
-            got = ops.self_attention(qkv.to(DEV).to(dtype), heads)
-            torch.cuda.synchronize()
-            assert rel(got.float(), want) < tol, describe(got.float(), want, f"{name} {dtype} v{variant}")
-    finally:
-        P._lib.load().pcd_set_attention_variant(P._lib.load().pcd_default_attention_variant())
+    g = load_golden("ops")
+    for name, shape, seed, std, heads in (("self_attn", (2, 70, 384), 301, 1.0, 2),
+                                          ("self_attn_h8", (1, 300, 1536), 302, 2.0, 8)):
+        qkv = det.normal(shape, seed, std=std)
+        want = torch.from_numpy(g[name])
+        if dtype == torch.bfloat16:
+            want = D.qkv_attention(bf16_round(qkv), heads)
+        got = ops.self_attention(qkv.to(DEV).to(dtype), heads, variant=variant)
+        torch.cuda.synchronize()
+        assert rel(got.float(), want) < tol, describe(got.float(), want, f"{name} {dtype} v{variant}")
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
@@ -213,11 +209,15 @@ def test_self_attention_lengths(dtype, tol, L):
     assert rel(got.float(), want) < tol, describe(got.float(), want, f"L={L} {dtype}")
 
 
-@pytest.mark.parametrize("variant", [7, 6, 5, 3])
+@pytest.mark.parametrize("variant", [8, 9, 7, 6, 5])
 @pytest.mark.parametrize("B,heads,L,std", [(2, 2, 1, 1.5), (2, 2, 63, 1.5), (3, 2, 64, 1.5), (2, 3, 65, 1.5),
                                            (2, 2, 127, 1.5), (2, 2, 129, 1.5), (1, 2, 1026, 1.5),
-                                           (40, 8, 200, 1.0),    # 640 items on 296 persistent CTAs
-                                           (33, 8, 1026, 2.5),   # 9 query tiles x 17 KV tiles (odd), 8 items / CTA
+                                           (3, 2, 257, 1.5),     # 3 query tiles, the third holding one row
+                                           (2, 2, 385, 1.5),     # a second query group with a single one-row tile
+                                           (2, 2, 640, 1.5),     # groups of 3 + 2 query tiles
+                                           (40, 8, 200, 1.0),    # 640 items on the persistent CTAs
+                                           (33, 8, 1026, 2.5),   # 9 query tiles x 17 KV tiles (odd), several items / CTA
+                                           (2, 8, 4353, 1.0),    # upsampler length: 35 query tiles (11 groups of 3 + 2)
                                            (5, 16, 1281, 4.0)])  # large logits: lazy rescaling path
 def test_attention_bf16_variants_vs_torch(variant, B, heads, L, std):
     """Tensor-core attention variants against an fp32 torch evaluation of the same bf16 inputs, at
@@ -232,12 +232,8 @@ def test_attention_bf16_variants_vs_torch(variant, B, heads, L, std):
     for b0 in range(0, B, 8):
         w = torch.einsum("bthc,bshc->bhts", q[b0:b0 + 8], k[b0:b0 + 8]) / 8.0
         want[b0:b0 + 8] = torch.einsum("bhts,bshc->bthc", torch.softmax(w, -1), v[b0:b0 + 8]).reshape(-1, L, heads * 64)
-    lib.pcd_set_attention_variant(variant)
-    try:
-        got = ops.self_attention(qkv, heads)
-        torch.cuda.synchronize()
-    finally:
-        lib.pcd_set_attention_variant(lib.pcd_default_attention_variant())
+    got = ops.self_attention(qkv, heads, variant=variant)
+    torch.cuda.synchronize()
     assert torch.isfinite(got.float()).all()
     assert rel(got.float(), want) < 1e-2, describe(got.float(), want, f"v{variant} B{B} H{heads} L{L}")
     # per-sequence check so that one bad item cannot hide in the norm of many good ones
@@ -274,10 +270,12 @@ def test_rotary_attention_golden():
 
 
 def test_rotary_attention_bf16():
-    """bf16 mode of RotarySelfAttention (rotaryencoderpcd.py:58-84): tensor-core projections and
-    attention with pcd_rope_bf16 in between, against the reference golden and against an fp32
-    evaluation of the rotation on the same bf16 inputs."""
+    """bf16 mode of RotarySelfAttention (rotaryencoderpcd.py:58-84): tensor-core projections and ONE attention launch
+    that rotates q / k inside the kernel (shared-memory tiles, between TMA arrival and the first MMA), against the
+    reference golden, against the fp32 rotary kernel on the same values, and bit for bit against the stand-alone
+    rotation (pcd_rope_bf16) followed by plain attention."""
     g = load_golden("ops")
+    lib = P._lib.load()
     coords = det.uniform((2, 70, 3), 307, std=0.5 / 3 ** 0.5)
     sd = det.fill_state_dict({"qkv.weight": torch.zeros(384, 128), "qkv.bias": torch.zeros(384),
                               "out_proj.weight": torch.zeros(128, 128), "out_proj.bias": torch.zeros(128)}, 308)
@@ -286,17 +284,27 @@ def test_rotary_attention_bf16():
     got = mod(det.normal((2, 70, 128), 309).to(DEV), coords.to(DEV))
     assert got.dtype == torch.float32
     assert rel(got, g["rotary_self_attn"]) < 2e-2, describe(got, g["rotary_self_attn"])
-    # kernel level: larger problem, bf16 rotary attention vs the fp32 rotary kernel on the same values
-    B, N, H = 3, 333, 4
-    qkv = bf16_round(det.normal((B, N, 3 * H * 64), 330, std=1.2)).to(DEV)
-    pos = det.uniform((B, N, 3), 331, std=0.4).to(DEV)
-    want = ops.rotary_attention(qkv, pos, H)
-    keep = qkv.bfloat16()
-    snapshot = keep.clone()
-    got2 = ops.rotary_attention(keep, pos, H)
-    torch.cuda.synchronize()
-    assert torch.equal(keep, snapshot), "the caller's qkv must not be modified"
-    assert rel(got2.float(), want) < 1e-2, describe(got2.float(), want)
+    # kernel level: several query groups, ragged tails, bf16 rotary attention vs the fp32 rotary kernel
+    for B, N, H in ((3, 333, 4), (2, 1026, 2), (1, 64, 1)):
+        qkv = bf16_round(det.normal((B, N, 3 * H * 64), 330 + N, std=1.2)).to(DEV)
+        pos = det.uniform((B, N, 3), 331 + N, std=0.4).to(DEV)
+        want = ops.rotary_attention(qkv, pos, H)
+        keep = qkv.bfloat16()
+        snapshot = keep.clone()
+        n0 = lib.pcd_launch_count()
+        got2 = ops.rotary_attention(keep, pos, H)
+        assert lib.pcd_launch_count() - n0 == 1, "rotary attention must be a single launch"
+        torch.cuda.synchronize()
+        assert torch.equal(keep, snapshot), "the caller's qkv must not be modified"
+        assert rel(got2.float(), want) < 1e-2, describe(got2.float(), want, f"B{B} N{N} H{H}")
+        # the fused rotation computes exactly what the stand-alone one does
+        D = H * 64
+        rot = keep.clone()
+        ops.rope_bf16_(rot[..., :D], pos, H)
+        ops.rope_bf16_(rot[..., D:2 * D], pos, H)
+        plain = ops.attention_views(rot[..., :D], rot[..., D:2 * D], rot[..., 2 * D:], H, D ** -0.5, 1.0)
+        torch.cuda.synchronize()
+        assert torch.equal(plain, got2), describe(got2.float(), plain.float(), "fused vs stand-alone rotation")
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])

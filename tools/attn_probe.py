@@ -25,12 +25,11 @@ def t(fn, it=int(os.environ.get('ATTN_IT', '10'))):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / it
 fl = 4.0 * L * L * 64 * H * B
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [5, 3]
-for v in variants:
-    lib.pcd_set_attention_variant(v)
-    out = P.ops.self_attention(qkv, H)
-    torch.cuda.synchronize()
-    err = float((out[:2].float() - want).norm() / want.norm())
-    ms = t(lambda: P.ops.self_attention(qkv, H))
-    print(f"variant {v}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  rel err {err:.2e}")
-lib.pcd_set_attention_variant(lib.pcd_default_attention_variant())
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 9, 5]
+for rep in range(int(os.environ.get("ATTN_REPS", "2"))):
+    for v in variants:
+        out = P.ops.self_attention(qkv, H, variant=v)
+        torch.cuda.synchronize()
+        err = float((out[:2].float() - want).norm() / want.norm())
+        ms = t(lambda: P.ops.self_attention(qkv, H, variant=v))
+        print(f"L={L} variant {v}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s  rel err {err:.2e}", flush=True)

@@ -24,12 +24,10 @@ for phase in ("cold", "after 2 s of GEMMs"):
     if phase != "cold":
         for _ in range(8000): ops.linear(a, w, bias, out=y)
         torch.cuda.synchronize()
-    for v in (5, 3, 5, 3, 5, 3):
-        lib.pcd_set_attention_variant(v)
-        us = t(lambda: ops.self_attention(qkv, H))
+    for v in (8, 5, 8, 5, 8, 5):
+        us = t(lambda: ops.self_attention(qkv, H, variant=v))
         print(f"{phase}: variant {v}: {us:7.1f} us   [sm MHz, W] {clock()}")
 # long steady run of variant 5: 400 launches
-lib.pcd_set_attention_variant(5)
 for i in range(5):
-    us = t(lambda: ops.self_attention(qkv, H), it=100)
+    us = t(lambda: ops.self_attention(qkv, H, variant=5), it=100)
     print(f"steady v5 x100: {us:7.1f} us   {clock()}")

@@ -21,12 +21,20 @@ for name, N, K, epi, od in (("qkv", 1536, 512, 0, torch.bfloat16), ("proj", 512,
     bias = torch.zeros(N, device=dev)
     res = torch.randn(M, N, device=dev) if epi == 2 else None
     out = torch.empty(M, N, device=dev, dtype=od)
-    fn = lambda: P.ops.linear(a, w, bias, epilogue=epi, residual=res, out_dtype=od, out=out)
+    import ctypes as C
+    g = P._lib.GemmArgs()
+    g.A, g.lda, g.W, g.ldw, g.bias = P._lib.ptr(a), K, P._lib.ptr(w), K, P._lib.ptr(bias)
+    g.residual, g.ldr = P._lib.ptr(res), N
+    g.C, g.ldc, g.out_precision = P._lib.ptr(out), N, (P._lib.PCD_BF16 if od == torch.bfloat16 else P._lib.PCD_F32)
+    g.M, g.N, g.K, g.epilogue = M, N, K, epi
+
+    def fn():
+        P._lib.check(lib.pcd_gemm_bf16_ex(C.byref(g), P._lib.stream_ptr()), "gemm")
     r = {}
-    for flags in (0, 1, 2, 3, 10):
-        lib.pcd_set_debug_flags(flags)
+    for flags in (0, 1, 2, 3, 10):  # per-call profiling switches (pcd_gemm_args.debug)
+        g.debug = flags
         r[flags] = t(fn)
-    lib.pcd_set_debug_flags(0)
+    g.debug = 0
     fl = 2.0 * M * N * K
     print(f"{name:5s} N={N} K={K}: full {r[0]*1e3:7.1f}us ({fl/r[0]/1e9:6.0f} TF) | no-epilogue {r[1]*1e3:7.1f}us ({fl/r[1]/1e9:6.0f} TF) | "
           f"no-TMA {r[2]*1e3:7.1f}us | MMA-only {r[3]*1e3:7.1f}us ({fl/r[3]/1e9:6.0f} TF) | epilogue-only {r[10]*1e3:7.1f}us")
