@@ -31,7 +31,8 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
     const int64_t nq = (len_q + 127) / 128, grouped_items = ((nq + 2) / 3) * heads * batch;
     variant = (rope != nullptr || grouped_items >= num_sms()) ? PCD_ATTN_GROUPED : PCD_ATTN_PAIRED;
   }
-  if (variant != PCD_ATTN_GROUPED && variant != PCD_ATTN_GROUPED_FREE && variant != PCD_ATTN_PAIRED &&
+  const bool grouped = variant == PCD_ATTN_GROUPED || variant == PCD_ATTN_GROUPED_TOKEN;
+  if (!grouped && variant != PCD_ATTN_PAIRED &&
       variant != PCD_ATTN_PAIRED_POLY4 && variant != PCD_ATTN_PAIRED_POLY2) {
     set_error("attention(bf16): unknown kernel variant %d", variant);
     return PCD_ERR_INVALID;
@@ -42,9 +43,9 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
   if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, 64)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, 64)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
-  if (variant == PCD_ATTN_GROUPED || variant == PCD_ATTN_GROUPED_FREE)
+  if (grouped)
     return launch_attn_tc8(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, rope,
-                           variant == PCD_ATTN_GROUPED, st);
+                           variant == PCD_ATTN_GROUPED_TOKEN, st);
   if (rope != nullptr) {
     set_error("attention(bf16): the paired kernel takes pre-rotated operands (pcd_rope_bf16); use PCD_ATTN_GROUPED");
     return PCD_ERR_UNSUPPORTED;

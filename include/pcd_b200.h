@@ -176,16 +176,16 @@ typedef struct {
 } pcd_attn_operand;
 
 /* Tensor-core attention kernels selectable per call (bf16 only; the fp32 kernel ignores `variant`):
- *  GROUPED      one CTA per SM over three query tiles of one (sequence, head) that share every K / V tile; the
- *               three softmax warps of a scheduler pass a MUFU token so that exactly one exponentiates at a
- *               time (attn_tc8.cu) -- the default;
- *  GROUPED_FREE the same kernel without the token (A/B measurement of the hand-off);
- *  PAIRED       round-1 kernel: two CTAs per SM, one query tile each, softmax software-pipelined over KV tiles
- *               (attn_tc5.cu); _POLY4 / _POLY2 evaluate 1/4 / 1/2 of the exponentials with an FMA-pipe polynomial. */
+ *  GROUPED        one CTA per SM over three query tiles of one (sequence, head) that share every K / V tile: three
+ *                 softmax warps per scheduler keep the special-function pipe fed (attn_tc8.cu) -- the default;
+ *  GROUPED_TOKEN  the same kernel with a per-scheduler MUFU token (one of the three warps exponentiates at a time);
+ *                 measured slower than GROUPED, kept for A/B runs;
+ *  PAIRED         round-1 kernel: two CTAs per SM, one query tile each, softmax software-pipelined over KV tiles
+ *                 (attn_tc5.cu); _POLY4 / _POLY2 evaluate 1/4 / 1/2 of the exponentials with an FMA-pipe polynomial. */
 typedef enum {
   PCD_ATTN_DEFAULT = 0,
   PCD_ATTN_GROUPED = 8,
-  PCD_ATTN_GROUPED_FREE = 9,
+  PCD_ATTN_GROUPED_TOKEN = 9,
   PCD_ATTN_PAIRED = 5,
   PCD_ATTN_PAIRED_POLY4 = 6,
   PCD_ATTN_PAIRED_POLY2 = 7

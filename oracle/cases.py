@@ -67,7 +67,23 @@ FORWARD_CASES = {
     "full_imagevec": (copy.deepcopy(MODEL_CONFIGS["base40M-imagevec"]), 2, 201, "reference"),
     "full_upsample": (copy.deepcopy(MODEL_CONFIGS["upsample"]), 1, 202, "reference"),
     "full_base300M": (copy.deepcopy(MODEL_CONFIGS["base300M"]), 1, 203, "reference"),
+    # the bench's own batch shape class: 32 clouds = 64 guided sequences' worth of persistent-tile work per launch
+    # (many items per CTA in every GEMM / attention launch); stored every 8th point (FORWARD_POINT_STRIDE)
+    "full_imagevec_b32": (copy.deepcopy(MODEL_CONFIGS["base40M-imagevec"]), 32, 204, "reference"),
 }
+# golden stores out[:, :, ::stride] for these cases (file size); every sequence stays pinned
+FORWARD_POINT_STRIDE = {"full_imagevec_b32": 8}
+
+# BASELINE config 3 (ii): perceiver cross-attention at the text-conditioning shape -- queries = the 1026 denoiser
+# tokens (width 512, 8 heads), data = 77 CLIP ViT-L/14 text tokens of width 768
+PERCEIVER_TEXT = dict(B=2, n_q=1026, n_data=77, width=512, heads=8, data_width=768, layers=2, seed=320,
+                      row_stride=8)
+
+
+def perceiver_text_inputs():
+    c = PERCEIVER_TEXT
+    return (det.normal((c["B"], c["n_q"], c["width"]), c["seed"] + 1),
+            det.normal((c["B"], c["n_data"], c["data_width"]), c["seed"] + 2))
 
 
 def forward_inputs(name):

@@ -100,7 +100,22 @@ def gen_forward(m, case):
     with torch.no_grad():
         y = model(x, t, **kw)
     print(f"  reference forward {time.time() - t0:.2f}s  out std {y.std():.4f}")
-    save("forward_" + case, out=y)
+    stride = cases.FORWARD_POINT_STRIDE.get(case, 1)
+    save("forward_" + case, out=y[:, :, ::stride])
+
+
+def gen_perceiver_text(m):
+    """SimplePerceiver at the BASELINE config-3 text-conditioning shape (perceiver.py:107-146)."""
+    print("perceiver_text")
+    c = cases.PERCEIVER_TEXT
+    per = m.perceiver.SimplePerceiver(device="cpu", dtype=torch.float32, n_data=c["n_data"], width=c["width"],
+                                      layers=c["layers"], heads=c["heads"], data_width=c["data_width"]).eval()
+    per.load_state_dict(det.fill_state_dict(per.state_dict(), c["seed"]))
+    x, data = cases.perceiver_text_inputs()
+    with torch.no_grad():
+        y = per(x, data)
+    print("  out std", float(y.std()))
+    save("perceiver_text", out=y[:, ::c["row_stride"]])
 
 
 def gen_schedule(m):
@@ -265,6 +280,7 @@ def main():
             continue
         todo.append(("sampler_" + c, lambda c=c: gen_sampler(m, c)))
     todo.append(("sampler_two_stage", lambda: gen_two_stage(m)))
+    todo.append(("perceiver_text", lambda: gen_perceiver_text(m)))
     for c in cases.SOLVER_CASES:
         todo.append(("solver_" + c, lambda c=c: gen_solver(m, c)))
     for c in cases.DDPM_CASES:

@@ -41,6 +41,35 @@ def test_forward_full_size(case, dtype, tol):
     assert rel(y, g["out"]) < tol, describe(y, g["out"], f"{case} {dtype}")
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, TOL_BF16), (torch.float32, TOL_F32)])
+def test_forward_at_bench_batch(dtype, tol):
+    """base40M-imagevec at B = 32 (M = 32 832 rows, 768 grouped attention items: every persistent CTA of the GEMM and
+    attention kernels walks several tiles per launch) against the unmodified reference, every sequence on its own."""
+    case = "full_imagevec_b32"
+    g = load_golden("forward_" + case)
+    stride = cases.FORWARD_POINT_STRIDE[case]
+    model, cfg, _ = build_model(case, dtype)
+    x, t, kw = cases.forward_inputs(case)
+    with torch.no_grad():
+        y = model(x.to(DEV), t.to(DEV), **to_dev(kw))
+    torch.cuda.synchronize()
+    got, want = y[:, :, ::stride].cpu(), torch.from_numpy(g["out"])
+    assert got.shape == want.shape
+    assert rel(got, want) < tol, describe(got, want, f"{case} {dtype}")
+    per_seq = (got - want).flatten(1).norm(dim=1) / want.flatten(1).norm(dim=1)
+    assert float(per_seq.max()) < tol, f"worst sequence {int(per_seq.argmax())}: {float(per_seq.max()):.3e}"
+    if dtype == torch.bfloat16:
+        # the sampler's shape: the same 32 clouds as ONE 64-sequence guided evaluation (conditional + unconditional
+        # halves sharing x, common timestep) -- the conditional half must equal a plain forward at that timestep
+        tt = torch.full((32,), 511, device=DEV)
+        with torch.no_grad():
+            plain = model(x.to(DEV), tt, **to_dev(kw)).clone()
+            e = kw["embeddings"].to(DEV)
+            both = model.forward_cfg(x.to(DEV), 511, dict(embeddings=torch.cat([e, torch.zeros_like(e)])), doubled=True)
+        torch.cuda.synchronize()
+        assert rel(both[:32], plain) < 1e-3, describe(both[:32], plain, "guided batch vs plain forward")
+
+
 @pytest.mark.parametrize("case", ["full_imagevec", "full_base300M"])
 def test_forward_layernorm_folded_vs_separate(case):
     """The LayerNorm-folded bf16 forward (no LayerNorm kernels; residual update, bf16 copy and row

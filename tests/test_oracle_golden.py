@@ -123,6 +123,17 @@ def test_forward_full(case):
     assert rel_l2(y, g["out"]) < 1e-5
 
 
+def test_perceiver_text_shape():
+    """BASELINE config 3 (ii): SimplePerceiver with 1026 query tokens of width 512 over 77 text tokens of width 768."""
+    c = cases.PERCEIVER_TEXT
+    g = load_golden("perceiver_text")
+    sd = det.fill_state_dict(perceiver_shapes(c["width"], c["layers"], c["data_width"]), c["seed"])
+    x, data = cases.perceiver_text_inputs()
+    with torch.no_grad():
+        y = D.perceiver_forward(sd, c["layers"], c["heads"], x, data)
+    assert rel_l2(y[:, ::c["row_stride"]], g["out"]) < 1e-5
+
+
 def test_schedule():
     g = load_golden("schedule")
     for name, dcfg, smax, churn in (("base", "base", 120.0, 3.0), ("upsample", "upsample", 160.0, 0.0)):
