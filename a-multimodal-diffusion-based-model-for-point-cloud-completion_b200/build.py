@@ -50,6 +50,26 @@ def _stale():
         return f.read().strip() != source_hash()
 
 
+def build_variant(out_path: str, extra_flags, objdir_name: str) -> str:
+    """A side build of the library with extra compiler flags (profiling / tracing builds under tools/; never the
+    product library).  Load it with PCD_B200_LIB=<out_path>."""
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build", objdir_name)
+    os.makedirs(objdir, exist_ok=True)
+    procs = [(src, os.path.join(objdir, src.replace(".cu", ".o"))) for src in SOURCES]
+    running = [(src, obj, subprocess.Popen([nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj],
+                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for src, obj in procs]
+    for src, obj, p in running:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    r = subprocess.run([nvcc, "-shared", "-o", out_path, *[o for _, o in procs], "-Xcompiler", "-fPIC"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return out_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB

@@ -37,7 +37,8 @@ constexpr int BQ = 128, BKV = 64, HD = 64, NT = 3;
 constexpr int Q_TILE = BQ * HD * 2;    // 16 KB
 constexpr int KV_TILE = BKV * HD * 2;  // 8 KB
 constexpr int KSK = 4, KSV = 4;
-constexpr int TILE_BYTES = 2 * NT * Q_TILE + (KSK + KSV) * KV_TILE;  // 160 KB
+constexpr int O_STAGE = 32 * HD * 2;  // per softmax warp: 32 rows x 128 B of normalised output for one TMA store
+constexpr int TILE_BYTES = 2 * NT * Q_TILE + (KSK + KSV) * KV_TILE + 4 * NT * O_STAGE;  // 208 KB
 constexpr int BAR_BYTES = 1024;
 constexpr int SMEM_BYTES = TILE_BYTES + 1024 + BAR_BYTES;
 constexpr int TMEM_COLS = 512;
@@ -101,10 +102,41 @@ __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 struct Item {
   int g, h, b, n_act;
 };
-__device__ __forceinline__ Item decode_item(int item, int ngroups, int heads, int nq) {
-  const int g = item % ngroups, bh = item / ngroups;
-  return Item{g, bh % heads, bh / heads, min(NT, nq - g * NT)};
-}
+// The items of a CTA are blockIdx.x, + gridDim.x, ...: decoded once with divisions, then advanced with additions
+// and conditional subtractions (four integer divisions by run-time values per item and warp were ~400 cycles of
+// every item boundary).
+struct ItemIter {
+  int g, h, b;            // current item
+  int dg, dh, db;         // gridDim.x decomposed in the (group, head, sequence) mixed radix
+  int ngroups, heads, nq;
+  __device__ __forceinline__ ItemIter(int first, int stride, int ngroups_, int heads_, int nq_)
+      : ngroups(ngroups_), heads(heads_), nq(nq_) {
+    g = first % ngroups;
+    const int bh = first / ngroups;
+    h = bh % heads;
+    b = bh / heads;
+    dg = stride % ngroups;
+    const int dbh = stride / ngroups;
+    dh = dbh % heads;
+    db = dbh / heads;
+  }
+  __device__ __forceinline__ Item get() const { return Item{g, h, b, min(NT, nq - g * NT)}; }
+  __device__ __forceinline__ void next() {
+    g += dg;
+    int carry = 0;
+    if (g >= ngroups) {
+      g -= ngroups;
+      carry = 1;
+    }
+    h += dh + carry;
+    carry = 0;
+    if (h >= heads) {
+      h -= heads;
+      carry = 1;
+    }
+    b += db + carry;
+  }
+};
 
 // 3-axis rotation of head dims 0..5 of one 128-byte tile row held in 128B-swizzled shared memory
 // (apply_rotary_pos_emb, rotaryencoderpcd.py:6-27: out[0:3] = even * cos - odd * sin, out[3:6] = even * sin + odd * cos)
@@ -127,11 +159,25 @@ __device__ __forceinline__ void rope_row(uint32_t tile, int r, const float* __re
 
 constexpr float kRescaleThreshold = 8.f;  // log2 units: P <= 2^8, safe in bf16 / fp32
 
+// Timeline of the softmax warps of CTA 0 (tools build only: -DPCD_ATTN_TRACE, tools/attn_trace.py): clock stamps at
+// the points of a step where a warp can be held up, [slot][step][point].
+#ifdef PCD_ATTN_TRACE
+constexpr int TRACE_STEPS = 96, TRACE_PTS = 12;
+__device__ unsigned long long g_trace[NT * TRACE_STEPS * TRACE_PTS];
+#define PCD_TRACE(pt)                                                                                  \
+  do {                                                                                                 \
+    if (blockIdx.x == 0 && quarter == 0 && lane == 0 && trace_step < TRACE_STEPS)                     \
+      g_trace[(slot * TRACE_STEPS + trace_step) * TRACE_PTS + (pt)] = clock64();                       \
+  } while (0)
+#else
+#define PCD_TRACE(pt) do { } while (0)
+#endif
+
 // TOKEN = 1: MUFU hand-off ring; 0: warps exponentiate whenever they are ready (A/B of the ring itself)
 template <int TOKEN>
 __global__ void __launch_bounds__(512, 1)
 attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, uint16_t* __restrict__ out, int64_t o_bs, int64_t o_ls,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                      int len_q, int len_kv, float scale_log2, int nq, int ngroups, int heads, int n_items,
                      const float* __restrict__ rope) {
   extern __shared__ unsigned char smem_raw[];
@@ -140,6 +186,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t sQ = smem;                      // [NT][2] 16 KB
   const uint32_t sK = sQ + 2 * NT * Q_TILE;      // [KSK] 8 KB
   const uint32_t sV = sK + KSK * KV_TILE;        // [KSV] 8 KB
+  const uint32_t sO = sV + KSV * KV_TILE;        // [4 * NT] 4 KB output staging, one per softmax warp
   uint32_t bars = smem + TILE_BYTES;
   pin(bars);
   auto bar = [&](int slot) -> uint32_t { return bars + 8u * slot; };
@@ -151,11 +198,13 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int num_kv = (len_kv + BKV - 1) / BKV;
   const int last_valid = len_kv - (num_kv - 1) * BKV;  // keys in the last KV tile (1..64)
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  ItemIter items((int)blockIdx.x, (int)gridDim.x, ngroups, heads, nq);  // every role walks its own copy
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ);
     prefetch_tensormap(&tmK);
     prefetch_tensormap(&tmV);
+    prefetch_tensormap(&tmO);
     for (int i = 0; i < 2 * NT; ++i) {
       bar_init(bar(B_Q_FULL + i), 1);
       bar_init(bar(B_Q_EMPTY + i), 1);
@@ -199,8 +248,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         int kst = 0, vst = 0;
         uint32_t kph = 1, vph = 1;  // "empty" barriers: the first pass over a ring does not block
         uint32_t qcnt[NT] = {0, 0, 0};
-        for (int k = 0; k < my_items; ++k) {
-          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+        for (int k = 0; k < my_items; ++k, items.next()) {
+          const Item it = items.get();
 #pragma unroll
           for (int s = 0; s < NT; ++s) {
             if (s < it.n_act) {
@@ -235,8 +284,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         int kst = 0;
         uint32_t kph = 0;
         uint32_t qcnt[NT] = {0, 0, 0};
-        for (int k = 0; k < my_items; ++k) {
-          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+        for (int k = 0; k < my_items; ++k, items.next()) {
+          const Item it = items.get();
 #pragma unroll
           for (int s = 0; s < NT; ++s) {
             if (s < it.n_act) {
@@ -276,8 +325,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t kph = 0;
         uint32_t qcnt[NT] = {0, 0, 0};
         uint32_t su[NT] = {0, 0, 0};  // S products issued per slot
-        for (int k = 0; k < my_items; ++k) {
-          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+        for (int k = 0; k < my_items; ++k, items.next()) {
+          const Item it = items.get();
           uint64_t adesc[NT];
           int qi[NT];
 #pragma unroll
@@ -328,8 +377,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t vph = 0;
         uint32_t pu[NT] = {0, 0, 0};   // PV products issued per slot
         uint32_t ni[NT] = {0, 0, 0};   // items the slot took part in
-        for (int k = 0; k < my_items; ++k) {
-          const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+        for (int k = 0; k < my_items; ++k, items.next()) {
+          const Item it = items.get();
           for (int j = 0; j < num_kv; ++j) {
             bar_wait(bar(B_V_FULL + vst), vph);
             const int nks = (j == num_kv - 1) ? nks_last : BKV / 16;
@@ -370,10 +419,11 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                    b_ofree = bars + 8 * (B_O_FREE + slot), b_tok = bars + 8 * (B_TOK + quarter * NT);
     uint32_t u = 0;    // tiles this slot has processed (parity of S_FULL / P_READY / PV_DONE uses)
     uint32_t tk = 0;   // token acquisitions of this warp
+    bool stores_pending = false;
     const uint64_t sc2 = pack2(scale_log2, scale_log2);
 
-    for (int k = 0; k < my_items; ++k) {
-      const Item it = decode_item(blockIdx.x + k * gridDim.x, ngroups, heads, nq);
+    for (int k = 0; k < my_items; ++k, items.next()) {
+      const Item it = items.get();
       if (slot >= it.n_act) continue;
       const int q0 = (it.g * NT + slot) * BQ;
       if (q0 + quarter * 32 >= len_q) {
@@ -398,11 +448,17 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float m_used = 0.f, l_run = 0.f;
       for (int j = 0; j < num_kv; ++j) {
         uint32_t r[BKV];
+#ifdef PCD_ATTN_TRACE
+        const int trace_step = k * num_kv + j;
+#endif
+        PCD_TRACE(0);  // step begins
         bar_wait(b_sfull, u & 1);
+        PCD_TRACE(1);  // S_j has arrived
         tcgen05_fence_after();
         tmem_ld_32x32b_x32(tm + s_col(slot), r);
         tmem_ld_32x32b_x32(tm + s_col(slot) + 32, r + 32);
         tmem_ld_wait();
+        PCD_TRACE(2);  // S_j in registers
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(b_sfree);  // S sits in registers: the next QK^T of the slot may overwrite it
@@ -425,7 +481,9 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
         }
         // P buffer / O of the slot are free once the previous PV product has completed
+        PCD_TRACE(3);  // row maximum done
         bar_wait(b_pvdone, (u & 1) ^ 1);
+        PCD_TRACE(4);  // PV_{j-1} complete
         if (j == 0) {
           m_used = mx;
         } else {
@@ -452,6 +510,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // ---- exponentials, under this scheduler's MUFU token ----
         if (TOKEN) bar_wait(b_tok + 8 * slot, slot == 0 ? ((tk & 1) ^ 1) : (tk & 1));
         ++tk;
+        PCD_TRACE(5);  // exponentials begin
         tcgen05_fence_after();
         uint64_t sum_a = 0ull, sum_b = 0ull;
 #pragma unroll
@@ -486,14 +545,21 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           unpack2(sum_b, s2, s3);
           l_run += (s0 + s1) + (s2 + s3);
         }
+        PCD_TRACE(6);  // exponentials issued
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(b_pready);  // P in TMEM -> PV may be issued
+        PCD_TRACE(7);  // P handed over
         ++u;
       }
       // ---- epilogue: O / l -> global ----
+#ifdef PCD_ATTN_TRACE
+      const int trace_step = k * num_kv + num_kv - 1;
+#endif
+      PCD_TRACE(8);   // epilogue begins
       bar_wait(b_pvdone, (u & 1) ^ 1);  // every PV product of the item has landed in O
+      PCD_TRACE(9);   // last PV complete
       tcgen05_fence_after();
       uint32_t o[HD];
       tmem_ld_32x32b_x32(tm + o_col(slot), o);
@@ -502,20 +568,43 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(b_ofree);  // O is in registers: the slot's next item may overwrite it
-      const int row = q0 + quarter * 32 + lane;
-      if (row < len_q) {
-        uint16_t* orow = out + it.b * o_bs + (int64_t)row * o_ls + it.h * HD;
+      PCD_TRACE(10);  // O in registers
+      // O / l -> bf16 -> this warp's 32 x 128 B staging tile (128B-swizzled like the tensor map) -> ONE TMA store.
+      // Storing from registers (each thread its own 128-byte row: 32 distinct lines per instruction) kept a warp
+      // in the load/store unit for 1100-2250 cycles per item (tools/attn_trace.py); rows >= len_q are clipped by
+      // the tensor map.
+      const uint32_t stage = sO + (warp - 4) * O_STAGE;
+      if (stores_pending) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous item's store has read the tile
+        __syncwarp();
+      }
+      {
         const float inv = 1.f / l_run;
+        const uint32_t row_addr = stage + lane * 128;
 #pragma unroll
         for (int i = 0; i < HD; i += 8) {
           float v[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(o[i + t]) * inv;
-          *reinterpret_cast<uint4*>(orow + i) =
-              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          const uint32_t a = row_addr + ((((uint32_t)i >> 3) ^ ((uint32_t)lane & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[0], v[1])),
+                       "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                       : "memory");
         }
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmO)),
+                     "r"(stage), "r"(0), "r"(it.h), "r"(q0 + quarter * 32), "r"(it.b)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      stores_pending = true;
+      PCD_TRACE(11);  // output handed to the TMA engine
     }
+    if (stores_pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // outputs globally visible
   }
 
   tcgen05_fence_before();
@@ -528,9 +617,15 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 }  // namespace a8
 
+#ifdef PCD_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int pcd_attn_trace_read(unsigned long long* dst, int n) {
+  const int total = a8::NT * a8::TRACE_STEPS * a8::TRACE_PTS;
+  return cudaMemcpyFromSymbol(dst, a8::g_trace, sizeof(unsigned long long) * (n < total ? n : total)) == cudaSuccess ? total : -1;
+}
+#endif
+
 template <int TOKEN>
-static int launch_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out, int64_t o_bs,
-                      int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
+static int launch_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
                       cudaStream_t st) {
   auto kern = a8::attn_bf16_tc8_kernel<TOKEN>;
   // the attribute is per device: set it on every launch (cheap) rather than caching a per-process flag
@@ -547,19 +642,18 @@ static int launch_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     return PCD_ERR_INVALID;
   }
   const int n_items = (int)n_items64;
-  const int grid = min(n_items, num_sms());  // one CTA per SM: 162 KB shared memory, all 512 TMEM columns
-  kern<<<grid, 512, a8::SMEM_BYTES, st>>>(tq, tk, tv, out, o_bs, o_ls, len_q, len_kv, scale_log2, nq, ngroups, heads,
+  const int grid = min(n_items, num_sms());  // one CTA per SM: 210 KB shared memory, all 512 TMEM columns
+  kern<<<grid, 512, a8::SMEM_BYTES, st>>>(tq, tk, tv, to, len_q, len_kv, scale_log2, nq, ngroups, heads,
                                           n_items, rope);
   PCD_CHECK_LAUNCH("attention_bf16");
   return PCD_OK;
 }
 
 // token: 1 = MUFU hand-off ring (default), 0 = free-running softmax warps (A/B measurement of the ring)
-int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out, int64_t o_bs,
-                    int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
+int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
                     int token, cudaStream_t st) {
-  if (token) return launch_tc8<1>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, rope, st);
-  return launch_tc8<0>(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  if (token) return launch_tc8<1>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  return launch_tc8<0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
 }
 
 }  // namespace pcd

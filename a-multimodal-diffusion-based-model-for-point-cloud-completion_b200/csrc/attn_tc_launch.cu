@@ -8,8 +8,7 @@ namespace pcd {
 int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out, int64_t o_bs,
                     int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, int poly,
                     cudaStream_t st);  // attn_tc5.cu
-int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, uint16_t* out, int64_t o_bs,
-                    int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
+int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
                     int token, cudaStream_t st);  // attn_tc8.cu
 int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const float* coords, int batch, int heads,
                      int len, cudaStream_t st);  // attn_simt.cu
@@ -43,9 +42,14 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
   if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, 64)) != PCD_OK) return rc;
   if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, 64)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
-  if (grouped)
-    return launch_attn_tc8(tq, tk, tv, out, o_bs, o_ls, batch, heads, len_q, len_kv, scale_log2, rope,
+  if (grouped) {
+    // the output through the same kind of map: [batch, len_q, heads, 64] at the caller's strides, 32-row boxes
+    CUtensorMap to;
+    const pcd_attn_operand oo = {out, o_bs, o_ls, 64};
+    if ((rc = make_operand_map(&to, &oo, batch, heads, len_q, 32)) != PCD_OK) return rc;
+    return launch_attn_tc8(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope,
                            variant == PCD_ATTN_GROUPED_TOKEN, st);
+  }
   if (rope != nullptr) {
     set_error("attention(bf16): the paired kernel takes pre-rotated operands (pcd_rope_bf16); use PCD_ATTN_GROUPED");
     return PCD_ERR_UNSUPPORTED;

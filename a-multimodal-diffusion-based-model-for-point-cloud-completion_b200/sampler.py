@@ -40,14 +40,14 @@ class _GraphedStage:
         self.eps_channels = self.shape[1] if diffusion.eps_channels_doubled else None
         self.launches_per_replay = 0
 
-    def _enqueue(self):
+    def _enqueue(self, max_steps: Optional[int] = None):
         st, plan = self.state, self.plan
         B = self.shape[0]
         torch.mul(self.noise[0], plan.sigma_max, out=st.x)
         if hasattr(self.model, "begin_trajectory"):
             self.model.begin_trajectory(B * (2 if st.guided else 1))  # an unguided run's prev_latent was staged by run()
         st.begin(self.noise[1])
-        for i, step in enumerate(plan.steps):
+        for i, step in enumerate(plan.steps[:max_steps]):
             out = self.model.forward_cfg(st.model_in, step.first.t, self.kwargs, st.guided, self.eps_channels)
             st.predictor(i, out, self.preds[i])
             if step.second is not None:
@@ -73,16 +73,20 @@ class _GraphedStage:
             self.model.prepare_cond(seqs, self.kwargs)
         self.model.prepare_time_tokens(self.plan.eval_timesteps())
         if self.graph is None:
-            # warm-up on a side stream (populates every cache), then capture
+            # warm-up on a side stream, then capture.  ONE Heun step is enough to populate every cache the capture
+            # relies on (workspace, conditioning tokens; the time tokens of the whole schedule were prepared above)
+            from . import _lib
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self._enqueue()
+                self._enqueue(max_steps=1)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.load().pcd_launch_count()
             with torch.cuda.graph(self.graph):
                 self._enqueue()
+            self.launches_per_replay = int(_lib.load().pcd_launch_count() - n0)  # kernels of this library in the graph
         self.graph.replay()
         return self.preds
 

@@ -241,6 +241,31 @@ def test_attention_bf16_variants_vs_torch(variant, B, heads, L, std):
     assert float(per) < 1e-2, float(per)
 
 
+@pytest.mark.parametrize("variant", [8, 9, 5])
+@pytest.mark.parametrize("late", [1, 5, 16])
+def test_attention_rereferences_rows_when_later_tiles_dominate(variant, late):
+    """Online softmax with a lazily updated reference point: keys from tile `late` on are scaled so that their logits
+    sit tens of binades above everything seen before (and some rows overflow an un-rescaled exponential), for every
+    row at a different tile.  The kernels must re-reference (rescale O and l) and still match an fp32 softmax."""
+    B, H, L = 2, 4, 1026
+    gen = torch.Generator(device="cpu").manual_seed(77 + late)
+    qkv = torch.randn(B, L, H * 192, generator=gen)
+    x = qkv.view(B, L, H, 192)
+    boost = torch.ones(L)
+    boost[late * 64:] = 6.0
+    boost[(late + 3) * 64 + 7:] = 30.0      # a second jump in the middle of a tile (if it exists)
+    x[..., 64:128] *= boost[None, :, None, None]
+    qkv = x.reshape(B, L, H * 192).to(DEV).bfloat16()
+    xf = qkv.float().view(B, L, H, 192)
+    q, k, v = xf[..., :64], xf[..., 64:128], xf[..., 128:]
+    w = torch.einsum("bthc,bshc->bhts", q, k) / 8.0
+    want = torch.einsum("bhts,bshc->bthc", torch.softmax(w, -1), v).reshape(B, L, H * 64)
+    got = ops.self_attention(qkv, H, variant=variant)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    assert rel(got.float(), want) < 1e-2, describe(got.float(), want, f"v{variant} late={late}")
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.bfloat16, 1e-2)])
 def test_cross_attention_golden(dtype, tol):
     g = load_golden("ops")
