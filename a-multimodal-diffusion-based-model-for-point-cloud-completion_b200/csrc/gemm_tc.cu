@@ -28,6 +28,19 @@ constexpr int G_BM = 128, G_BK = 64;
 constexpr int G_THREADS = 320, G_EPI_WARPS = 8;
 constexpr int G_STAGE_TILE = 32 * 128;  // epilogue staging tile: 32 rows x 128 bytes
 
+// Timeline of one epilogue warp and of the MMA issuer of CTA 0 (tools build only: -DPCD_GEMM_TRACE, tools/gemm_trace.py)
+#ifdef PCD_GEMM_TRACE
+constexpr int GT_TILES = 24, GT_PTS = 24;
+__device__ unsigned long long g_gemm_trace[2 * GT_TILES * GT_PTS];
+#define PCD_GTRACE(who, pt)                                                                        \
+  do {                                                                                             \
+    if (blockIdx.x == 0 && lane == 0 && it < GT_TILES) g_gemm_trace[((who) * GT_TILES + it) * GT_PTS + (pt)] = clock64(); \
+  } while (0)
+#else
+#define PCD_GTRACE(who, pt) do { } while (0)
+#endif
+
+
 template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int NBUF = 1;  // staging tiles per epilogue warp
@@ -253,6 +266,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *pp = o;
           }
         }
+        if (ew == 0) PCD_GTRACE(0, 5 + 4 * c);  // chunk c: math + staging stores issued
         if (last_of_store) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -302,7 +316,7 @@ struct Gemm2Cfg {
   // copy): a second set of staging tiles
   static constexpr int OUT1_BYTES = G_EPI_WARPS * NBUF * G_STAGE_TILE;
   static constexpr int OUT_BYTES = OUT1_BYTES + (EPI == PCD_EPI_RESIDUAL_STATS ? G_EPI_WARPS * G_STAGE_TILE : 0);
-  static constexpr int MISC_BYTES = 512 + 2 * BN * 4;  // barriers + per-tile bias slices
+  static constexpr int MISC_BYTES = 512 + 4 * BN * 4;  // barriers + per-tile bias and column-sum slices (two tiles each)
   static constexpr int BUDGET = 232448 - OUT_BYTES - MISC_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN;
@@ -332,6 +346,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* res_bar = acc_empty + 2;        // [8 warps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * G_EPI_WARPS);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);  // [2][BN]
+  float* scolsum = sbias + 2 * BN;                                                         // [2][BN] (LN-folded epilogues)
   constexpr bool kResid = (EPI == PCD_EPI_BIAS_RESIDUAL || EPI == PCD_EPI_RESIDUAL_STATS);
   constexpr bool kStats = (EPI == PCD_EPI_RESIDUAL_STATS);
   constexpr bool kLnFold = (EPI == PCD_EPI_LN_BIAS || EPI == PCD_EPI_LN_BIAS_GELU);
@@ -400,11 +415,15 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        PCD_GTRACE(1, 0);  // issuer: tile begins
         mbar_wait(&acc_empty[as], aphase ^ 1);
+        PCD_GTRACE(1, 1);  // issuer: accumulator buffer free
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (kb == 0) PCD_GTRACE(1, 2);  // issuer: first operands landed
+          if (kb == num_kb - 1) PCD_GTRACE(1, 3);  // issuer: last operands landed
           tcgen05_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
@@ -480,9 +499,14 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int row0 = m_blk * 2 * G_BM + (int)rank * G_BM + quarter * 32;
       const int colbase = n_blk * BN + half * HALF_N;
       float* sb = sbias + as * BN;
+      float* scs = scolsum + as * BN;
       if (etid < BN) {
         const int n = n_blk * BN + etid;
         sb[etid] = (bias != nullptr && n < N) ? __ldg(bias + n) : 0.f;
+        // the column sums of the folded weights go through shared memory like the bias: with the whole carve-out
+        // given to shared memory there is no L1 to speak of, and eight uniform global loads per 32-column chunk
+        // were L2 round trips inside the epilogue's critical path (tools/gemm_trace.py)
+        if (kLnFold) scs[etid] = (n < N) ? __ldg(colsum + n) : 0.f;
       }
       // LayerNorm statistics of this thread's row (LN-folded projections): normally prefetched during
       // the previous tile (below); wide rows (> 8 slots) are loaded here
@@ -524,8 +548,11 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         __syncwarp();
       }
+      if (ew == 0) PCD_GTRACE(0, 0);  // epilogue: tile begins (bias slice written, residual prefetch issued)
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ew == 0) PCD_GTRACE(0, 1);  // epilogue: past the per-tile CTA barrier
       mbar_wait(&acc_full[as], aphase);
+      if (ew == 0) PCD_GTRACE(0, 2);  // epilogue: accumulators complete
       tcgen05_fence_after();
       const uint32_t leader_acc_empty = mapa_shared(smem_u32(&acc_empty[as]), 0);
       if (dbg & 1) {
@@ -569,7 +596,9 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (elect_one()) tma_store_wait_read<NBUF - 1>();  // the store that used this tile two groups ago has read it
           __syncwarp();
         }
+        if (ew == 0) PCD_GTRACE(0, 3 + 4 * c);  // chunk c: staging tile free / residual landed
         tmem_ld_wait();
+        if (ew == 0) PCD_GTRACE(0, 4 + 4 * c);  // chunk c: accumulators in registers
         if (c + 1 < NCH) {
           tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rbuf[(c + 1) & 1]);
         } else {
@@ -587,7 +616,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           // epilogue warps, two per scheduler, are issue-latency bound).  LayerNorm folded into the
           // projection: with W' = gamma o W (bf16), s_n = sum_k W'[n,k], c_n = beta . W[n,:] + b_n:
           //   LN(x) W^T + b = rstd (x W'^T - mu s) + c
-          const float* scc = kLnFold ? colsum + colbase + c * 32 : nullptr;  // warp-uniform: broadcast loads
+          const float* scc = scs + half * HALF_N + c * 32;  // warp-uniform: broadcast loads from shared memory
           const uint64_t nmu2 = pack2(-cur_mu, -cur_mu), rstd2 = pack2(cur_rstd, cur_rstd);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -595,7 +624,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             uint64_t a01 = pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
             uint64_t a23 = pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             if (kLnFold) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(scc + j));
+              const float4 s4 = *reinterpret_cast<const float4*>(scc + j);
               a01 = fma2(rstd2, fma2(nmu2, pack2(s4.x, s4.y), a01), pack2(b4.x, b4.y));
               a23 = fma2(rstd2, fma2(nmu2, pack2(s4.z, s4.w), a23), pack2(b4.z, b4.w));
             } else {
@@ -617,6 +646,12 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             *reinterpret_cast<uint4*>(buf_row + piece * 16) =
                 make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
                            pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        } else {
+              *reinterpret_cast<uint4*>(buf_row + piece * 16) =
+                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+            }
           }
         } else {
 #pragma unroll
@@ -667,6 +702,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           st_mean += delta * (nb / (na + nb));
           st_m2 += cm2 + delta * delta * (na * nb / (na + nb));
         }
+        if (ew == 0) PCD_GTRACE(0, 5 + 4 * c);  // chunk c: math + staging stores issued
         if (last_of_store) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -691,6 +727,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (kPrefetch) __syncwarp();
           ++sidx;
         }
+        if (ew == 0) PCD_GTRACE(0, 6 + 4 * c);  // chunk c: TMA store(s) issued
       }
       if (kLnFold && stats_in_slots <= LN_MAXS && t + num_pairs < num_tiles) ln_combine();
       if (kStats) {
@@ -709,6 +746,13 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
+
+#ifdef PCD_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int pcd_gemm_trace_read(unsigned long long* dst, int n) {
+  const int total = 2 * GT_TILES * GT_PTS;
+  return cudaMemcpyFromSymbol(dst, g_gemm_trace, sizeof(unsigned long long) * (n < total ? n : total)) == cudaSuccess ? total : -1;
+}
+#endif
 
 struct LnArgs {  // extra operands of the residual+statistics and LayerNorm-folded epilogues
   CUtensorMap tmC2;
