@@ -648,12 +648,6 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                            pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
         } else {
-              *reinterpret_cast<uint4*>(buf_row + piece * 16) =
-                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-            }
-          }
-        } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4* pp = reinterpret_cast<float4*>(buf_row + ((i ^ sw) * 16));
