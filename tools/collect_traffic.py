@@ -18,7 +18,7 @@ def kernel_key(name):
         return "flash_attention"
     if "cast_rowstats" in name:
         return "cast_rowstats"
-    m = re.search(r"gemm_bf16_tc2_kernel<\(int\)(\d+), \(bool\)(\d), \(bool\)(\d)>", name)
+    m = re.search(r"gemm_bf16_tc2_kernel<(?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d)>", name)
     if m:  # <epilogue, bf16 output, deep-K>: 4 = c_qkv, 5 = c_fc + GELU, 3 = residual + statistics (deep-K: mlp.c_proj)
         epi, _, deepk = int(m.group(1)), int(m.group(2)), int(m.group(3))
         return {4: "gemm_qkv_lnfold", 5: "gemm_fc1_lnfold_gelu"}.get(epi, "gemm_fc2_resid_stats" if deepk else "gemm_attn_proj_resid_stats")
