@@ -25,3 +25,7 @@ TAILN=3 run bench 1800 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 ${BE
 grep -h '^{' $OUT/bench.log | tail -1 > $OUT/bench.json
 python tools/benchsum.py $OUT/bench.json 2>/dev/null | head -60
 echo "=== done ($(date +%T))"
+if [ "${EAGER:-0}" = "1" ]; then
+  TAILN=3 run eager_gpu 900 python bench.py --impl eager-gpu --steps 2 --warmup 1
+  grep -h '^{' $OUT/eager_gpu.log | tail -1 > $OUT/eager_gpu.json
+fi
