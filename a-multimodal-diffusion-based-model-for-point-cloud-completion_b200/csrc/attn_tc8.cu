@@ -1,27 +1,34 @@
-// bf16 flash attention (head dim 64, non-causal) on tcgen05 -- three query tiles per CTA, MUFU hand-off ring.
+// bf16 flash attention (head dim 64, non-causal) on tcgen05 -- three query tiles per CTA ("grouped" kernel).
 //
 // What bounds head-dim-64 attention on this chip is the special-function unit: one ex2 per logit against 256
-// tensor FLOP, 16 ex2/clk/SM.  Variant 5 (attn_tc5.cu: two CTAs per SM, one 128-query tile each) left that
-// unit 43 % idle for a reason its ncu capture shows directly (profiles/r01/prof_attn_v5.ncu-rep, stall
-// reasons of MUFU.EX2: `wait` 55 %, `mio_throttle` 23 %): the two softmax warps that share a scheduler drift
-// INTO phase -- while both exponentiate they split the pipe and finish together, then both do their
-// non-exponential work (row maximum, P hand-off, barrier and TMEM round trips, ~580 cycles) with the pipe
-// empty: 2 x 512 + 580 cycles per pair of tiles where 2 x 512 would do (measured 0.96 us per pair against
-// 0.64 us for a lone CTA).  This kernel removes the convoy instead of shortening the chain:
-//   * ONE CTA per SM with THREE query tiles ("slots") of the same (sequence, head): 12 softmax warps, three
-//     per scheduler, sharing every K / V tile (one TMA load and one shared-memory copy serve three S = Q K^T
-//     products);
-//   * a MUFU TOKEN per scheduler: the three warps of a scheduler pass an mbarrier token round-robin and
-//     exponentiate only while holding it, so the pipe always belongs to exactly one warp running at the
-//     full 8 cycles per instruction, while the other two do their non-exponential work; the token is passed
-//     on a few instructions before the last exponential so the wake-up latency of the next warp is hidden;
-//   * with three warps to cover for each other the per-warp chain may be 3 x 512 cycles long, so the
-//     softmax needs no software pipelining: one S tile in registers (about 110 registers per thread), S, P
-//     and O single-buffered per slot in TMEM (3 x (64 + 32 + 64) = 480 of 512 columns);
-//   * the ragged last KV tile costs only its real 16-key groups (exponentials and P columns of fully masked
-//     groups are skipped, the PV product stops at the last real group);
-//   * rotary point encoding (rotaryencoderpcd.py:6-27) inside the kernel: a dedicated warp rotates head dims
-//     0..5 of every Q / K tile in shared memory between the TMA arrival and the first MMA that reads it.
+// tensor FLOP, 16 ex2/clk/SM = 8 cycles of the pipe per warp instruction.  The paired kernel (attn_tc5.cu: two CTAs
+// per SM, one 128-query tile each, i.e. two softmax warps per scheduler) left that unit 43 % idle
+// (profiles/r01/prof_attn_v5.ncu-rep).  A warp's step is a chain -- S from TMEM, row maximum, 64 exponentials,
+// P to TMEM, the barrier round trips to the two MMA issuers -- of ~1600 cycles of which it holds the pipe for 512;
+// two such warps cannot keep it busy however they interleave.  This kernel gives every scheduler THREE:
+//   * ONE CTA per SM with three query tiles ("slots") of the same (sequence, head): 12 softmax warps, three per
+//     scheduler, sharing every K / V tile (one TMA load and one shared-memory copy serve three S = Q K^T products);
+//   * no software pipelining inside a warp any more (the paired kernel held two S tiles per thread): one S tile in
+//     registers, S, P and O single-buffered per slot in TMEM (3 x (64 + 32 + 64) = 480 of 512 columns); latency is
+//     hidden by the other two warps of the scheduler instead;
+//   * the two MMA issuers walk (KV tile, slot) in a FIXED order with blocking waits.  That order keeps the three
+//     slots ~600 cycles apart, which is what lets their exponential phases interleave: with one independent issuer
+//     thread per slot the slots fell into phase (all three exponentiating, then all three idle) and the kernel was
+//     5 % slower; polling issuers stole issue slots from the softmax warps they share schedulers with (-25 %);
+//   * the ragged last KV tile costs only its real 16-key groups (exponentials and P columns of fully masked groups
+//     are skipped, the PV product stops at the last real group);
+//   * the normalised output leaves through a per-warp 32 x 128 B staging tile and ONE TMA store per (warp, item):
+//     storing from registers (thread = row: 32 distinct lines per instruction) held a warp in the load/store unit
+//     for 1100-2250 cycles per item (tools/attn_trace.py), and the (group, head, sequence) of the next item is
+//     derived incrementally instead of with four integer divisions;
+//   * rotary point encoding (rotaryencoderpcd.py:6-27) inside the kernel: a dedicated warp rotates head dims 0..5 of
+//     every Q / K tile in shared memory between the TMA arrival and the first MMA that reads it.
+// Measured at the bench shape (128 sequences x 8 heads, L = 1026): 400 us against 485 us for the paired kernel
+// (361 / 419 us at L = 1024), XU pipe 67 % busy (57 %).  TOKEN = 1 keeps a negative result runnable: a per-scheduler
+// MUFU token (an mbarrier passed round-robin so that exactly one warp exponentiates at a time, handed on 16
+// exponentials early) costs more in hand-offs than the convoys it prevents (+12 %); so did issuing the 64
+// exponentials of a tile as one uninterrupted MUFU run, dropping the per-tile row maximum in favour of a
+// sum-triggered re-referencing, and evaluating 1/8-1/2 of the exponentials with an FMA-pipe polynomial.
 // Warp roles (512 threads): 0 = TMA producer (Q, K, V), 1 = QK^T issuer, 2 = rotary warp, 3 = PV issuer,
 // 4..15 = softmax: slot = (warp - 4) / 4, TMEM lane quarter = warp % 4, thread = query row.
 #include "common.cuh"
@@ -173,7 +180,7 @@ __device__ unsigned long long g_trace[NT * TRACE_STEPS * TRACE_PTS];
 #define PCD_TRACE(pt) do { } while (0)
 #endif
 
-// TOKEN = 1: MUFU hand-off ring; 0: warps exponentiate whenever they are ready (A/B of the ring itself)
+// TOKEN = 0 (default): warps exponentiate whenever they are ready; 1: MUFU hand-off ring (A/B of the ring itself)
 template <int TOKEN>
 __global__ void __launch_bounds__(512, 1)
 attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
