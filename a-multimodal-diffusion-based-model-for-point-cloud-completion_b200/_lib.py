@@ -53,7 +53,7 @@ class DdpmArgs(C.Structure):  # include/pcd_b200.h: pcd_ddpm_args
     _fields_ = ([(n, vp) for n in ("x", "model_out", "noise", "t", "table", "ch_scale", "ch_bias", "x_next",
                                    "pred_xstart", "sample_unscaled", "mean", "log_variance")]
                 + [(n, C.c_int) for n in ("batch", "channels", "n_points", "out_channels", "var_mode",
-                                          "clip_denoised", "unscale")])
+                                          "clip_denoised", "unscale", "num_timesteps")])
 
 
 DDPM_COLS = 8
@@ -96,7 +96,7 @@ _SIGS = {
     "pcd_attention_hd32": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                      C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
     "pcd_rope_bf16": (C.c_int, [C.POINTER(AttnOperand), vp, C.c_int, C.c_int, C.c_int, vp]),
-    "pcd_farthest_point_sample": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    "pcd_farthest_point_sample": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "pcd_nearest_points": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     "pcd_fscore": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_float, C.c_int, vp, vp, vp]),
     "pcd_sampler_begin": (C.c_int, [vp, vp, vp, C.POINTER(StepScalars), C.c_int64, vp]),

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
     }
     dist[k] = 3.4e38f;
   }
-  int win = init_idx[blockIdx.x];
+  int win = min(max(init_idx[blockIdx.x], 0), n - 1);  // a caller-supplied index never reads outside the cloud
   for (int s = 0; s < n_samples; ++s) {
     if (tid == 0) o[s] = win;
     if (s + 1 == n_samples) break;
@@ -53,6 +53,62 @@ __global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restric
           best = dist[k];
           best_i = i;
         }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+      if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+    }
+    if (lane == 0) { red_v[wid] = best; red_i[wid] = best_i; }
+    __syncthreads();
+    if (wid == 0) {
+      best = lane < FPS_THREADS / 32 ? red_v[lane] : -3.4e38f;
+      best_i = lane < FPS_THREADS / 32 ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+      }
+      if (lane == 0) s_win = best_i;
+    }
+    __syncthreads();
+    win = s_win;
+  }
+}
+
+// Clouds of more than 8192 points (e.g. the 16384-point complete clouds of the MVP dataset): the same scheme with the
+// running minimum distances in a caller-supplied global workspace [batch, n] and the coordinates re-read every round.
+__global__ void __launch_bounds__(FPS_THREADS) fps_large_kernel(const float* __restrict__ pts, int n, int n_samples,
+                                                                const int* __restrict__ init_idx, float* __restrict__ ws,
+                                                                long long* __restrict__ out) {
+  __shared__ float red_v[FPS_THREADS / 32];
+  __shared__ int red_i[FPS_THREADS / 32];
+  __shared__ int s_win;
+  const float* p = pts + (size_t)blockIdx.x * n * 3;
+  float* dist = ws + (size_t)blockIdx.x * n;
+  long long* o = out + (size_t)blockIdx.x * n_samples;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < n; i += FPS_THREADS) dist[i] = 3.4e38f;
+  int win = min(max(init_idx[blockIdx.x], 0), n - 1);
+  for (int s = 0; s < n_samples; ++s) {
+    if (tid == 0) o[s] = win;
+    if (s + 1 == n_samples) break;
+    const float wx = p[3 * win], wy = p[3 * win + 1], wz = p[3 * win + 2];
+    const float wsq = __fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz));
+    float best = -3.4e38f;
+    int best_i = 0x7fffffff;
+    for (int i = tid; i < n; i += FPS_THREADS) {
+      const float x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+      const float sq = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+      const float dot = __fadd_rn(__fadd_rn(__fmul_rn(x, wx), __fmul_rn(y, wy)), __fmul_rn(z, wz));
+      const float d = fminf(dist[i], __fsub_rn(__fadd_rn(sq, wsq), __fmul_rn(2.f, dot)));
+      dist[i] = d;
+      if (d > best) {  // ascending i within the thread: strict > keeps the first maximum
+        best = d;
+        best_i = i;
       }
     }
 #pragma unroll
@@ -161,12 +217,15 @@ __global__ void fscore_reduce_kernel(const float* __restrict__ d1, int n1, const
 using namespace pcd;
 
 extern "C" int pcd_farthest_point_sample(const float* points, int batch, int n, int n_samples, const int* init_idx,
-                                         long long* out_idx, void* stream) {
+                                         long long* out_idx, float* workspace, void* stream) {
   PCD_CHECK_ARG(points != nullptr && init_idx != nullptr && out_idx != nullptr, "farthest_point_sample: null argument");
   PCD_CHECK_ARG(batch > 0 && n > 0 && n_samples > 0 && n_samples <= n, "farthest_point_sample: need 0 < n_samples <= n");
-  PCD_CHECK_ARG(n <= FPS_THREADS * FPS_MAX_PER_THREAD, "farthest_point_sample: at most %d points per cloud (got %d)",
-                FPS_THREADS * FPS_MAX_PER_THREAD, n);
-  fps_kernel<<<batch, FPS_THREADS, 0, (cudaStream_t)stream>>>(points, n, n_samples, init_idx, out_idx);
+  if (n > FPS_THREADS * FPS_MAX_PER_THREAD) {
+    PCD_CHECK_ARG(workspace != nullptr, "farthest_point_sample: clouds of more than %d points need a [batch, n] float workspace",
+                  FPS_THREADS * FPS_MAX_PER_THREAD);
+    fps_large_kernel<<<batch, FPS_THREADS, 0, (cudaStream_t)stream>>>(points, n, n_samples, init_idx, workspace, out_idx);
+  } else
+    fps_kernel<<<batch, FPS_THREADS, 0, (cudaStream_t)stream>>>(points, n, n_samples, init_idx, out_idx);
   PCD_CHECK_LAUNCH("farthest_point_sample");
   return PCD_OK;
 }

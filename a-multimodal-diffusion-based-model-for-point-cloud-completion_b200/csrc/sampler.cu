@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(pcd_ddpm_args a) {
   const int64_t xi = ((int64_t)b * a.channels + c) * a.n_points + n;
   const int64_t oe = ((int64_t)b * a.out_channels + c) * a.n_points + n;
   const int64_t ov = oe + (int64_t)a.channels * a.n_points;
-  const int64_t t = a.t[b];
+  int64_t t = a.t[b];  // device-side indices never read outside the schedule table
+  t = t < 0 ? 0 : (t >= a.num_timesteps ? a.num_timesteps - 1 : t);
   const float* row = a.table + t * PCD_DDPM_COLS;
   const float ca = row[PCD_DDPM_RECIP], cb = row[PCD_DDPM_RECIPM1], c1 = row[PCD_DDPM_MEAN_X0], c2 = row[PCD_DDPM_MEAN_XT];
   const float min_log = row[PCD_DDPM_MIN_LOG], max_log = row[PCD_DDPM_MAX_LOG], fixed_log = row[PCD_DDPM_FIXED_LOG];
@@ -350,6 +351,7 @@ extern "C" int pcd_ddpm_step(const pcd_ddpm_args* a, void* stream) {
   PCD_CHECK_ARG(a != nullptr, "ddpm_step: null argument block");
   PCD_CHECK_ARG(a->batch > 0 && a->channels > 0 && a->n_points > 0, "ddpm_step: bad shape");
   PCD_CHECK_ARG(a->x && a->model_out && a->t && a->table, "ddpm_step: x, model_out, t and table are required");
+  PCD_CHECK_ARG(a->num_timesteps > 0, "ddpm_step: num_timesteps (rows of the schedule table) must be set");
   PCD_CHECK_ARG(a->var_mode == PCD_VAR_FIXED || a->var_mode == PCD_VAR_LEARNED_RANGE || a->var_mode == PCD_VAR_LEARNED,
                 "ddpm_step: unknown variance mode %d", a->var_mode);
   PCD_CHECK_ARG(a->out_channels >= (a->var_mode == PCD_VAR_FIXED ? 1 : 2) * a->channels,

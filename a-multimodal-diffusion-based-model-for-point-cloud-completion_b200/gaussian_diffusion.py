@@ -171,6 +171,7 @@ class GaussianDiffusion:
             setattr(a, k, _lib.ptr(res.get(k)))
         a.batch, a.channels, a.n_points, a.out_channels = B, Cc, n_points, out.shape[1]
         a.var_mode, a.clip_denoised, a.unscale = mode, int(bool(clip_denoised)), int("sample_unscaled" in outputs)
+        a.num_timesteps = self.num_timesteps
         _lib.check(_lib.load().pcd_ddpm_step(C.byref(a), _lib.stream_ptr()), "ddpm_step")
         res["extra"] = extra
         return res

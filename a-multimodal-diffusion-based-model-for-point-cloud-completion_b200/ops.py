@@ -302,10 +302,13 @@ def farthest_point_sample(points: torch.Tensor, n_samples: int, init_idx) -> tor
     B, N, _ = points.shape
     points = points.contiguous()
     if not torch.is_tensor(init_idx):
+        if not 0 <= int(init_idx) < N:
+            raise IndexError(f"farthest_point_sample: init_idx {int(init_idx)} outside a cloud of {N} points")
         init_idx = torch.full((B,), int(init_idx), dtype=torch.int32, device=points.device)
-    init_idx = init_idx.to(device=points.device, dtype=torch.int32).contiguous()
+    init_idx = init_idx.to(device=points.device, dtype=torch.int32).contiguous()  # (device tensors are clamped by the kernel)
     out = torch.empty(B, n_samples, dtype=torch.int64, device=points.device)
-    check(_lib.load().pcd_farthest_point_sample(ptr(points), B, N, n_samples, ptr(init_idx), ptr(out), stream_ptr()),
+    ws = torch.empty(B, N, dtype=torch.float32, device=points.device) if N > 8192 else None  # running distances
+    check(_lib.load().pcd_farthest_point_sample(ptr(points), B, N, n_samples, ptr(init_idx), ptr(out), ptr(ws), stream_ptr()),
           "farthest_point_sample")
     return out
 

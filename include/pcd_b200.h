@@ -299,6 +299,7 @@ typedef struct pcd_ddpm_args {
   int var_mode;             /* PCD_VAR_* */
   int clip_denoised;
   int unscale;
+  int num_timesteps;        /* rows of `table`: step indices are clamped to [0, num_timesteps) on the device */
 } pcd_ddpm_args;
 PCD_API int pcd_ddpm_step(const pcd_ddpm_args* args, void* stream);
 
@@ -315,9 +316,10 @@ PCD_API int pcd_chamfer(const float* p1, int c1, int n1, const float* p2, int c2
 
 /* Greedy farthest-point sampling (util/point_cloud.py:82-118; evaluation.py:40-48): points fp32
  * [batch, n, 3] row-major, init_idx int32 [batch] -> out_idx int64 [batch, n_samples]; distances in the
- * reference's |a|^2 + |b|^2 - 2 a.b form, first arg-max.  n <= 8192 (the reference evaluates at <= 8192 points). */
+ * reference's |a|^2 + |b|^2 - 2 a.b form, first arg-max.  Up to 8192 points per cloud the running distances live in
+ * registers (workspace may be NULL); larger clouds need workspace = [batch, n] floats.  init_idx is clamped to the cloud. */
 PCD_API int pcd_farthest_point_sample(const float* points, int batch, int n, int n_samples, const int* init_idx,
-                                      long long* out_idx, void* stream);
+                                      long long* out_idx, float* workspace, void* stream);
 /* For every point of a [batch, na, 3]: squared distance to / index of its nearest point of b [batch, nb, 3]
  * (either output may be NULL).  form 0: sum (a-b)^2 (models/util.py:213-214); form 1: |a|^2 + |b|^2 - 2 a.b
  * (PointCloud.nearest_points, util/point_cloud.py:148-165).  First minimum wins. */

@@ -28,7 +28,8 @@ def test_point_cloud_methods_match_reference_goldens():
     assert np.allclose(sub.channels["G"], g["sub_avg_G"], rtol=1e-6)
 
 
-@pytest.mark.parametrize("B,N,n", [(1, 700, 128), (3, 4096, 1024), (2, 8192, 1024), (2, 33, 33)])
+@pytest.mark.parametrize("B,N,n", [(1, 700, 128), (3, 4096, 1024), (2, 8192, 1024), (2, 33, 33),
+                                   (2, 16384, 512)])   # MVP-size complete clouds: distances in a global workspace
 def test_farthest_point_sample_indices(B, N, n):
     """Index parity (bit-exact) with the oracle's numpy restatement at the evaluation sizes."""
     pts = det.uniform((B, N, 3), 930 + N, 0.5)
@@ -47,6 +48,19 @@ def test_farthest_point_sample_indices(B, N, n):
             assert abs(d(got[b][k]) - d(want[k])) <= 1e-6, (b, k, got[b][k], want[k], d(got[b][k]), d(want[k]))
             assert np.array_equal(got[b][:k], want[:k])
     assert len(set(got[0].tolist())) == n  # no point twice
+
+
+def test_farthest_point_sample_rejects_and_clamps_bad_start_indices():
+    pts = det.uniform((2, 100, 3), 951, 0.5).to(DEV)
+    with pytest.raises(IndexError):
+        ops.farthest_point_sample(pts, 10, 100)
+    with pytest.raises(IndexError):
+        ops.farthest_point_sample(pts, 10, -1)
+    # a device tensor cannot be checked without a sync: the kernel clamps it into the cloud
+    got = ops.farthest_point_sample(pts, 10, torch.tensor([1000, -5], dtype=torch.int32, device=DEV)).cpu()
+    assert got[0, 0] == 99 and got[1, 0] == 0
+    want = ops.farthest_point_sample(pts, 10, torch.tensor([99, 0], dtype=torch.int32, device=DEV)).cpu()
+    assert torch.equal(got, want)
 
 
 def test_fscore_and_nearest_points():
