@@ -78,7 +78,7 @@ _SIGS = {
     "pcd_timestep_embed": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     "pcd_layernorm": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp]),
     "pcd_embed_tokens": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
-                                   C.c_float, vp, C.c_int, C.c_int, vp]),
+                                   C.c_float, vp, C.c_int, C.c_int, vp, vp, vp]),
     "pcd_add_layernorm": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_float, vp]),
     "pcd_output_proj": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, vp, vp,

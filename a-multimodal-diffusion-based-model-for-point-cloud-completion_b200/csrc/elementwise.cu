@@ -156,6 +156,54 @@ __global__ void __launch_bounds__(256) cast_rowstats_kernel(const float* __restr
   }
 }
 
+// The bf16 copy of one stream row held in registers + per-128-column (mean, M2) of the ROUNDED values, exactly as
+// cast_rowstats_kernel computes them (dim % 128 == 0): the first LayerNorm-folded projection consumes them, so the
+// forward saves one pass over the stream (read 4 + write 2 bytes per element).  The MAXV slices reduce side by side
+// (independent shuffle chains).
+template <int MAXV>
+__device__ __forceinline__ void emit_bf16_stats(const RowRegs<MAXV>& r, int64_t row, int dim, int lane,
+                                                uint16_t* __restrict__ hb, float2* __restrict__ stats) {
+  float q[MAXV][4], sm[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    sm[i] = 0.f;
+    if (c < dim) {
+      const uint32_t p0 = pack_bf16x2(r.v[i].x, r.v[i].y), p1 = pack_bf16x2(r.v[i].z, r.v[i].w);
+      *reinterpret_cast<uint2*>(hb + (size_t)row * dim + c) = make_uint2(p0, p1);
+      q[i][0] = __uint_as_float(p0 << 16); q[i][1] = __uint_as_float(p0 & 0xffff0000u);
+      q[i][2] = __uint_as_float(p1 << 16); q[i][3] = __uint_as_float(p1 & 0xffff0000u);
+      sm[i] = (q[i][0] + q[i][1]) + (q[i][2] + q[i][3]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) sm[i] += __shfl_xor_sync(0xffffffffu, sm[i], o);
+  }
+  float m2[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    sm[i] *= (1.f / 128.f);
+    m2[i] = 0.f;
+    if (c < dim) {
+      const float a = q[i][0] - sm[i], b = q[i][1] - sm[i], cc = q[i][2] - sm[i], d = q[i][3] - sm[i];
+      m2[i] = (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) m2[i] += __shfl_xor_sync(0xffffffffu, m2[i], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+      if (i * 128 < dim) stats[(size_t)row * (dim / 128) + i] = make_float2(sm[i], m2[i]);
+  }
+}
+
 // out = a + b (fp32, out may alias a): the stream additions of the TwoStream denoiser that are not the
 // tail of a projection (z + ln_latent(..), token-type embeddings; models/modules.py:228-229, model.py:536)
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
@@ -180,7 +228,7 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
     const float* __restrict__ w_in, const float* __restrict__ b_in,
     const float* __restrict__ prefix, int n_prefix, const float* __restrict__ add_cond,
     const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
-    float* __restrict__ h, int seqs, int dim) {
+    float* __restrict__ h, int seqs, int dim, uint16_t* __restrict__ hb, float2* __restrict__ stats) {
   // Each warp owns EMB_ROWS_PER_WARP consecutive token rows; the lane's slice of the input
   // projection (4*MAXV output features x c_in) is loaded once into shared memory per block and
   // re-used for every row, so the loop is bound by the 4*dim bytes written per token.
@@ -254,7 +302,111 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
         y.z = (r.v[i].z - mean) * rstd * g.z + b.z;
         y.w = (r.v[i].w - mean) * rstd * g.w + b.w;
         *reinterpret_cast<float4*>(hr + c) = y;
+        r.v[i] = y;
       }
+    }
+    if (hb != nullptr) emit_bf16_stats<MAXV>(r, row, dim, lane, hb, stats);
+  }
+}
+
+// The same operation with the lane's slice of the input projection, its bias and the ln_pre parameters held in REGISTERS
+// (widths <= 512, CIN channels): the shared-memory form above re-reads 7 x 16 B of weights and 2 x 16 B of LayerNorm
+// parameters per 16 B it writes and is bound by the shared-memory / L1 datapath (170 us at the bench shape against a
+// 41 us write floor); here a row costs only FMAs, shuffles and its stores.  A warp takes chunks of EMBR_CHUNK
+// consecutive rows: 16 lanes fetch the rows' point channels with coalesced loads up front, the row loop broadcasts
+// them by shuffle.  Arithmetic (FMA order, statistics, LayerNorm expression) is the shared-memory kernel's, bit for bit.
+constexpr int EMBR_CHUNK = 16;
+
+template <int MAXV, int CIN>
+__global__ void __launch_bounds__(128, 2) embed_tokens_reg_kernel(
+    const float* __restrict__ x, int x_seqs, int n_points, const float* __restrict__ w_in,
+    const float* __restrict__ b_in, const float* __restrict__ prefix, int n_prefix,
+    const float* __restrict__ add_cond, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+    float* __restrict__ h, int seqs, int dim, uint16_t* __restrict__ hb, float2* __restrict__ stats, int64_t n_chunks) {
+  const int lane = threadIdx.x & 31;
+  const int L = n_prefix + n_points;
+  const int64_t total = (int64_t)seqs * L;
+  float4 w[CIN][MAXV], bs[MAXV], g[MAXV], bt[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const bool ok = c < dim;
+#pragma unroll
+    for (int k = 0; k < CIN; ++k)
+      w[k][i] = ok ? make_float4(w_in[(size_t)c * CIN + k], w_in[(size_t)(c + 1) * CIN + k], w_in[(size_t)(c + 2) * CIN + k],
+                                 w_in[(size_t)(c + 3) * CIN + k])
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    bs[i] = ok ? *reinterpret_cast<const float4*>(b_in + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    g[i] = ok ? *reinterpret_cast<const float4*>(ln_g + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[i] = ok ? *reinterpret_cast<const float4*>(ln_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < n_chunks; ch += nwarps) {
+    const int64_t base = ch * EMBR_CHUNK;
+    const int nrows = (int)((total - base < EMBR_CHUNK) ? (total - base) : EMBR_CHUNK);
+    float xm[CIN];
+    {
+      int64_t mine = base + (lane & (EMBR_CHUNK - 1));
+      if (mine >= total) mine = total - 1;
+      const int ms = (int)(mine / L), ml = (int)(mine % L);
+      const float* xs = x + (size_t)(ms % x_seqs) * CIN * n_points + (ml >= n_prefix ? ml - n_prefix : 0);
+#pragma unroll
+      for (int k = 0; k < CIN; ++k) xm[k] = xs[(size_t)k * n_points];
+    }
+    int s = (int)(base / L), l = (int)(base % L);
+    for (int rr = 0; rr < nrows; ++rr) {
+      const int64_t row = base + rr;
+      RowRegs<MAXV> r;
+      if (l < n_prefix) {
+        const float* p = prefix + ((size_t)s * n_prefix + l) * dim;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (c < dim) r.v[i] = *reinterpret_cast<const float4*>(p + c);
+        }
+      } else {
+        float xv[CIN];
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) xv[k] = __shfl_sync(0xffffffffu, xm[k], rr);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          const int c = (i * 32 + lane) * 4;
+          if (c < dim) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < CIN; ++k) {
+              acc[0] = fmaf(xv[k], w[k][i].x, acc[0]);
+              acc[1] = fmaf(xv[k], w[k][i].y, acc[1]);
+              acc[2] = fmaf(xv[k], w[k][i].z, acc[2]);
+              acc[3] = fmaf(xv[k], w[k][i].w, acc[3]);
+            }
+            acc[0] += bs[i].x; acc[1] += bs[i].y; acc[2] += bs[i].z; acc[3] += bs[i].w;
+            if (add_cond != nullptr) {
+              const float4 e = *reinterpret_cast<const float4*>(add_cond + (size_t)s * dim + c);
+              acc[0] += e.x; acc[1] += e.y; acc[2] += e.z; acc[3] += e.w;
+            }
+            r.v[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          }
+        }
+      }
+      float mean, rstd;
+      row_stats<MAXV>(r, dim, lane, mean, rstd, eps);
+      float* hr = h + (size_t)row * dim;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < dim) {
+          float4 y;
+          y.x = (r.v[i].x - mean) * rstd * g[i].x + bt[i].x;
+          y.y = (r.v[i].y - mean) * rstd * g[i].y + bt[i].y;
+          y.z = (r.v[i].z - mean) * rstd * g[i].z + bt[i].z;
+          y.w = (r.v[i].w - mean) * rstd * g[i].w + bt[i].w;
+          *reinterpret_cast<float4*>(hr + c) = y;
+          r.v[i] = y;
+        }
+      }
+      if (hb != nullptr) emit_bf16_stats<MAXV>(r, row, dim, lane, hb, stats);
+      if (++l == L) { l = 0; ++s; }
     }
   }
 }
@@ -325,6 +477,100 @@ __global__ void __launch_bounds__(256) output_proj_kernel(
   for (int idx = threadIdx.x; idx < c_out * 8; idx += blockDim.x) {
     int o = idx / 8, j = idx % 8;
     if (n0 + j < n_points) out[((size_t)s * c_out + o) * n_points + n0 + j] = stage[j][o];
+  }
+}
+
+// The same operation for the LayerNorm-folded forward (no pending MLP output, widths <= 512, COUT channels) with
+// gamma o w_out held in registers and beta . w_out + b_out precomputed per warp:
+//   out_o = rstd * sum_c (v_c - mean) (gamma_c w_oc) + (sum_c beta_c w_oc + b_o)
+// The kernel above issues 36 16-byte loads per 2 KB row (h, gamma, beta, 6 weight rows) and is bound by the L1
+// datapath (107 us at the bench shape against a 41 us read floor); here a row costs its own 4 loads.  A warp takes chunks
+// of OPR_CHUNK consecutive point tokens, prefetches the next row while it reduces the current one, and lane j keeps the
+// results of row j so that the NCL store is one coalesced segment per channel.
+constexpr int OPR_CHUNK = 16;
+
+template <int MAXV, int COUT>
+__global__ void __launch_bounds__(128, 2) output_proj_reg_kernel(
+    const float* __restrict__ h, int seqs, int n_prefix, int n_points, int dim, const float* __restrict__ ln_g,
+    const float* __restrict__ ln_b, float eps, const float* __restrict__ w_out, const float* __restrict__ b_out,
+    float* __restrict__ out, int64_t n_chunks) {
+  const int lane = threadIdx.x & 31;
+  const int L = n_prefix + n_points;
+  const int64_t total = (int64_t)seqs * n_points;
+  float4 gw[COUT][MAXV];
+  float cst[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      gw[o][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < dim) {
+        const float4 g = *reinterpret_cast<const float4*>(ln_g + c), b = *reinterpret_cast<const float4*>(ln_b + c);
+        const float4 w = *reinterpret_cast<const float4*>(w_out + (size_t)o * dim + c);
+        gw[o][i] = make_float4(g.x * w.x, g.y * w.y, g.z * w.z, g.w * w.w);
+        a += (b.x * w.x + b.y * w.y) + (b.z * w.z + b.w * w.w);
+      }
+    }
+    cst[o] = warp_sum(a) + b_out[o];
+  }
+  auto load_row = [&](RowRegs<MAXV>& r, int s, int n) {
+    const float* hr = h + ((size_t)s * L + n_prefix + n) * dim;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      r.v[i] = (c < dim) ? *reinterpret_cast<const float4*>(hr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t ch = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ch < n_chunks; ch += nwarps) {
+    const int64_t base = ch * OPR_CHUNK;
+    const int nrows = (int)((total - base < OPR_CHUNK) ? (total - base) : OPR_CHUNK);
+    int s = (int)(base / n_points), n = (int)(base % n_points);
+    RowRegs<MAXV> cur, nxt;
+    load_row(cur, s, n);
+    float res[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) res[o] = 0.f;
+    for (int rr = 0; rr < nrows; ++rr) {
+      if (++n == n_points) { n = 0; ++s; }
+      if (rr + 1 < nrows) load_row(nxt, s, n);
+      float mean, rstd;
+      row_stats<MAXV>(cur, dim, lane, mean, rstd, eps);
+      float a[COUT];
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) a[o] = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const float d0 = cur.v[i].x - mean, d1 = cur.v[i].y - mean, d2 = cur.v[i].z - mean, d3 = cur.v[i].w - mean;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {   // gw is zero beyond dim
+          a[o] = fmaf(d0, gw[o][i].x, a[o]);
+          a[o] = fmaf(d1, gw[o][i].y, a[o]);
+          a[o] = fmaf(d2, gw[o][i].z, a[o]);
+          a[o] = fmaf(d3, gw[o][i].w, a[o]);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) a[o] += __shfl_xor_sync(0xffffffffu, a[o], off);
+      }
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float val = fmaf(a[o], rstd, cst[o]);
+        if (lane == rr) res[o] = val;
+      }
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) cur.v[i] = nxt.v[i];
+    }
+    if (lane < nrows) {
+      const int64_t mine = base + lane;
+      const int ms = (int)(mine / n_points), mn = (int)(mine % n_points);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) out[((size_t)ms * COUT + o) * n_points + mn] = res[o];
+    }
   }
 }
 
@@ -409,14 +655,28 @@ extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_poin
                                 const float* w_in, const float* b_in, const float* prefix,
                                 int n_prefix, const float* add_cond, const float* ln_g,
                                 const float* ln_b, float eps, float* h, int seqs, int dim,
-                                void* stream) {
+                                uint16_t* h_bf16, float* stats, void* stream) {
+  PCD_CHECK_ARG((h_bf16 == nullptr) == (stats == nullptr), "embed_tokens: h_bf16 and stats come together");
+  PCD_CHECK_ARG(h_bf16 == nullptr || dim % 128 == 0, "embed_tokens: the bf16 copy + statistics need dim %% 128 == 0");
   PCD_CHECK_ARG(seqs > 0 && x_seqs > 0 && seqs % x_seqs == 0, "embed_tokens: seqs must be a multiple of x_seqs");
   PCD_CHECK_ARG(c_in >= 1 && c_in <= 8, "embed_tokens: c_in must be in [1,8] (got %d)", c_in);
   PCD_CHECK_ARG(dim % 4 == 0 && dim <= 2048, "embed_tokens: bad width %d", dim);
   PCD_CHECK_ARG(n_prefix >= 0 && (n_prefix == 0 || prefix != nullptr), "embed_tokens: prefix missing");
   int64_t rows = (int64_t)seqs * (n_prefix + n_points);
-  dim3 grid((unsigned)ceil_div64(rows, 8 * EMB_ROWS_PER_WARP)), block(256);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dim <= 512 && (c_in == 3 || c_in == 6)) {
+    // weights in registers; persistent grid, two 128-thread blocks per SM
+    const int64_t n_chunks = ceil_div64(rows, EMBR_CHUNK);
+    int64_t blocks = ceil_div64(n_chunks, 4);
+    if (blocks > 2 * (int64_t)num_sms()) blocks = 2 * num_sms();
+#define PCD_EMBR(CIN) DISPATCH_MAXV(dim, (embed_tokens_reg_kernel<(MAXV <= 4 ? MAXV : 4), CIN><<<(unsigned)blocks, 128, 0, st>>>( \
+      x, x_seqs, n_points, w_in, b_in, prefix, n_prefix, add_cond, ln_g, ln_b, eps, h, seqs, dim, h_bf16, reinterpret_cast<float2*>(stats), n_chunks)))
+    if (c_in == 3) { PCD_EMBR(3); } else { PCD_EMBR(6); }
+#undef PCD_EMBR
+    PCD_CHECK_LAUNCH("embed_tokens");
+    return PCD_OK;
+  }
+  dim3 grid((unsigned)ceil_div64(rows, 8 * EMB_ROWS_PER_WARP)), block(256);
   const size_t smem = (size_t)dim * (c_in + 1) * sizeof(float);  // <= 2048 * 9 * 4 = 72 KB
   if (smem > 48 * 1024) {
     // width 2048 (base1B) with >= 5 channels: opt in to more than 48 KB of dynamic shared memory
@@ -427,7 +687,7 @@ extern "C" int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_poin
       return PCD_ERR_CUDA;
     }
   }
-  DISPATCH_MAXV(dim, (embed_tokens_kernel<MAXV><<<grid, block, smem, st>>>(x, x_seqs, c_in, n_points, w_in, b_in, prefix, n_prefix, add_cond, ln_g, ln_b, eps, h, seqs, dim)));
+  DISPATCH_MAXV(dim, (embed_tokens_kernel<MAXV><<<grid, block, smem, st>>>(x, x_seqs, c_in, n_points, w_in, b_in, prefix, n_prefix, add_cond, ln_g, ln_b, eps, h, seqs, dim, h_bf16, reinterpret_cast<float2*>(stats))));
   PCD_CHECK_LAUNCH("embed_tokens");
   return PCD_OK;
 }
@@ -438,8 +698,19 @@ extern "C" int pcd_output_proj(const float* h, const void* y, int y_precision, i
                                void* stream) {
   PCD_CHECK_ARG(seqs > 0 && n_points > 0 && dim % 4 == 0 && dim <= 2048, "output_proj: bad shape");
   PCD_CHECK_ARG(c_out >= 1 && c_out <= 32, "output_proj: c_out must be in [1,32] (got %d)", c_out);
-  dim3 grid(seqs * ceil_div(n_points, 8)), block(256);
   cudaStream_t st = (cudaStream_t)stream;
+  if (y == nullptr && dim <= 512 && (c_out == 3 || c_out == 6)) {
+    const int64_t n_chunks = ceil_div64((int64_t)seqs * n_points, OPR_CHUNK);
+    int64_t blocks = ceil_div64(n_chunks, 4);
+    if (blocks > 2 * (int64_t)num_sms()) blocks = 2 * num_sms();
+#define PCD_OPR(COUT) DISPATCH_MAXV(dim, (output_proj_reg_kernel<(MAXV <= 4 ? MAXV : 4), COUT><<<(unsigned)blocks, 128, 0, st>>>( \
+      h, seqs, n_prefix, n_points, dim, ln_g, ln_b, eps, w_out, b_out, out, n_chunks)))
+    if (c_out == 3) { PCD_OPR(3); } else { PCD_OPR(6); }
+#undef PCD_OPR
+    PCD_CHECK_LAUNCH("output_proj");
+    return PCD_OK;
+  }
+  dim3 grid(seqs * ceil_div(n_points, 8)), block(256);
   DISPATCH_MAXV(dim, (output_proj_kernel<MAXV><<<grid, block, 0, st>>>(h, y, y_precision == PCD_BF16, seqs, n_prefix, n_points, dim, ln_g, ln_b, eps, w_out, b_out, c_out, out)));
   PCD_CHECK_LAUNCH("output_proj");
   return PCD_OK;

@@ -282,9 +282,20 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
       addc = w.tcond;
     }
   }
-  // input_proj + token concat + ln_pre (transformer.py:208-220)
+  // LayerNorm-folded path (bf16, width % 256 == 0, >= 512 tokens, folded weights supplied): no
+  // LayerNorm kernels at all.  The c_proj / mlp.c_proj GEMMs update the fp32 residual stream in their
+  // epilogue and emit its bf16 copy + per-row statistics; c_qkv / c_fc consume that copy with
+  // W' = gamma o W and apply mean / rstd algebraically in their epilogue (gemm_tc.cu).
+  bool fold = bf && W % 256 == 0 && M >= 512 && !(d.flags & PCD_MODEL_SEPARATE_LAYERNORM);
+  for (int l = 0; l < d.layers && fold; ++l) {
+    const pcd_block_weights& b = m->blocks[l];
+    fold = b.w_qkv_ln && b.w_fc_ln && b.qkv_colsum && b.qkv_const && b.fc_colsum && b.fc_const;
+  }
+  // input_proj + token concat + ln_pre (transformer.py:208-220); on the folded path the same kernel also emits the
+  // bf16 copy of the stream and its row statistics for the first c_qkv
   PCD_TRY(pcd_embed_tokens(x, x_seqs, d.c_in, d.n_points, d.in_w, d.in_b, prefix, d.n_prefix, addc, d.ln_pre_g,
-                           d.ln_pre_b, d.ln_eps, w.h, seqs, W, stream));
+                           d.ln_pre_b, d.ln_eps, w.h, seqs, W, fold ? (uint16_t*)w.xn : nullptr, fold ? w.stats : nullptr,
+                           stream));
 
   const float qk_scale = 1.0f / sqrtf(sqrtf(64.0f));  // hd^-1/4 on q and on k (transformer.py:76)
   const int prec = d.precision;
@@ -297,18 +308,8 @@ extern "C" int pcd_model_forward(pcd_model* m, const float* x, int x_seqs, const
       return pcd_gemm_bf16((const uint16_t*)A, lda, (const uint16_t*)Wt, K, bias, nullptr, 0, C, N, PCD_BF16, M, N, K, epi, stream);
     return pcd_gemm_f32((const float*)A, lda, (const float*)Wt, K, bias, nullptr, 0, (float*)C, N, M, N, K, epi, stream);
   };
-  // LayerNorm-folded path (bf16, width % 256 == 0, >= 512 tokens, folded weights supplied): no
-  // LayerNorm kernels at all.  The c_proj / mlp.c_proj GEMMs update the fp32 residual stream in their
-  // epilogue and emit its bf16 copy + per-row statistics; c_qkv / c_fc consume that copy with
-  // W' = gamma o W and apply mean / rstd algebraically in their epilogue (gemm_tc.cu).
-  bool fold = bf && W % 256 == 0 && M >= 512 && !(d.flags & PCD_MODEL_SEPARATE_LAYERNORM);
   const int attn_variant = (d.flags >> PCD_MODEL_ATTN_VARIANT_SHIFT) & 0xff;
-  for (int l = 0; l < d.layers && fold; ++l) {
-    const pcd_block_weights& b = m->blocks[l];
-    fold = b.w_qkv_ln && b.w_fc_ln && b.qkv_colsum && b.qkv_const && b.fc_colsum && b.fc_const;
-  }
   if (fold) {
-    PCD_TRY(pcd_cast_rowstats(w.h, W, (uint16_t*)w.xn, W, w.stats, M, W, stream));
     auto lin_ln = [&](const void* Wt, const float* colsum, const float* cst, void* C, int N, int epi) -> int {
       pcd_gemm_args g = {};
       g.A = w.xn; g.lda = W; g.W = Wt; g.ldw = W; g.bias = cst; g.colsum = colsum; g.stats_in = w.stats;

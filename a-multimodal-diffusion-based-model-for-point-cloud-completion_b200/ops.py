@@ -147,6 +147,47 @@ def attention_hd32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
     return out
 
 
+def embed_tokens(x: torch.Tensor, w_in: torch.Tensor, b_in: torch.Tensor, prefix: Optional[torch.Tensor],
+                 add_cond: Optional[torch.Tensor], ln_g: torch.Tensor, ln_b: torch.Tensor, eps: float = 1e-5,
+                 seqs: Optional[int] = None, with_stats: bool = False):
+    """input_proj + token concat + ln_pre (reference transformer.py:208-220).  x [x_seqs, c_in, n_points] (NCL),
+    prefix [seqs, n_prefix, dim] or None, add_cond [seqs, dim] or None -> h [seqs, n_prefix + n_points, dim] fp32;
+    with_stats also returns (bf16 copy of h, per-128-column (mean, M2) [rows, dim/128, 2]) from the same launch."""
+    require_cuda(x, w_in, b_in, ln_g, ln_b)
+    x_seqs, c_in, n_points = x.shape
+    dim = w_in.shape[0]
+    seqs = x_seqs if seqs is None else seqs
+    n_prefix = 0 if prefix is None else prefix.shape[1]
+    assert x.is_contiguous() and w_in.is_contiguous() and (prefix is None or prefix.is_contiguous())
+    assert add_cond is None or (add_cond.is_contiguous() and add_cond.shape == (seqs, dim))
+    L = n_prefix + n_points
+    h = torch.empty(seqs, L, dim, device=x.device, dtype=torch.float32)
+    hb = stats = None
+    if with_stats:
+        hb = torch.empty(seqs, L, dim, device=x.device, dtype=torch.bfloat16)
+        stats = torch.empty(seqs * L, dim // 128, 2, device=x.device, dtype=torch.float32)
+    opt = lambda t: ptr(t) if t is not None else None
+    check(_lib.load().pcd_embed_tokens(ptr(x), x_seqs, c_in, n_points, ptr(w_in), ptr(b_in), opt(prefix), n_prefix,
+                                       opt(add_cond), ptr(ln_g), ptr(ln_b), float(eps), ptr(h), seqs, dim, opt(hb),
+                                       opt(stats), stream_ptr()), "embed_tokens")
+    return (h, hb, stats) if with_stats else h
+
+
+def output_proj(h: torch.Tensor, n_prefix: int, ln_g: torch.Tensor, ln_b: torch.Tensor, w_out: torch.Tensor,
+                b_out: torch.Tensor, eps: float = 1e-5, y: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ln_post + drop the prefix tokens + output_proj + permute (reference transformer.py:222-226).
+    h [seqs, L, dim] fp32 (+ y, a pending residual of the same shape, bf16 or fp32) -> [seqs, c_out, L - n_prefix]."""
+    require_cuda(h, ln_g, ln_b, w_out, b_out, y)
+    assert h.dtype == torch.float32 and h.is_contiguous() and w_out.is_contiguous()
+    seqs, L, dim = h.shape
+    c_out = w_out.shape[0]
+    out = torch.empty(seqs, c_out, L - n_prefix, device=h.device, dtype=torch.float32)
+    yprec = _PREC[y.dtype] if y is not None else PCD_F32
+    check(_lib.load().pcd_output_proj(ptr(h), ptr(y), yprec, seqs, n_prefix, L - n_prefix, dim, ptr(ln_g), ptr(ln_b),
+                                      float(eps), ptr(w_out), ptr(b_out), c_out, ptr(out), stream_ptr()), "output_proj")
+    return out
+
+
 def cast_rowstats(h: torch.Tensor):
     """bf16 copy of the fp32 residual stream h [rows, dim] + per-128-column (mean, M2) of the rounded
     values [rows, dim/128, 2]: the inputs of the LayerNorm-folded projections."""

@@ -94,12 +94,14 @@ PCD_API int pcd_add_layernorm(float* h, int ldh, const void* y, int ldy, int y_p
  *   l <  n_prefix : row = prefix[s, l, :]                     (conditioning tokens)
  *   l >= n_prefix : row = W_in x[s % x_seqs, :, l-n_prefix] + b_in (+ add_cond[s, :])
  * then h[s, l, :] = LayerNorm(row).  x is [x_seqs, c_in, n_points] (NCL, as the
- * sampler holds it); w_in is [dim, c_in]. */
+ * sampler holds it); w_in is [dim, c_in].  Optional (both or neither, dim % 128 == 0): h_bf16 = bf16 copy of h and
+ * stats float2 [rows, dim/128] = (mean, M2) of the rounded values per 128 columns -- what pcd_cast_rowstats would
+ * compute from h, emitted here so that the LayerNorm-folded forward needs no separate pass over the stream. */
 PCD_API int pcd_embed_tokens(const float* x, int x_seqs, int c_in, int n_points,
                      const float* w_in, const float* b_in,
                      const float* prefix, int n_prefix, const float* add_cond,
                      const float* ln_g, const float* ln_b, float eps,
-                     float* h, int seqs, int dim, void* stream);
+                     float* h, int seqs, int dim, uint16_t* h_bf16, float* stats, void* stream);
 
 /* ln_post + token slice + output_proj + NLC->NCL permute (transformer.py:222-226):
  * out[s, c, n] = W_out[c, :] . LayerNorm(h[s, n_prefix + n, :] (+ y[...])) + b_out[c];

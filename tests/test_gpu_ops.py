@@ -136,6 +136,62 @@ def test_cast_rowstats():
     assert rel(stats, want) < 1e-5, describe(stats, want)
 
 
+@pytest.mark.parametrize("dim,c_in,n_prefix,x_seqs,with_cond", [(512, 6, 2, 3, False), (512, 3, 0, 6, True),
+                                                                 (1024, 6, 258, 2, False), (384, 6, 1, 6, False)])
+def test_embed_tokens(dim, c_in, n_prefix, x_seqs, with_cond):
+    """input_proj + concat + ln_pre (reference transformer.py:208-220) against torch, and the bf16 copy + row statistics
+    the same launch emits for the LayerNorm-folded forward: bit-identical to pcd_cast_rowstats of its own fp32 output."""
+    seqs, n = 6, 333
+    x = det.normal((x_seqs, c_in, n), 840).to(DEV)
+    w = det.uniform((dim, c_in), 841, 1 / math.sqrt(c_in)).to(DEV)
+    b = det.uniform((dim,), 842, 0.5).to(DEV)
+    prefix = det.normal((seqs, n_prefix, dim), 843).to(DEV) if n_prefix else None
+    cond = det.normal((seqs, dim), 844).to(DEV) if with_cond else None
+    g = (1.0 + 0.1 * det.normal((dim,), 845)).to(DEV)
+    beta = (0.1 * det.normal((dim,), 846)).to(DEV)
+    stats_ok = dim % 128 == 0
+    if stats_ok:
+        h, hb, stats = ops.embed_tokens(x, w, b, prefix, cond, g, beta, 1e-5, seqs=seqs, with_stats=True)
+    else:
+        h = ops.embed_tokens(x, w, b, prefix, cond, g, beta, 1e-5, seqs=seqs)
+    torch.cuda.synchronize()
+    xt = x.repeat(seqs // x_seqs, 1, 1).double()
+    tok = xt.permute(0, 2, 1) @ w.double().t() + b.double()
+    if cond is not None:
+        tok = tok + cond.double()[:, None]
+    if prefix is not None:
+        tok = torch.cat([prefix.double(), tok], dim=1)
+    want = torch.nn.functional.layer_norm(tok, (dim,), g.double(), beta.double(), 1e-5)
+    assert rel(h, want) < 2e-6, describe(h, want)
+    assert torch.equal(h, ops.embed_tokens(x, w, b, prefix, cond, g, beta, 1e-5, seqs=seqs)), "same fp32 stream either way"
+    if stats_ok:
+        hb2, stats2 = ops.cast_rowstats(h.view(-1, dim))
+        assert torch.equal(hb.view(-1, dim), hb2) and torch.equal(stats, stats2)
+    else:
+        with pytest.raises(RuntimeError, match="128"):
+            ops.embed_tokens(x, w, b, prefix, cond, g, beta, 1e-5, seqs=seqs, with_stats=True)
+
+
+@pytest.mark.parametrize("dim,c_out,n_prefix,with_y", [(512, 6, 2, False), (512, 3, 0, False), (384, 6, 1, False),
+                                                        (512, 12, 2, False), (512, 6, 2, True), (1024, 6, 258, False)])
+def test_output_proj(dim, c_out, n_prefix, with_y):
+    """ln_post + slice + output_proj + permute (reference transformer.py:222-226) against torch in fp64, for the
+    register-resident kernel (no pending residual, width <= 512, 3 / 6 channels) and the general one."""
+    seqs, n = 5, 333
+    h = (det.normal((seqs, n_prefix + n, dim), 850) * 2.0 + 0.3).to(DEV)
+    y = det.normal((seqs, n_prefix + n, dim), 851).to(DEV) if with_y else None
+    g = (1.0 + 0.1 * det.normal((dim,), 852)).to(DEV)
+    beta = (0.1 * det.normal((dim,), 853)).to(DEV)
+    w = det.uniform((c_out, dim), 854, 1 / math.sqrt(dim)).to(DEV)
+    b = det.uniform((c_out,), 855, 0.5).to(DEV)
+    got = ops.output_proj(h, n_prefix, g, beta, w, b, 1e-5, y=y)
+    torch.cuda.synchronize()
+    hh = h.double() + (y.double() if with_y else 0.0)
+    xn = torch.nn.functional.layer_norm(hh, (dim,), g.double(), beta.double(), 1e-5)[:, n_prefix:]
+    want = (xn @ w.double().t() + b.double()).permute(0, 2, 1)
+    assert got.shape == want.shape and rel(got, want) < 2e-6, describe(got, want)
+
+
 @pytest.mark.parametrize("M,N,K", [(128 * 37 + 5, 512, 512), (2048, 512, 2048), (1500, 1024, 1024), (700, 2048, 512)])
 def test_gemm_residual_stats(M, N, K):
     """PCD_EPI_RESIDUAL_STATS: h <- h + A W^T + b in place, bf16 copy and row statistics

@@ -35,7 +35,15 @@ def t(fn, it=10):
         b.record(); torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b) / it)
     return best * 1e3
+xin = torch.randn(B2 // 2, 6, L - 2, device=dev, generator=g)
+w_in, b_in = torch.randn(W, 6, device=dev, generator=g), bias(W)
+pre = torch.randn(B2, 2, W, device=dev, generator=g)
+ones = torch.ones(W, device=dev)
 res = {
+    "embed": t(lambda: ops.embed_tokens(xin, w_in, b_in, pre, None, ones, b_in, seqs=B2)),
+    "embed_stats": t(lambda: ops.embed_tokens(xin, w_in, b_in, pre, None, ones, b_in, seqs=B2, with_stats=True)),
+    "cast_rowstats": t(lambda: ops.cast_rowstats(h)),
+    "output_proj": t(lambda: ops.output_proj(h.view(B2, L, W), 2, ones, b_in, w_in.t()[:6].contiguous(), b_in[:6])),
     "qkv_lnfold": t(lambda: ops.linear_layernorm_folded(hb, stats, w_qkv, cs_qkv, b3)),
     "proj_resid_stats": t(lambda: ops.linear_residual_stats(a_d, w_proj, b1, h)),
     "fc1_lnfold_gelu": t(lambda: ops.linear_layernorm_folded(hb, stats, w_fc, cs_fc, b4, gelu=True)),
@@ -43,4 +51,4 @@ res = {
     "fc1_plain_gelu": t(lambda: ops.linear(a_d, w_fc, b4, epilogue=1, out=hid)),
     "attention": t(lambda: ops.self_attention(qkv, H)),
 }
-print("  ".join(f"{k} {v:.1f}" for k, v in res.items()), " sum %.1f us" % sum(v for k, v in res.items() if k != "fc1_plain_gelu"))
+print("  ".join(f"{k} {v:.1f}" for k, v in res.items()), " sum %.1f us" % sum(v for k, v in res.items() if k in ("qkv_lnfold", "proj_resid_stats", "fc1_lnfold_gelu", "fc2_resid_stats", "attention")))
