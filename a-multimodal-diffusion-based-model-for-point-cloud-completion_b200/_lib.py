@@ -57,6 +57,7 @@ class DdpmArgs(C.Structure):  # include/pcd_b200.h: pcd_ddpm_args
 
 
 DDPM_COLS = 8
+DDPM_MEAN_X0, DDPM_MEAN_XT = 2, 3   # posterior_mean_coef1 / coef2 columns (PCD_DDPM_MEAN_X0 / _XT)
 VAR_FIXED, VAR_LEARNED_RANGE, VAR_LEARNED = 0, 1, 2
 
 

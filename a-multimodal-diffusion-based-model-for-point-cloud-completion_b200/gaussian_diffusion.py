@@ -176,31 +176,55 @@ class GaussianDiffusion:
         res["extra"] = extra
         return res
 
-    def p_mean_variance(self, model, x, t, clip_denoised=False, denoised_fn=None, model_kwargs=None):
-        """Same contract as the reference (:257-350): dict with mean / variance / log_variance / pred_xstart / extra."""
-        if denoised_fn is not None:
-            raise NotImplementedError("denoised_fn is not used by any caller of the reference's sampling path")
-        r = self._ddpm_step(model, x, t, clip_denoised, model_kwargs, None, ("mean", "log_variance", "pred_xstart"))
+    def _variance_of(self, r, x, t):
         if self._var_mode() == _lib.VAR_FIXED:
             # table lookup like the reference (:305-318): at t = 0 of fixed_small this is 0, not exp(clipped log)
             tab = (np.append(self.posterior_variance[1], self.betas[1:]) if self.model_var_type == "fixed_large"
                    else self.posterior_variance)
             row = th.from_numpy(tab).float().to(x.device)[t.to(x.device).long()]
-            variance = row.view(-1, *([1] * (x.dim() - 1))).expand_as(x).contiguous()
+            return row.view(-1, *([1] * (x.dim() - 1))).expand_as(x).contiguous()
+        return th.exp(r["log_variance"])
+
+    def p_mean_variance(self, model, x, t, clip_denoised=False, denoised_fn=None, model_kwargs=None):
+        """Same contract as the reference (:257-350): dict with mean / variance / log_variance / pred_xstart / extra.
+        ``denoised_fn`` (an arbitrary callable on the x_0 prediction, applied before the clamp, :321-326) splits the
+        fused step at the hook: the kernel produces the raw x_0 and the variance, the posterior mean of the hooked x_0
+        (:240-243) is two device-side multiply-adds."""
+        if denoised_fn is None:
+            r = self._ddpm_step(model, x, t, clip_denoised, model_kwargs, None, ("mean", "log_variance", "pred_xstart"))
+            mean, x0 = r["mean"], r["pred_xstart"]
         else:
-            variance = th.exp(r["log_variance"])
-        return {"mean": r["mean"], "variance": variance, "log_variance": r["log_variance"],
-                "pred_xstart": r["pred_xstart"], "extra": r["extra"]}
+            r = self._ddpm_step(model, x, t, False, model_kwargs, None, ("log_variance", "pred_xstart"))
+            x0 = denoised_fn(r["pred_xstart"])
+            if clip_denoised:
+                x0 = x0.clamp(-1, 1)
+            rows = self._ddpm_table(x.device)[t.to(x.device).long()]
+            col = lambda c: rows[:, c].view(-1, *([1] * (x.dim() - 1)))
+            mean = col(_lib.DDPM_MEAN_X0) * x0 + col(_lib.DDPM_MEAN_XT) * x
+        return {"mean": mean, "variance": self._variance_of(r, x, t), "log_variance": r["log_variance"],
+                "pred_xstart": x0, "extra": r["extra"]}
+
+    def condition_mean(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        """mean + variance * grad log p(y | x) (:374-385, Sohl-Dickstein et al. conditioning)."""
+        gradient = cond_fn(x, t, **(model_kwargs or {}))
+        return p_mean_var["mean"].float() + p_mean_var["variance"] * gradient.float()
 
     def p_sample(self, model, x, t, clip_denoised=False, denoised_fn=None, cond_fn=None, model_kwargs=None,
                  noise: Optional[th.Tensor] = None):
-        """x_{t-1} ~ p(. | x_t) (:407-449).  ``noise`` optionally replaces the torch draw (tests)."""
-        if denoised_fn is not None or cond_fn is not None:
-            raise NotImplementedError("denoised_fn / cond_fn are not used by any caller of the reference's sampling path")
+        """x_{t-1} ~ p(. | x_t) (:407-449).  ``noise`` optionally replaces the torch draw (tests).  Without hooks this is
+        ONE fused kernel; with ``denoised_fn`` / ``cond_fn`` the step is split around the callables."""
         if noise is None:
             noise = th.randn_like(x)
-        r = self._ddpm_step(model, x, t, clip_denoised, model_kwargs, noise.to(x), ("x_next", "pred_xstart"))
-        return {"sample": r["x_next"], "pred_xstart": r["pred_xstart"]}
+        if denoised_fn is None and cond_fn is None:
+            r = self._ddpm_step(model, x, t, clip_denoised, model_kwargs, noise.to(x), ("x_next", "pred_xstart"))
+            return {"sample": r["x_next"], "pred_xstart": r["pred_xstart"]}
+        out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                   model_kwargs=model_kwargs)
+        if cond_fn is not None:
+            out["mean"] = self.condition_mean(cond_fn, out, x, t, model_kwargs=model_kwargs)
+        nonzero = (t.to(x.device) != 0).float().view(-1, *([1] * (x.dim() - 1)))  # no noise when t == 0
+        sample = out["mean"] + nonzero * th.exp(0.5 * out["log_variance"]) * noise.to(x)
+        return {"sample": sample, "pred_xstart": out["pred_xstart"]}
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=False, denoised_fn=None, cond_fn=None,
                                   model_kwargs=None, device=None, progress=False, temp=1.0,
@@ -208,8 +232,6 @@ class GaussianDiffusion:
         """Generator over the T ancestral steps (:499-548); every yield is the *unscaled* {"sample", "pred_xstart"}
         dict like the reference's ``unscale_out_dict(out)``.  ``noise_fn(shape)`` optionally replaces the torch draws
         (x_T first, then one per step, the reference's order)."""
-        if denoised_fn is not None or cond_fn is not None:
-            raise NotImplementedError("denoised_fn / cond_fn are not used by any caller of the reference's sampling path")
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
@@ -220,9 +242,16 @@ class GaussianDiffusion:
         if progress:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
+        hooked = denoised_fn is not None or cond_fn is not None
         with th.no_grad():
             for i in indices:
                 t = th.full((shape[0],), i, device=device, dtype=th.int64)
+                if hooked:
+                    out = self.p_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                        cond_fn=cond_fn, model_kwargs=model_kwargs, noise=draw(tuple(shape)).to(img))
+                    yield self.unscale_out_dict(out)
+                    img = out["sample"].contiguous()
+                    continue
                 r = self._ddpm_step(model, img, t, clip_denoised, model_kwargs, draw(tuple(shape)).to(img),
                                     ("x_next", "pred_xstart", "sample_unscaled"))
                 yield {"sample": r["sample_unscaled"], "pred_xstart": r["pred_xstart"]}

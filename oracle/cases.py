@@ -194,7 +194,24 @@ DDPM_CASES = {
                                scaled=False, via="loop", B=2, noise_seed=9202),
     "fixed_large_cosine": dict(model="small_uncond_c6", schedule="cosine", timesteps=16, var_type="fixed_large",
                                scaled=True, via="loop", B=3, noise_seed=9203),
+    # the denoised_fn / cond_fn hooks of p_mean_variance / p_sample (:321-326, 374-385, 433-436), see ddpm_hooks()
+    "hooks_learned_range": dict(model="small_uncond", schedule="cosine", timesteps=12, var_type="learned_range",
+                                scaled=True, via="loop", B=3, noise_seed=9204, hooks=True),
+    "hooks_fixed_small": dict(model="small_uncond_c6", schedule="linear", timesteps=24, var_type="fixed_small",
+                              scaled=False, via="loop", B=2, noise_seed=9205, hooks=True),
 }
+
+
+def ddpm_hooks():
+    """Deterministic stand-ins for the user callables of the hook cases: a squashing ``denoised_fn`` and a ``cond_fn``
+    (gradient of a quadratic log-likelihood pulling towards 0.1, growing with the step index)."""
+    def denoised_fn(x0):
+        return 0.9 * torch.tanh(x0)
+
+    def cond_fn(x, t, **kwargs):
+        return 0.25 * (0.1 - x) * (1.0 + 0.05 * t.to(x.device).float().view(-1, 1, 1))
+
+    return denoised_fn, cond_fn
 
 
 def ddpm_kwargs(case):

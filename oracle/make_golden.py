@@ -238,6 +238,7 @@ def gen_ddpm(m, case):
                                      model_mean_type="epsilon", model_var_type=dc["var_type"], loss_type="mse", **scales)
     C, N, B = cfg["input_channels"], cfg["n_ctx"], dc["B"]
     kw = cases.ddpm_kwargs(case)
+    hooks = dict(zip(("denoised_fn", "cond_fn"), cases.ddpm_hooks())) if dc.get("hooks") else {}
     with patched_noise(cases.DetNoise(dc["noise_seed"])), torch.no_grad():
         if dc["via"] == "sampler":
             sampler = m.sampler.PointCloudSampler(
@@ -248,13 +249,14 @@ def gen_ddpm(m, case):
             arrays = dict(pred=preds)
         else:
             outs = list(diffusion.p_sample_loop_progressive(model, (B, C, N), clip_denoised=True, model_kwargs=kw,
-                                                            device=torch.device("cpu")))
+                                                            device=torch.device("cpu"), **hooks))
             arrays = dict(pred=torch.stack([o["pred_xstart"] for o in outs]),
                           sample=torch.stack([o["sample"] for o in outs]))
             # one p_mean_variance call (scaled units, no clipping) at a mixed batch of step indices
             x = det.normal((B, C, N), dc["noise_seed"] + 5)
             t = torch.tensor([(dc["timesteps"] - 1, 0, dc["timesteps"] // 2)[i % 3] for i in range(B)])
-            pmv = diffusion.p_mean_variance(model, x, t, clip_denoised=False, model_kwargs=kw)
+            pmv = diffusion.p_mean_variance(model, x, t, clip_denoised=False, model_kwargs=kw,
+                                            denoised_fn=hooks.get("denoised_fn"))
             arrays.update(pmv_mean=pmv["mean"], pmv_log_variance=pmv["log_variance"].expand_as(x).clone(),
                           pmv_variance=pmv["variance"].expand_as(x).clone(), pmv_pred=pmv["pred_xstart"])
     print("  ", {k: tuple(v.shape) for k, v in arrays.items()}, float(arrays["pred"].std()))

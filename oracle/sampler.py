@@ -345,8 +345,9 @@ def karras_progressive(model_fn, diffusion, shape, steps, sampler="heun", sigma_
 # Ancestral (DDPM) sampling of reference gaussian_diffusion.py (row f4 of SURVEY 8)
 # ---------------------------------------------------------------------------
 def p_mean_variance(tables: Tables, model_out: torch.Tensor, x: torch.Tensor, t: torch.Tensor, var_type: str,
-                    clip_denoised: bool):
-    """reference gaussian_diffusion.py:257-350 for epsilon-prediction models, given the model output."""
+                    clip_denoised: bool, denoised_fn: Optional[Callable] = None):
+    """reference gaussian_diffusion.py:257-350 for epsilon-prediction models, given the model output; ``denoised_fn``
+    acts on the x_0 prediction before the clamp (:321-326)."""
     ex = lambda arr: torch.from_numpy(arr)[t.cpu()].float().to(x.device)[(...,) + (None,) * (x.dim() - 1)]
     C = x.shape[1]
     if var_type in ("learned", "learned_range"):
@@ -368,6 +369,8 @@ def p_mean_variance(tables: Tables, model_out: torch.Tensor, x: torch.Tensor, t:
             var = ex(tables.posterior_variance).expand_as(x)
             log_var = ex(tables.posterior_log_variance_clipped).expand_as(x)
     x0 = ex(tables.sqrt_recip_alphas_cumprod) * x - ex(tables.sqrt_recipm1_alphas_cumprod) * eps
+    if denoised_fn is not None:
+        x0 = denoised_fn(x0)
     if clip_denoised:
         x0 = x0.clamp(-1, 1)
     mean = ex(tables.posterior_mean_coef1) * x0 + ex(tables.posterior_mean_coef2) * x
@@ -375,9 +378,11 @@ def p_mean_variance(tables: Tables, model_out: torch.Tensor, x: torch.Tensor, t:
 
 
 def ddpm_progressive(model_fn, tables: Tables, shape, var_type: str, clip_denoised: bool = True, model_kwargs=None,
-                     noise_fn: Optional[Callable] = None):
+                     noise_fn: Optional[Callable] = None, denoised_fn: Optional[Callable] = None,
+                     cond_fn: Optional[Callable] = None):
     """reference gaussian_diffusion.py:407-449 (p_sample) inside :499-548 (p_sample_loop_progressive): x_T ~ N(0, I);
-    for t = T-1 .. 0: x <- mean + [t != 0] exp(log_var / 2) noise.  Yields the unscaled dicts like the reference."""
+    for t = T-1 .. 0: x <- mean + [t != 0] exp(log_var / 2) noise, with the mean shifted by variance * cond_fn(x, t)
+    when a ``cond_fn`` is given (condition_mean, :374-385).  Yields the unscaled dicts like the reference."""
     model_kwargs = model_kwargs or {}
     if noise_fn is None:
         noise_fn = lambda shp: torch.randn(*shp)
@@ -387,7 +392,9 @@ def ddpm_progressive(model_fn, tables: Tables, shape, var_type: str, clip_denois
         out = model_fn(x, t, **model_kwargs)
         if isinstance(out, tuple):
             out = out[0]
-        r = p_mean_variance(tables, out, x, t, var_type, clip_denoised)
+        r = p_mean_variance(tables, out, x, t, var_type, clip_denoised, denoised_fn)
+        if cond_fn is not None:
+            r["mean"] = r["mean"] + r["variance"] * cond_fn(x, t, **model_kwargs)
         noise = noise_fn(tuple(shape))
         sample = r["mean"] + (0.0 if i == 0 else 1.0) * torch.exp(0.5 * r["log_variance"]) * noise
         yield {"sample": tables.unscale(sample), "pred_xstart": tables.unscale(r["pred_xstart"])}

@@ -56,6 +56,8 @@ def test_ddpm_loop_matches_reference(case):
     kw = to_dev(cases.ddpm_kwargs(case))
     noise = cases.DetNoise(dc["noise_seed"])
     draw = lambda shp: noise(shp).to(DEV)
+    # denoised_fn / cond_fn cases (:321-326,374-385,433-436): the fused step is split around the user callables
+    hooks = dict(zip(("denoised_fn", "cond_fn"), cases.ddpm_hooks())) if dc.get("hooks") else {}
     if dc["via"] == "sampler":
         sampler = P.PointCloudSampler(device=DEV, models=[model], diffusions=[diffusion], num_points=[N],
                                       aux_channels=["R", "G", "B"][: C - 3], guidance_scale=[0.0], use_karras=[False],
@@ -63,16 +65,18 @@ def test_ddpm_loop_matches_reference(case):
         preds = torch.stack([y.clone() for y in sampler.sample_batch_progressive(B, kw)])
     else:
         outs = list(diffusion.p_sample_loop_progressive(model, (B, C, N), clip_denoised=True, model_kwargs=kw, device=DEV,
-                                                        noise_fn=draw))
+                                                        noise_fn=draw, **hooks))
         preds = torch.stack([o["pred_xstart"] for o in outs])
         samples = torch.stack([o["sample"] for o in outs])
         assert rel(samples, g["sample"]) < 1e-3, describe(samples, g["sample"], "samples")
         noise.__init__(dc["noise_seed"])
-        final = diffusion.p_sample_loop(model, (B, C, N), clip_denoised=True, model_kwargs=kw, device=DEV, noise_fn=draw)
+        final = diffusion.p_sample_loop(model, (B, C, N), clip_denoised=True, model_kwargs=kw, device=DEV, noise_fn=draw,
+                                        **hooks)
         assert torch.equal(final, samples[-1])
         x = det.normal((B, C, N), dc["noise_seed"] + 5).to(DEV)
         t = torch.tensor([(dc["timesteps"] - 1, 0, dc["timesteps"] // 2)[i % 3] for i in range(B)], device=DEV)
-        r = diffusion.p_mean_variance(model, x, t, clip_denoised=False, model_kwargs=kw)
+        r = diffusion.p_mean_variance(model, x, t, clip_denoised=False, model_kwargs=kw,
+                                      denoised_fn=hooks.get("denoised_fn"))
         for k, gk in (("mean", "pmv_mean"), ("variance", "pmv_variance"), ("log_variance", "pmv_log_variance"),
                       ("pred_xstart", "pmv_pred")):
             assert rel(r[k], g[gk]) < TOL_F32, describe(r[k], g[gk], k)

@@ -204,8 +204,9 @@ def test_ddpm_ancestral_loop(case):
     shape = (dc["B"], cfg["input_channels"], cfg["n_ctx"])
     fn = S.make_model_fn(sd, cfg)
     kw = cases.ddpm_kwargs(case)
+    hooks = dict(zip(("denoised_fn", "cond_fn"), cases.ddpm_hooks())) if dc.get("hooks") else {}
     with torch.no_grad():
-        outs = list(S.ddpm_progressive(fn, tab, shape, dc["var_type"], True, kw, cases.DetNoise(dc["noise_seed"])))
+        outs = list(S.ddpm_progressive(fn, tab, shape, dc["var_type"], True, kw, cases.DetNoise(dc["noise_seed"]), **hooks))
     preds = torch.stack([o["pred_xstart"] for o in outs])
     assert preds.shape == g["pred"].shape
     assert rel_l2(preds[:2], g["pred"][:2]) < 1e-5 and rel_l2(preds, g["pred"]) < 1e-3
@@ -214,7 +215,7 @@ def test_ddpm_ancestral_loop(case):
         x = det.normal(shape, dc["noise_seed"] + 5)
         t = torch.tensor([(dc["timesteps"] - 1, 0, dc["timesteps"] // 2)[i % 3] for i in range(dc["B"])])
         with torch.no_grad():
-            r = S.p_mean_variance(tab, fn(x, t, **kw), x, t, dc["var_type"], False)
+            r = S.p_mean_variance(tab, fn(x, t, **kw), x, t, dc["var_type"], False, hooks.get("denoised_fn"))
         for k in ("mean", "log_variance", "variance"):
             assert rel_l2(r[k], g["pmv_" + k]) < 1e-5, k
         assert rel_l2(r["pred_xstart"], g["pmv_pred"]) < 1e-5
