@@ -546,7 +546,19 @@ def kernel_breakdown(P, B2, L, width, heads, layers, evals, Bc, C, N, pk, min_se
         add("gemm_fc2_resid_stats", lambda: ops.linear_residual_stats(a_4d, w_fc2, bias(width), h), per,
             flops=2.0 * M * 4 * width * width)
         res["gemm_fc2_resid_stats"]["hbm_gbs"] = M * width * 18.0 / (res["gemm_fc2_resid_stats"]["ms"] * 1e-3) / 1e9
-        add("cast_rowstats", lambda: ops.cast_rowstats(h), evals, bytes_=M * width * 6.0)
+        # token assembly + ln_pre (emits the fp32 stream, its bf16 copy and the row statistics: 6 bytes per element)
+        # and ln_post + output projection (reads the fp32 stream of the point tokens), once per evaluation
+        n_pre = L - N
+        x_in = torch.randn(Bc, C, N, device=dev, generator=g)   # guided: both halves of the 2B batch share x
+        w_in = torch.randn(width, C, device=dev, generator=g)
+        pre = torch.randn(B2, n_pre, width, device=dev, generator=g) if n_pre else None
+        ones, zeros = torch.ones(width, device=dev), torch.zeros(width, device=dev)
+        add("embed_tokens_ln_stats", lambda: ops.embed_tokens(x_in, w_in, zeros, pre, None, ones, zeros, seqs=B2, with_stats=True),
+            evals, bytes_=M * width * 6.0)
+        w_out = torch.randn(C, width, device=dev, generator=g)
+        h3 = h.view(B2, L, width)
+        add("ln_output_proj", lambda: ops.output_proj(h3, n_pre, ones, zeros, w_out, zeros[:C]), evals,
+            bytes_=B2 * N * width * 4.0)
     else:
         add("gemm_qkv", lambda: ops.linear(a_d, w_qkv, bias(3 * width), out=qkv), per, flops=2.0 * M * 3 * width * width)
         add("gemm_attn_proj", lambda: ops.linear(a_d, w_proj, bias(width), out=y), per, flops=2.0 * M * width * width)
