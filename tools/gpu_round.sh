@@ -20,6 +20,7 @@ run sampler    900 $PYT tests/test_gpu_sampler.py
 run twostream  600 $PYT tests/test_gpu_twostream.py
 run ddpm       300 $PYT tests/test_gpu_ddpm.py
 run dist       300 $PYT tests/test_gpu_dist.py
+run guard      600 $PYT tests/test_gpu_guard.py
 run smoke      600 python __graft_entry__.py --smoke
 TAILN=3 run bench 1800 python bench.py --steps ${BENCH_STEPS:-3} --warmup 3 ${BENCH_ARGS:-}
 grep -h '^{' $OUT/bench.log | tail -1 > $OUT/bench.json
