@@ -49,16 +49,19 @@ constexpr int TILE_BYTES = 2 * NT * Q_TILE + (KSK + KSV) * KV_TILE + 4 * NT * O_
 constexpr int BAR_BYTES = 1024;
 constexpr int SMEM_BYTES = TILE_BYTES + 1024 + BAR_BYTES;
 constexpr int TMEM_COLS = 512;
+// TMEM columns per slot: S 64 (fp32), P 32 (bf16 pairs), O 64.  TAIL kernels (see below) give P eight more columns for
+// the 16-key tail group: S 0..191, O 192..383, P 384..503.
+constexpr int MAX_TAIL = 4;
 __host__ __device__ constexpr int s_col(int s) { return s * 64; }
-__host__ __device__ constexpr int p_col(int s) { return 192 + s * 32; }
-__host__ __device__ constexpr int o_col(int s) { return 288 + s * 64; }
+template <int TAIL> __host__ __device__ constexpr int p_col(int s) { return TAIL ? 384 + s * 40 : 192 + s * 32; }
+template <int TAIL> __host__ __device__ constexpr int o_col(int s) { return TAIL ? 192 + s * 64 : 288 + s * 64; }
 
 // barrier slots (8 bytes each)
 constexpr int B_Q_FULL = 0, B_Q_EMPTY = B_Q_FULL + 2 * NT, B_Q_ROT = B_Q_EMPTY + 2 * NT, B_K_FULL = B_Q_ROT + 2 * NT,
               B_K_EMPTY = B_K_FULL + KSK, B_K_ROT = B_K_EMPTY + KSK, B_V_FULL = B_K_ROT + KSK,
               B_V_EMPTY = B_V_FULL + KSV, B_S_FULL = B_V_EMPTY + KSV, B_S_FREE = B_S_FULL + NT,
               B_P_READY = B_S_FREE + NT, B_PV_DONE = B_P_READY + NT, B_O_FREE = B_PV_DONE + NT,
-              B_TOK = B_O_FREE + NT, B_COUNT = B_TOK + 4 * NT;
+              B_TOK = B_O_FREE + NT, B_T_FULL = B_TOK + 4 * NT, B_T_FREE = B_T_FULL + NT, B_COUNT = B_T_FREE + NT;
 static_assert(B_COUNT * 8 + 16 <= BAR_BYTES, "barrier block too small");
 
 __device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
@@ -101,6 +104,12 @@ __device__ __forceinline__ float ex2v(float x) {
 __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
                : "memory");
 }
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
@@ -181,7 +190,15 @@ __device__ unsigned long long g_trace[NT * TRACE_STEPS * TRACE_PTS];
 #endif
 
 // TOKEN = 0 (default): warps exponentiate whenever they are ready; 1: MUFU hand-off ring (A/B of the ring itself)
-template <int TOKEN>
+// TAIL = 1: len_kv = 64 n + t with 1 <= t <= MAX_TAIL (every registered config: L = 1025 / 1026 / 1281 / 4097 / 4353 have
+// t = 1 or 2).  The t keys do not get a KV step of their own (a step whose exponentials are already skipped still costs
+// its barrier round trips: 18.5 us of 399 at L = 1026).  Instead
+//   * S_tail[s] = Q[s] K_tail^T (N = 16) is issued once per item, right after the first QK^T, into the slot's O columns --
+//     free until the first PV of the item -- and read (4 columns) by the softmax warps during step 0;
+//   * the tail scores join the row maximum, exponentials and row sum of the LAST full step, their P goes to eight extra
+//     P columns, and the PV issuer appends one K = 16 product with the V_tail tile (rows beyond len_kv are zero-filled by
+//     TMA, the matching P entries are zero).
+template <int TOKEN, int TAIL>
 __global__ void __launch_bounds__(512, 1)
 attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
@@ -202,8 +219,9 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint32_t tid = threadIdx.x;
   pin(tid);
   const int warp = tid >> 5, lane = tid & 31;
-  const int num_kv = (len_kv + BKV - 1) / BKV;
-  const int last_valid = len_kv - (num_kv - 1) * BKV;  // keys in the last KV tile (1..64)
+  const int num_kv = TAIL ? len_kv / BKV : (len_kv + BKV - 1) / BKV;   // KV steps (TAIL: full tiles only)
+  const int last_valid = TAIL ? BKV : len_kv - (num_kv - 1) * BKV;      // keys in the last KV tile (1..64)
+  const int tail = TAIL ? len_kv - num_kv * BKV : 0;                    // keys handled outside the steps (TAIL)
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   ItemIter items((int)blockIdx.x, (int)gridDim.x, ngroups, heads, nq);  // every role walks its own copy
 
@@ -232,6 +250,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       bar_init(bar(B_P_READY + s), 4);
       bar_init(bar(B_PV_DONE + s), 1);
       bar_init(bar(B_O_FREE + s), 4);
+      bar_init(bar(B_T_FULL + s), 1);
+      bar_init(bar(B_T_FREE + s), 4);
     }
     for (int i = 0; i < 4 * NT; ++i) bar_init(bar(B_TOK + i), 1);
     fence_barrier_init();
@@ -267,17 +287,29 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               ++qcnt[s];
             }
           }
-          for (int j = 0; j < num_kv; ++j) {
-            bar_wait(bar(B_K_EMPTY + kst), kph);
-            bar_expect_tx(bar(B_K_FULL + kst), KV_TILE);
-            tma4(sK + kst * KV_TILE, &tmK, bar(B_K_FULL + kst), 0, it.h, j * BKV, it.b);
-            if (++kst == KSK) {
-              kst = 0;
-              kph ^= 1;
+          // ring order (the consumers walk it the same way): K_0, [K_tail], V_0, K_1, V_1, ..., [V_tail]
+          for (int j = 0; j < num_kv + (TAIL ? 1 : 0); ++j) {
+            if (j < num_kv) {
+              bar_wait(bar(B_K_EMPTY + kst), kph);
+              bar_expect_tx(bar(B_K_FULL + kst), KV_TILE);
+              tma4(sK + kst * KV_TILE, &tmK, bar(B_K_FULL + kst), 0, it.h, j * BKV, it.b);
+              if (++kst == KSK) {
+                kst = 0;
+                kph ^= 1;
+              }
+            }
+            if (TAIL && j == 0) {
+              bar_wait(bar(B_K_EMPTY + kst), kph);
+              bar_expect_tx(bar(B_K_FULL + kst), KV_TILE);
+              tma4(sK + kst * KV_TILE, &tmK, bar(B_K_FULL + kst), 0, it.h, num_kv * BKV, it.b);
+              if (++kst == KSK) {
+                kst = 0;
+                kph ^= 1;
+              }
             }
             bar_wait(bar(B_V_EMPTY + vst), vph);
             bar_expect_tx(bar(B_V_FULL + vst), KV_TILE);
-            tma4(sV + vst * KV_TILE, &tmV, bar(B_V_FULL + vst), 0, it.h, j * BKV, it.b);
+            tma4(sV + vst * KV_TILE, &tmV, bar(B_V_FULL + vst), 0, it.h, j * BKV, it.b);   // j == num_kv: V_tail
             if (++vst == KSV) {
               vst = 0;
               vph ^= 1;
@@ -332,6 +364,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         uint32_t kph = 0;
         uint32_t qcnt[NT] = {0, 0, 0};
         uint32_t su[NT] = {0, 0, 0};  // S products issued per slot
+        uint32_t nq_items[NT] = {0, 0, 0};  // items the slot took part in (TAIL: parity of O_FREE)
+        constexpr uint32_t idesc_tail = idesc_bf16_f32(BQ, 16, 0);
         for (int k = 0; k < my_items; ++k, items.next()) {
           const Item it = items.get();
           uint64_t adesc[NT];
@@ -363,14 +397,36 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               }
             }
             commit(bar(B_K_EMPTY + kst));
+            if (++kst == KSK) {
+              kst = 0;
+              kph ^= 1;
+            }
+            if (TAIL && j == 0) {
+              // S_tail[s] -> the slot's O columns (free once the previous item's epilogue has read O)
+              bar_wait(bar(kbar + kst), kph);
+              const uint64_t tdesc = smem_desc_sw128(sK + kst * KV_TILE);
+#pragma unroll
+              for (int s = 0; s < NT; ++s) {
+                if (s < it.n_act) {
+                  if (nq_items[s] > 0) bar_wait(bar(B_O_FREE + s), (nq_items[s] - 1) & 1);
+                  ++nq_items[s];
+                  tcgen05_fence_after();
+                  const uint32_t t_tmem = tmem_base + o_col<TAIL>(s);
+#pragma unroll
+                  for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(t_tmem, adesc[s] + 2 * kk, tdesc + 2 * kk, idesc_tail, kk != 0);
+                  commit(bar(B_T_FULL + s));
+                }
+              }
+              commit(bar(B_K_EMPTY + kst));
+              if (++kst == KSK) {
+                kst = 0;
+                kph ^= 1;
+              }
+            }
             if (last) {
 #pragma unroll
               for (int s = 0; s < NT; ++s)
                 if (s < it.n_act) commit(bar(B_Q_EMPTY + qi[s]));
-            }
-            if (++kst == KSK) {
-              kst = 0;
-              kph ^= 1;
             }
           }
         }
@@ -388,18 +444,30 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const Item it = items.get();
           for (int j = 0; j < num_kv; ++j) {
             bar_wait(bar(B_V_FULL + vst), vph);
-            const int nks = (j == num_kv - 1) ? nks_last : BKV / 16;
+            const bool lastj = (j == num_kv - 1);
+            const int nks = lastj ? nks_last : BKV / 16;
             const uint32_t v_addr = sV + vst * KV_TILE;
+            // TAIL: the last step also consumes the V_tail tile (next ring stage)
+            int tst = vst + 1;
+            uint32_t tph = vph;
+            if (tst == KSV) {
+              tst = 0;
+              tph ^= 1;
+            }
+            if (TAIL && lastj) bar_wait(bar(B_V_FULL + tst), tph);
+            const uint64_t tdesc = smem_desc_sw128(sV + tst * KV_TILE);
 #pragma unroll
             for (int s = 0; s < NT; ++s) {
               if (s < it.n_act) {
                 if (j == 0 && ni[s] > 0) bar_wait(bar(B_O_FREE + s), (ni[s] - 1) & 1);  // previous O read out
                 bar_wait(bar(B_P_READY + s), pu[s] & 1);
                 ++pu[s];
+                if (TAIL && j == 0) bar_wait(bar(B_T_FREE + s), ni[s] & 1);  // S_tail has left the O columns
                 tcgen05_fence_after();
-                const uint32_t o_tmem = tmem_base + o_col(s), p_tmem = tmem_base + p_col(s);
+                const uint32_t o_tmem = tmem_base + o_col<TAIL>(s), p_tmem = tmem_base + p_col<TAIL>(s);
                 for (int kk = 0; kk < nks; ++kk)
                   umma_bf16_ts(o_tmem, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0);
+                if (TAIL && lastj) umma_bf16_ts(o_tmem, p_tmem + 32, tdesc, idesc_pv, 1);
                 commit(bar(B_PV_DONE + s));
               }
             }
@@ -407,6 +475,13 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (++vst == KSV) {
               vst = 0;
               vph ^= 1;
+            }
+            if (TAIL && lastj) {
+              commit(bar(B_V_EMPTY + vst));
+              if (++vst == KSV) {
+                vst = 0;
+                vph ^= 1;
+              }
             }
           }
 #pragma unroll
@@ -423,7 +498,9 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     pin(tm);
     const uint32_t b_sfull = bars + 8 * (B_S_FULL + slot), b_sfree = bars + 8 * (B_S_FREE + slot),
                    b_pready = bars + 8 * (B_P_READY + slot), b_pvdone = bars + 8 * (B_PV_DONE + slot),
-                   b_ofree = bars + 8 * (B_O_FREE + slot), b_tok = bars + 8 * (B_TOK + quarter * NT);
+                   b_ofree = bars + 8 * (B_O_FREE + slot), b_tok = bars + 8 * (B_TOK + quarter * NT),
+                   b_tfull = bars + 8 * (B_T_FULL + slot), b_tfree = bars + 8 * (B_T_FREE + slot);
+    uint32_t nis = 0;  // items this slot has taken part in (TAIL: parity of T_FULL)
     uint32_t u = 0;    // tiles this slot has processed (parity of S_FULL / P_READY / PV_DONE uses)
     uint32_t tk = 0;   // token acquisitions of this warp
     bool stores_pending = false;
@@ -435,6 +512,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int q0 = (it.g * NT + slot) * BQ;
       if (q0 + quarter * 32 >= len_q) {
         // no real query row in this warp (ragged last query tile): keep the slot's barrier counts in step
+        if (TAIL && lane == 0) bar_arrive(b_tfree);
+        ++nis;
         for (int j = 0; j < num_kv; ++j) {
           if (lane == 0) {
             bar_arrive(b_sfree);
@@ -453,6 +532,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t tok_next = b_tok + 8 * ((slot + 1 < ring) ? slot + 1 : 0);
 
       float m_used = 0.f, l_run = 0.f;
+      float ts[MAX_TAIL];   // TAIL: raw scores of the tail keys (-inf beyond the real ones)
       for (int j = 0; j < num_kv; ++j) {
         uint32_t r[BKV];
 #ifdef PCD_ATTN_TRACE
@@ -469,6 +549,21 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(b_sfree);  // S sits in registers: the next QK^T of the slot may overwrite it
+        if (TAIL && j == 0) {
+          // the tail scores wait in the O columns: fetch them before the first PV of the item overwrites O
+          bar_wait(b_tfull, nis & 1);
+          ++nis;
+          tcgen05_fence_after();
+          uint32_t tr[MAX_TAIL];
+          tmem_ld_32x32b_x4(tm + o_col<TAIL>(slot), tr);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) bar_arrive(b_tfree);
+#pragma unroll
+          for (int i = 0; i < MAX_TAIL; ++i) ts[i] = i < tail ? __uint_as_float(tr[i]) : -INFINITY;
+        }
+        const bool with_tail = TAIL && j == num_kv - 1;
         const int nvalid = (j == num_kv - 1) ? last_valid : BKV;
         if (nvalid < BKV) {
 #pragma unroll
@@ -484,6 +579,12 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
             mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
             mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+          }
+          if (with_tail) {
+            mx0 = fmaxf(mx0, ts[0]);
+            mx1 = fmaxf(mx1, ts[1]);
+            mx2 = fmaxf(mx2, ts[2]);
+            mx3 = fmaxf(mx3, ts[3]);
           }
           mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
         }
@@ -502,11 +603,11 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint32_t o[32];
-              tmem_ld_32x32b_x32(tm + o_col(slot) + h * 32, o);
+              tmem_ld_32x32b_x32(tm + o_col<TAIL>(slot) + h * 32, o);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x32b_x32(tm + o_col(slot) + h * 32, o);
+              tmem_st_32x32b_x32(tm + o_col<TAIL>(slot) + h * 32, o);
             }
             tmem_st_wait();
             l_run *= alpha;
@@ -538,7 +639,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               pk[i >> 1] = pack_bf16x2(p0, p1);
               pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
             }
-            tmem_st_32x32b_x8(tm + p_col(slot) + c * 8, pk);
+            tmem_st_32x32b_x8(tm + p_col<TAIL>(slot) + c * 8, pk);
           }
           if (TOKEN && c == 2) {
             // pass the token on one group early: the next warp's wake-up overlaps the last 16 exponentials
@@ -551,6 +652,14 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           unpack2(sum_a, s0, s1);
           unpack2(sum_b, s2, s3);
           l_run += (s0 + s1) + (s2 + s3);
+        }
+        if (with_tail) {
+          // the tail keys: same reference maximum, P into the eight extra columns (keys beyond the tail: exp2(-inf) = 0)
+          const float p0 = ex2v(fmaf(ts[0], scale_log2, -m_used)), p1 = ex2v(fmaf(ts[1], scale_log2, -m_used));
+          const float p2 = ex2v(fmaf(ts[2], scale_log2, -m_used)), p3 = ex2v(fmaf(ts[3], scale_log2, -m_used));
+          l_run += (p0 + p1) + (p2 + p3);
+          uint32_t pk[8] = {pack_bf16x2(p0, p1), pack_bf16x2(p2, p3), 0u, 0u, 0u, 0u, 0u, 0u};
+          tmem_st_32x32b_x8(tm + p_col<TAIL>(slot) + 32, pk);
         }
         PCD_TRACE(6);  // exponentials issued
         tmem_st_wait();
@@ -569,8 +678,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       PCD_TRACE(9);   // last PV complete
       tcgen05_fence_after();
       uint32_t o[HD];
-      tmem_ld_32x32b_x32(tm + o_col(slot), o);
-      tmem_ld_32x32b_x32(tm + o_col(slot) + 32, o + 32);
+      tmem_ld_32x32b_x32(tm + o_col<TAIL>(slot), o);
+      tmem_ld_32x32b_x32(tm + o_col<TAIL>(slot) + 32, o + 32);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
@@ -631,10 +740,10 @@ extern "C" __attribute__((visibility("default"))) int pcd_attn_trace_read(unsign
 }
 #endif
 
-template <int TOKEN>
+template <int TOKEN, int TAIL>
 static int launch_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
                       cudaStream_t st) {
-  auto kern = a8::attn_bf16_tc8_kernel<TOKEN>;
+  auto kern = a8::attn_bf16_tc8_kernel<TOKEN, TAIL>;
   // the attribute is per device: set it on every launch (cheap) rather than caching a per-process flag
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a8::SMEM_BYTES);
   if (e != cudaSuccess) {
@@ -656,11 +765,17 @@ static int launch_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   return PCD_OK;
 }
 
-// token: 1 = MUFU hand-off ring (default), 0 = free-running softmax warps (A/B measurement of the ring)
+// mode: 0 = free-running softmax warps, short tails ride on the last step (default); 1 = MUFU hand-off ring;
+// 2 = like 0 but a short tail stays an ordinary masked KV step (A/B measurements)
 int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
-                    int token, cudaStream_t st) {
-  if (token) return launch_tc8<1>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
-  return launch_tc8<0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+                    int mode, cudaStream_t st) {
+  const bool no_tail = mode == 2;
+  if (mode == 1) return launch_tc8<1, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  // a short tail (1..MAX_TAIL keys beyond the last full KV tile: every registered sequence length) rides on the last step
+  const int tail = len_kv % a8::BKV;
+  if (rope == nullptr && len_kv >= a8::BKV && tail >= 1 && tail <= a8::MAX_TAIL && !no_tail)
+    return launch_tc8<0, 1>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  return launch_tc8<0, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
 }
 
 }  // namespace pcd

@@ -9,7 +9,7 @@ int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
                     int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, int poly,
                     cudaStream_t st);  // attn_tc5.cu
 int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
-                    int token, cudaStream_t st);  // attn_tc8.cu
+                    int mode, cudaStream_t st);  // attn_tc8.cu (mode: 0 default, 1 MUFU token ring, 2 tail keys as a KV step)
 int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const float* coords, int batch, int heads,
                      int len, cudaStream_t st);  // attn_simt.cu
 
@@ -30,7 +30,7 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
     const int64_t nq = (len_q + 127) / 128, grouped_items = ((nq + 2) / 3) * heads * batch;
     variant = (rope != nullptr || grouped_items >= num_sms()) ? PCD_ATTN_GROUPED : PCD_ATTN_PAIRED;
   }
-  const bool grouped = variant == PCD_ATTN_GROUPED || variant == PCD_ATTN_GROUPED_TOKEN;
+  const bool grouped = variant == PCD_ATTN_GROUPED || variant == PCD_ATTN_GROUPED_TOKEN || variant == PCD_ATTN_GROUPED_STEPTAIL;
   if (!grouped && variant != PCD_ATTN_PAIRED &&
       variant != PCD_ATTN_PAIRED_POLY4 && variant != PCD_ATTN_PAIRED_POLY2) {
     set_error("attention(bf16): unknown kernel variant %d", variant);
@@ -48,7 +48,7 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
     const pcd_attn_operand oo = {out, o_bs, o_ls, 64};
     if ((rc = make_operand_map(&to, &oo, batch, heads, len_q, 32)) != PCD_OK) return rc;
     return launch_attn_tc8(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope,
-                           variant == PCD_ATTN_GROUPED_TOKEN, st);
+                           variant == PCD_ATTN_GROUPED_TOKEN ? 1 : (variant == PCD_ATTN_GROUPED_STEPTAIL ? 2 : 0), st);
   }
   if (rope != nullptr) {
     set_error("attention(bf16): the paired kernel takes pre-rotated operands (pcd_rope_bf16); use PCD_ATTN_GROUPED");

@@ -265,8 +265,10 @@ def test_self_attention_lengths(dtype, tol, L):
     assert rel(got.float(), want) < tol, describe(got.float(), want, f"L={L} {dtype}")
 
 
-@pytest.mark.parametrize("variant", [8, 9, 7, 6, 5])
+@pytest.mark.parametrize("variant", [8, 10, 9, 7, 6, 5])
 @pytest.mark.parametrize("B,heads,L,std", [(2, 2, 1, 1.5), (2, 2, 63, 1.5), (3, 2, 64, 1.5), (2, 3, 65, 1.5),
+                                           (2, 3, 66, 1.5), (2, 3, 68, 2.5),  # 1 full KV tile + a 2- / 4-key tail
+                                           (2, 3, 69, 1.5), (3, 2, 196, 1.5),  # 5-key tail (an ordinary step); 3 + 4 keys
                                            (2, 2, 127, 1.5), (2, 2, 129, 1.5), (1, 2, 1026, 1.5),
                                            (3, 2, 257, 1.5),     # 3 query tiles, the third holding one row
                                            (2, 2, 385, 1.5),     # a second query group with a single one-row tile
@@ -297,7 +299,7 @@ def test_attention_bf16_variants_vs_torch(variant, B, heads, L, std):
     assert float(per) < 1e-2, float(per)
 
 
-@pytest.mark.parametrize("variant", [8, 9, 5])
+@pytest.mark.parametrize("variant", [8, 10, 9, 5])
 @pytest.mark.parametrize("late", [1, 5, 16])
 def test_attention_rereferences_rows_when_later_tiles_dominate(variant, late):
     """Online softmax with a lazily updated reference point: keys from tile `late` on are scaled so that their logits

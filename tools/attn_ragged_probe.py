@@ -28,5 +28,6 @@ def t(fn, it=10):
     return best * 1e3
 import itertools
 pairs = [(int(a), int(b)) for a, b in (p.split('x') for p in sys.argv[1].split(','))] if len(sys.argv) > 1 else [(1024, 1024), (1026, 1024), (1024, 1026), (1026, 1026)]
+variants = [int(v) for v in os.environ.get("VARIANTS", "0").split(",")]
 for lq, lkv in pairs:
-    print(f"len_q {lq} len_kv {lkv}: {t(lambda: run(lq, lkv)):7.1f} us", flush=True)
+    print(f"len_q {lq} len_kv {lkv}: " + "  ".join(f"v{v} {t(lambda: run(lq, lkv, v)):7.1f} us" for v in variants), flush=True)
