@@ -23,8 +23,10 @@
 //     derived incrementally instead of with four integer divisions;
 //   * rotary point encoding (rotaryencoderpcd.py:6-27) inside the kernel: a dedicated warp rotates head dims 0..5 of
 //     every Q / K tile in shared memory between the TMA arrival and the first MMA that reads it.
-// Measured at the bench shape (128 sequences x 8 heads, L = 1026): 400 us against 485 us for the paired kernel
-// (361 / 419 us at L = 1024), XU pipe 67 % busy (57 %).  TOKEN = 1 keeps a negative result runnable: a per-scheduler
+//   * 1..4 keys beyond the last full KV tile (every registered sequence length) do not take a step of their own: see
+//     the TAIL template parameter of the kernel.
+// Measured at the bench shape (128 sequences x 8 heads, L = 1026): 366 us (400 with the two tail keys as a 17th step)
+// against 485 us for the paired kernel (361 / 419 us at L = 1024), XU pipe 72 % busy (57 %).  TOKEN = 1 keeps a negative result runnable: a per-scheduler
 // MUFU token (an mbarrier passed round-robin so that exactly one warp exponentiates at a time, handed on 16
 // exponentials early) costs more in hand-offs than the convoys it prevents (+12 %); so did issuing the 64
 // exponentials of a tile as one uninterrupted MUFU run, dropping the per-tile row maximum in favour of a
