@@ -192,8 +192,8 @@ __device__ unsigned long long g_trace[NT * TRACE_STEPS * TRACE_PTS];
 #endif
 
 // TOKEN = 0 (default): warps exponentiate whenever they are ready; 1: MUFU hand-off ring (A/B of the ring itself)
-// TAIL = 1: len_kv = 64 n + t with 1 <= t <= MAX_TAIL (every registered config: L = 1025 / 1026 / 1281 / 4097 / 4353 have
-// t = 1 or 2).  The t keys do not get a KV step of their own (a step whose exponentials are already skipped still costs
+// TAIL = 1: len_kv = 64 n + t with 0 <= t <= MAX_TAIL (every registered config: L = 1025 / 1026 / 1281 / 4097 / 4353 have
+// t = 1 or 2; with t = 0 the tail products are all zeros and what is gained is a step loop without masking code).  The t keys do not get a KV step of their own (a step whose exponentials are already skipped still costs
 // its barrier round trips: 18.5 us of 399 at L = 1026).  Instead
 //   * S_tail[s] = Q[s] K_tail^T (N = 16) is issued once per item, right after the first QK^T, into the slot's O columns --
 //     free until the first PV of the item -- and read (4 columns) by the softmax warps during step 0;
@@ -341,10 +341,12 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               ++qcnt[s];
             }
           }
-          for (int j = 0; j < num_kv; ++j) {
+          for (int j = 0; j < num_kv + (TAIL ? 1 : 0); ++j) {
+            // ring order K_0, [K_tail], K_1, ...: tile index of the j-th arrival
+            const int tile = !TAIL ? j : (j == 0 ? 0 : (j == 1 ? num_kv : j - 1));
             bar_wait(bar(B_K_FULL + kst), kph);
             for (int r = lane; r < BKV; r += 32)
-              if (j * BKV + r < len_kv) rope_row(sK + kst * KV_TILE, r, rope + ((int64_t)it.b * len_kv + j * BKV + r) * 3);
+              if (tile * BKV + r < len_kv) rope_row(sK + kst * KV_TILE, r, rope + ((int64_t)it.b * len_kv + tile * BKV + r) * 3);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) bar_arrive(bar(B_K_ROT + kst));
@@ -773,9 +775,10 @@ int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
                     int mode, cudaStream_t st) {
   const bool no_tail = mode == 2;
   if (mode == 1) return launch_tc8<1, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
-  // a short tail (1..MAX_TAIL keys beyond the last full KV tile: every registered sequence length) rides on the last step
+  // a short tail (0..MAX_TAIL keys beyond the last full KV tile: every registered sequence length) rides on the last
+  // step; tail == 0 takes the same kernel because its step loop has no masking code at all (344 vs 360 us at L = 1024)
   const int tail = len_kv % a8::BKV;
-  if (rope == nullptr && len_kv >= a8::BKV && tail >= 1 && tail <= a8::MAX_TAIL && !no_tail)
+  if (len_kv >= a8::BKV && tail <= a8::MAX_TAIL && !no_tail)
     return launch_tc8<0, 1>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
   return launch_tc8<0, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
 }

@@ -368,7 +368,7 @@ def test_rotary_attention_bf16():
     assert got.dtype == torch.float32
     assert rel(got, g["rotary_self_attn"]) < 2e-2, describe(got, g["rotary_self_attn"])
     # kernel level: several query groups, ragged tails, bf16 rotary attention vs the fp32 rotary kernel
-    for B, N, H in ((3, 333, 4), (2, 1026, 2), (1, 64, 1)):
+    for B, N, H in ((3, 333, 4), (2, 1026, 2), (1, 64, 1), (2, 131, 2), (2, 256, 2), (40, 1025, 4)):
         qkv = bf16_round(det.normal((B, N, 3 * H * 64), 330 + N, std=1.2)).to(DEV)
         pos = det.uniform((B, N, 3), 331 + N, std=0.4).to(DEV)
         want = ops.rotary_attention(qkv, pos, H)
