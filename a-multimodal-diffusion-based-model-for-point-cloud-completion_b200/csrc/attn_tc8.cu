@@ -33,6 +33,8 @@
 // sum-triggered re-referencing, and evaluating 1/8-1/2 of the exponentials with an FMA-pipe polynomial.
 // Warp roles (512 threads): 0 = TMA producer (Q, K, V), 1 = QK^T issuer, 2 = rotary warp, 3 = PV issuer,
 // 4..15 = softmax: slot = (warp - 4) / 4, TMEM lane quarter = warp % 4, thread = query row.
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_sm100.cuh"
 
@@ -537,7 +539,10 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
       float m_used = 0.f, l_run = 0.f;
       float ts[MAX_TAIL];   // TAIL: raw scores of the tail keys (-inf beyond the real ones)
-      for (int j = 0; j < num_kv; ++j) {
+      // one KV step; FIRST / LAST are compile-time so that the steady-state instance carries neither the item set-up
+      // nor the masking / tail code of the last step (a step loop without per-chunk predicates measured 4.5 % faster)
+      auto kv_step = [&](const int j, auto first_c, auto last_c) {
+        constexpr bool FIRST = decltype(first_c)::value, LAST = decltype(last_c)::value;
         uint32_t r[BKV];
 #ifdef PCD_ATTN_TRACE
         const int trace_step = k * num_kv + j;
@@ -553,7 +558,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(b_sfree);  // S sits in registers: the next QK^T of the slot may overwrite it
-        if (TAIL && j == 0) {
+        if (TAIL && FIRST) {
           // the tail scores wait in the O columns: fetch them before the first PV of the item overwrites O
           bar_wait(b_tfull, nis & 1);
           ++nis;
@@ -567,8 +572,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int i = 0; i < MAX_TAIL; ++i) ts[i] = i < tail ? __uint_as_float(tr[i]) : -INFINITY;
         }
-        const bool with_tail = TAIL && j == num_kv - 1;
-        const int nvalid = (j == num_kv - 1) ? last_valid : BKV;
+        constexpr bool with_tail = TAIL && LAST;
+        const int nvalid = LAST ? last_valid : BKV;   // (compile-time BKV in every step but the last)
         if (nvalid < BKV) {
 #pragma unroll
           for (int i = 0; i < BKV; ++i)
@@ -596,7 +601,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         PCD_TRACE(3);  // row maximum done
         bar_wait(b_pvdone, (u & 1) ^ 1);
         PCD_TRACE(4);  // PV_{j-1} complete
-        if (j == 0) {
+        if (FIRST) {
           m_used = mx;
         } else {
           // lazy rescale of O and l when the maximum grows by more than 2^8 (rare)
@@ -672,6 +677,15 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (lane == 0) bar_arrive(b_pready);  // P in TMEM -> PV may be issued
         PCD_TRACE(7);  // P handed over
         ++u;
+      };
+      using T_ = std::integral_constant<bool, true>;
+      using F_ = std::integral_constant<bool, false>;
+      if (num_kv == 1) {
+        kv_step(0, T_{}, T_{});
+      } else {
+        kv_step(0, T_{}, F_{});
+        for (int j = 1; j < num_kv - 1; ++j) kv_step(j, F_{}, F_{});
+        kv_step(num_kv - 1, F_{}, T_{});
       }
       // ---- epilogue: O / l -> global ----
 #ifdef PCD_ATTN_TRACE
