@@ -55,7 +55,7 @@ constexpr int SMEM_BYTES = TILE_BYTES + 1024 + BAR_BYTES;
 constexpr int TMEM_COLS = 512;
 // TMEM columns per slot: S 64 (fp32), P 32 (bf16 pairs), O 64.  TAIL kernels (see below) give P eight more columns for
 // the 16-key tail group: S 0..191, O 192..383, P 384..503.
-constexpr int MAX_TAIL = 4;
+constexpr int MAX_TAIL = 16;   // TAIL template values: 0 (none), 4 or 16 = tail score columns a softmax thread keeps
 __host__ __device__ constexpr int s_col(int s) { return s * 64; }
 template <int TAIL> __host__ __device__ constexpr int p_col(int s) { return TAIL ? 384 + s * 40 : 192 + s * 32; }
 template <int TAIL> __host__ __device__ constexpr int o_col(int s) { return TAIL ? 192 + s * 64 : 288 + s * 64; }
@@ -115,6 +115,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
@@ -194,7 +202,7 @@ __device__ unsigned long long g_trace[NT * TRACE_STEPS * TRACE_PTS];
 #endif
 
 // TOKEN = 0 (default): warps exponentiate whenever they are ready; 1: MUFU hand-off ring (A/B of the ring itself)
-// TAIL = 1: len_kv = 64 n + t with 0 <= t <= MAX_TAIL (every registered config: L = 1025 / 1026 / 1281 / 4097 / 4353 have
+// TAIL = 4 / 16: len_kv = 64 n + t with 0 <= t <= TAIL (every registered config: L = 1025 / 1026 / 1281 / 4097 / 4353 have
 // t = 1 or 2; with t = 0 the tail products are all zeros and what is gained is a step loop without masking code).  The t keys do not get a KV step of their own (a step whose exponentials are already skipped still costs
 // its barrier round trips: 18.5 us of 399 at L = 1026).  Instead
 //   * S_tail[s] = Q[s] K_tail^T (N = 16) is issued once per item, right after the first QK^T, into the slot's O columns --
@@ -538,7 +546,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t tok_next = b_tok + 8 * ((slot + 1 < ring) ? slot + 1 : 0);
 
       float m_used = 0.f, l_run = 0.f;
-      float ts[MAX_TAIL];   // TAIL: raw scores of the tail keys (-inf beyond the real ones)
+      float ts[TAIL ? TAIL : 1];   // TAIL: raw scores of the tail keys (-inf beyond the real ones)
       // one KV step; FIRST / LAST are compile-time so that the steady-state instance carries neither the item set-up
       // nor the masking / tail code of the last step (a step loop without per-chunk predicates measured 4.5 % faster)
       auto kv_step = [&](const int j, auto first_c, auto last_c) {
@@ -563,14 +571,15 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           bar_wait(b_tfull, nis & 1);
           ++nis;
           tcgen05_fence_after();
-          uint32_t tr[MAX_TAIL];
-          tmem_ld_32x32b_x4(tm + o_col<TAIL>(slot), tr);
+          uint32_t tr[TAIL ? TAIL : 1];
+          if (TAIL == 4) tmem_ld_32x32b_x4(tm + o_col<TAIL>(slot), tr);
+          if (TAIL == 16) tmem_ld_32x32b_x16(tm + o_col<TAIL>(slot), tr);
           tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) bar_arrive(b_tfree);
 #pragma unroll
-          for (int i = 0; i < MAX_TAIL; ++i) ts[i] = i < tail ? __uint_as_float(tr[i]) : -INFINITY;
+          for (int i = 0; i < TAIL; ++i) ts[i] = i < tail ? __uint_as_float(tr[i]) : -INFINITY;
         }
         constexpr bool with_tail = TAIL && LAST;
         const int nvalid = LAST ? last_valid : BKV;   // (compile-time BKV in every step but the last)
@@ -590,10 +599,13 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
           }
           if (with_tail) {
-            mx0 = fmaxf(mx0, ts[0]);
-            mx1 = fmaxf(mx1, ts[1]);
-            mx2 = fmaxf(mx2, ts[2]);
-            mx3 = fmaxf(mx3, ts[3]);
+#pragma unroll
+            for (int i = 0; i < TAIL; i += 4) {
+              mx0 = fmaxf(mx0, ts[i]);
+              mx1 = fmaxf(mx1, ts[i + 1]);
+              mx2 = fmaxf(mx2, ts[i + 2]);
+              mx3 = fmaxf(mx3, ts[i + 3]);
+            }
           }
           mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
         }
@@ -664,10 +676,15 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         if (with_tail) {
           // the tail keys: same reference maximum, P into the eight extra columns (keys beyond the tail: exp2(-inf) = 0)
-          const float p0 = ex2v(fmaf(ts[0], scale_log2, -m_used)), p1 = ex2v(fmaf(ts[1], scale_log2, -m_used));
-          const float p2 = ex2v(fmaf(ts[2], scale_log2, -m_used)), p3 = ex2v(fmaf(ts[3], scale_log2, -m_used));
-          l_run += (p0 + p1) + (p2 + p3);
-          uint32_t pk[8] = {pack_bf16x2(p0, p1), pack_bf16x2(p2, p3), 0u, 0u, 0u, 0u, 0u, 0u};
+          uint32_t pk[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int i = 0; i < TAIL; i += 4) {
+            const float p0 = ex2v(fmaf(ts[i], scale_log2, -m_used)), p1 = ex2v(fmaf(ts[i + 1], scale_log2, -m_used));
+            const float p2 = ex2v(fmaf(ts[i + 2], scale_log2, -m_used)), p3 = ex2v(fmaf(ts[i + 3], scale_log2, -m_used));
+            l_run += (p0 + p1) + (p2 + p3);
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
           tmem_st_32x32b_x8(tm + p_col<TAIL>(slot) + 32, pk);
         }
         PCD_TRACE(6);  // exponentials issued
@@ -789,11 +806,14 @@ int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
                     int mode, cudaStream_t st) {
   const bool no_tail = mode == 2;
   if (mode == 1) return launch_tc8<1, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
-  // a short tail (0..MAX_TAIL keys beyond the last full KV tile: every registered sequence length) rides on the last
+  // a short tail (0..16 keys beyond the last full KV tile: every registered sequence length has 1 or 2, the 77 text
+  // tokens of the perceiver 13) rides on the last
   // step; tail == 0 takes the same kernel because its step loop has no masking code at all (344 vs 360 us at L = 1024)
   const int tail = len_kv % a8::BKV;
+  if (len_kv >= a8::BKV && tail <= 4 && !no_tail)
+    return launch_tc8<0, 4>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
   if (len_kv >= a8::BKV && tail <= a8::MAX_TAIL && !no_tail)
-    return launch_tc8<0, 1>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+    return launch_tc8<0, 16>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
   return launch_tc8<0, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
 }
 

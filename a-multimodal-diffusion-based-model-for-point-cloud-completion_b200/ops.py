@@ -283,7 +283,7 @@ def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int, variant: int 
 
 
 def attention_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, q_scale: float,
-                    k_scale: float) -> torch.Tensor:
+                    k_scale: float, variant: int = 0) -> torch.Tensor:
     """softmax((q_scale q) (k_scale k)^T) v per 64-wide head over strided views: q [B, Lq, H*64], k / v [B, Lkv, H*64]
     (any batch / row strides, unit last stride; e.g. column blocks of one fused projection output)."""
     B, Lq, W = q.shape
@@ -293,7 +293,7 @@ def attention_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
         assert t.stride(2) == 1
     out = torch.empty(B, Lq, W, device=q.device, dtype=q.dtype)
     opnd = lambda t: _operand(t, 0, t.stride(0), t.stride(1), 64)
-    return attention_packed(opnd(q), opnd(k), opnd(v), out, B, heads, Lq, Lkv, q_scale, k_scale)
+    return attention_packed(opnd(q), opnd(k), opnd(v), out, B, heads, Lq, Lkv, q_scale, k_scale, None, variant)
 
 
 def rotary_attention(qkv: torch.Tensor, coords: torch.Tensor, heads: int) -> torch.Tensor:

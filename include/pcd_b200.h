@@ -180,7 +180,7 @@ typedef struct {
 /* Tensor-core attention kernels selectable per call (bf16 only; the fp32 kernel ignores `variant`):
  *  GROUPED        one CTA per SM over three query tiles of one (sequence, head) that share every K / V tile: three
  *                 softmax warps per scheduler keep the special-function pipe fed (attn_tc8.cu) -- the default;
- *                 0..4 keys beyond the last full 64-key tile (every registered sequence length) ride on the last full
+ *                 0..16 keys beyond the last full 64-key tile (every registered sequence length) ride on the last full
  *                 step instead of taking a step of their own;
  *  GROUPED_STEPTAIL the same kernel with such a tail as an ordinary (masked) KV step: A/B of the tail path;
  *  GROUPED_TOKEN  the same kernel with a per-scheduler MUFU token (one of the three warps exponentiates at a time);

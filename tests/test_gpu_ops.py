@@ -268,7 +268,8 @@ def test_self_attention_lengths(dtype, tol, L):
 @pytest.mark.parametrize("variant", [8, 10, 9, 7, 6, 5])
 @pytest.mark.parametrize("B,heads,L,std", [(2, 2, 1, 1.5), (2, 2, 63, 1.5), (3, 2, 64, 1.5), (2, 3, 65, 1.5),
                                            (2, 3, 66, 1.5), (2, 3, 68, 2.5),  # 1 full KV tile + a 2- / 4-key tail
-                                           (2, 3, 69, 1.5), (3, 2, 196, 1.5),  # 5-key tail (an ordinary step); 3 + 4 keys
+                                           (2, 3, 69, 1.5), (3, 2, 196, 1.5),  # 5-key tail (16-column form); 3 x 64 + 4 keys
+                                           (2, 3, 80, 1.5), (2, 3, 81, 1.5), (3, 2, 141, 2.5),  # 16 keys; 17 (a step); 13
                                            (2, 2, 127, 1.5), (2, 2, 129, 1.5), (1, 2, 1026, 1.5),
                                            (3, 2, 257, 1.5),     # 3 query tiles, the third holding one row
                                            (2, 2, 385, 1.5),     # a second query group with a single one-row tile
@@ -385,7 +386,10 @@ def test_rotary_attention_bf16():
         rot = keep.clone()
         ops.rope_bf16_(rot[..., :D], pos, H)
         ops.rope_bf16_(rot[..., D:2 * D], pos, H)
-        plain = ops.attention_views(rot[..., :D], rot[..., D:2 * D], rot[..., 2 * D:], H, D ** -0.5, 1.0)
+        # (same kernel on both sides: rotary attention always takes the grouped one, a small plain problem would go to the
+        # paired kernel, whose tail keys are summed in a different order)
+        plain = ops.attention_views(rot[..., :D], rot[..., D:2 * D], rot[..., 2 * D:], H, D ** -0.5, 1.0,
+                                    variant=P._lib.ATTN_GROUPED)
         torch.cuda.synchronize()
         assert torch.equal(plain, got2), describe(got2.float(), plain.float(), "fused vs stand-alone rotation")
 
