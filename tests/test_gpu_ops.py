@@ -300,6 +300,29 @@ def test_attention_bf16_variants_vs_torch(variant, B, heads, L, std):
     assert float(per) < 1e-2, float(per)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_attention_bf16_random_lengths(seed):
+    """The dispatcher over random (len_q, len_kv, sequences, heads): every tail length 0..63 class (tail-key forms for
+    0..4 and 5..16 keys, masked last step beyond), 1..n KV steps, ragged query tiles, cross-attention shapes; the default
+    kernel choice and the forced grouped kernel against an fp32 torch evaluation of the same bf16 inputs."""
+    rng = torch.Generator(device="cpu").manual_seed(4242 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))
+    for case in range(14):
+        B, H = ri(1, 5), ri(1, 4)
+        lq = ri(1, 700)
+        lkv = (ri(1, 9) * 64 + (ri(0, 20) if case % 2 == 0 else ri(0, 63))) if case % 5 else ri(1, 63)
+        q = (torch.randn(B, lq, H * 64, generator=rng) * 1.3).to(DEV).bfloat16()
+        k = (torch.randn(B, lkv, H * 64, generator=rng) * 1.3).to(DEV).bfloat16()
+        v = torch.randn(B, lkv, H * 64, generator=rng).to(DEV).bfloat16()
+        w = torch.einsum("bthc,bshc->bhts", q.float().view(B, lq, H, 64), k.float().view(B, lkv, H, 64)) / 8.0
+        want = torch.einsum("bhts,bshc->bthc", torch.softmax(w, -1), v.float().view(B, lkv, H, 64)).reshape(B, lq, H * 64)
+        for variant in (0, 8):
+            got = ops.attention_views(q, k, v, H, 64 ** -0.25, 64 ** -0.25, variant=variant)
+            torch.cuda.synchronize()
+            assert torch.isfinite(got.float()).all(), (B, H, lq, lkv, variant)
+            assert rel(got.float(), want) < 1e-2, describe(got.float(), want, f"B{B} H{H} Lq{lq} Lkv{lkv} v{variant}")
+
+
 @pytest.mark.parametrize("variant", [8, 10, 9, 5])
 @pytest.mark.parametrize("late", [1, 5, 16])
 def test_attention_rereferences_rows_when_later_tiles_dominate(variant, late):
