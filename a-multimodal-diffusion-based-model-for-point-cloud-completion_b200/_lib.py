@@ -18,7 +18,7 @@ PCD_F32, PCD_BF16 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 EPI_RESIDUAL_STATS, EPI_LN_BIAS, EPI_LN_BIAS_GELU = 3, 4, 5
 # pcd_attn_variant (tensor-core attention kernels, per call) and pcd_model_desc.flags
-ATTN_DEFAULT, ATTN_GROUPED, ATTN_GROUPED_TOKEN, ATTN_GROUPED_STEPTAIL = 0, 8, 9, 10
+ATTN_DEFAULT, ATTN_GROUPED, ATTN_GROUPED_TOKEN, ATTN_GROUPED_STEPTAIL, ATTN_GROUPED_WIDE = 0, 8, 9, 10, 11
 ATTN_PAIRED, ATTN_PAIRED_POLY4, ATTN_PAIRED_POLY2 = 5, 6, 7
 MODEL_SEPARATE_LAYERNORM, MODEL_ATTN_VARIANT_SHIFT = 1, 8
 

@@ -44,29 +44,47 @@ using namespace tc;
 
 namespace a8 {
 
-constexpr int BQ = 128, BKV = 64, HD = 64, NT = 3;
-constexpr int Q_TILE = BQ * HD * 2;    // 16 KB
-constexpr int KV_TILE = BKV * HD * 2;  // 8 KB
-constexpr int KSK = 4, KSV = 4;
+constexpr int BQ = 128, HD = 64;
+constexpr int Q_TILE = BQ * HD * 2;   // 16 KB
 constexpr int O_STAGE = 32 * HD * 2;  // per softmax warp: 32 rows x 128 B of normalised output for one TMA store
-constexpr int TILE_BYTES = 2 * NT * Q_TILE + (KSK + KSV) * KV_TILE + 4 * NT * O_STAGE;  // 208 KB
 constexpr int BAR_BYTES = 1024;
-constexpr int SMEM_BYTES = TILE_BYTES + 1024 + BAR_BYTES;
 constexpr int TMEM_COLS = 512;
-// TMEM columns per slot: S 64 (fp32), P 32 (bf16 pairs), O 64.  TAIL kernels (see below) give P eight more columns for
-// the 16-key tail group: S 0..191, O 192..383, P 384..503.
 constexpr int MAX_TAIL = 16;   // TAIL template values: 0 (none), 4 or 16 = tail score columns a softmax thread keeps
-__host__ __device__ constexpr int s_col(int s) { return s * 64; }
-template <int TAIL> __host__ __device__ constexpr int p_col(int s) { return TAIL ? 384 + s * 40 : 192 + s * 32; }
-template <int TAIL> __host__ __device__ constexpr int o_col(int s) { return TAIL ? 192 + s * 64 : 288 + s * 64; }
+constexpr int MAX_NT = 3;   // (trace buffers)
 
-// barrier slots (8 bytes each)
-constexpr int B_Q_FULL = 0, B_Q_EMPTY = B_Q_FULL + 2 * NT, B_Q_ROT = B_Q_EMPTY + 2 * NT, B_K_FULL = B_Q_ROT + 2 * NT,
-              B_K_EMPTY = B_K_FULL + KSK, B_K_ROT = B_K_EMPTY + KSK, B_V_FULL = B_K_ROT + KSK,
-              B_V_EMPTY = B_V_FULL + KSV, B_S_FULL = B_V_EMPTY + KSV, B_S_FREE = B_S_FULL + NT,
-              B_P_READY = B_S_FREE + NT, B_PV_DONE = B_P_READY + NT, B_O_FREE = B_PV_DONE + NT,
-              B_TOK = B_O_FREE + NT, B_T_FULL = B_TOK + 4 * NT, B_T_FREE = B_T_FULL + NT, B_COUNT = B_T_FREE + NT;
-static_assert(B_COUNT * 8 + 16 <= BAR_BYTES, "barrier block too small");
+// Two geometries of the same kernel:
+//   WIDE = 0: three query tiles ("slots") per CTA, 64-key steps  -- 12 softmax warps, three per scheduler;
+//   WIDE = 1: two slots, 128-key steps -- 8 softmax warps, two per scheduler, but each step carries twice the
+//             exponentials for the same barrier round trips (S 128 + P 64 + O 64 columns per slot = all of TMEM, so
+//             no tail-key form: a ragged last step is masked).
+template <int WIDE>
+struct Geo {
+  static constexpr int NT = WIDE ? 2 : 3, BKV = WIDE ? 128 : 64;
+  static constexpr int KV_TILE = BKV * HD * 2;   // 8 / 16 KB
+  static constexpr int KSK = WIDE ? 3 : 4, KSV = KSK;
+  static constexpr int TILE_BYTES = 2 * NT * Q_TILE + (KSK + KSV) * KV_TILE + 4 * NT * O_STAGE;  // 208 / 192 KB
+  static constexpr int SMEM_BYTES = TILE_BYTES + 1024 + BAR_BYTES;
+  static constexpr int THREADS = 128 + 128 * NT;
+  static constexpr int SOFTMAX_REGS = WIDE ? 208 : 152;
+  // TMEM columns per slot: S BKV (fp32), P BKV / 2 (bf16 pairs), O 64.  TAIL kernels (WIDE = 0) give P eight more
+  // columns for the 16-key tail group: S 0..191, O 192..383, P 384..503.
+  __host__ __device__ static constexpr int s_col(int s) { return s * BKV; }
+  template <int TAIL> __host__ __device__ static constexpr int p_col(int s) {
+    return WIDE ? 256 + s * 64 : (TAIL ? 384 + s * 40 : 192 + s * 32);
+  }
+  template <int TAIL> __host__ __device__ static constexpr int o_col(int s) {
+    return WIDE ? 384 + s * 64 : (TAIL ? 192 + s * 64 : 288 + s * 64);
+  }
+  // barrier slots (8 bytes each)
+  static constexpr int B_Q_FULL = 0, B_Q_EMPTY = B_Q_FULL + 2 * NT, B_Q_ROT = B_Q_EMPTY + 2 * NT,
+                       B_K_FULL = B_Q_ROT + 2 * NT, B_K_EMPTY = B_K_FULL + KSK, B_K_ROT = B_K_EMPTY + KSK,
+                       B_V_FULL = B_K_ROT + KSK, B_V_EMPTY = B_V_FULL + KSV, B_S_FULL = B_V_EMPTY + KSV,
+                       B_S_FREE = B_S_FULL + NT, B_P_READY = B_S_FREE + NT, B_PV_DONE = B_P_READY + NT,
+                       B_O_FREE = B_PV_DONE + NT, B_TOK = B_O_FREE + NT, B_T_FULL = B_TOK + 4 * NT,
+                       B_T_FREE = B_T_FULL + NT, B_COUNT = B_T_FREE + NT;
+  static_assert(B_COUNT * 8 + 16 <= BAR_BYTES, "barrier block too small");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
 
 __device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -126,7 +144,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) 
 }
 __device__ __forceinline__ void pin(uint32_t& v) { asm volatile("" : "+r"(v)); }
 
-// work item = (group of NT consecutive query tiles, head, sequence); consecutive items share (sequence, head)
+// work item = (group of NT (2 or 3) consecutive query tiles, head, sequence); consecutive items share (sequence, head)
 struct Item {
   int g, h, b, n_act;
 };
@@ -136,9 +154,9 @@ struct Item {
 struct ItemIter {
   int g, h, b;            // current item
   int dg, dh, db;         // gridDim.x decomposed in the (group, head, sequence) mixed radix
-  int ngroups, heads, nq;
-  __device__ __forceinline__ ItemIter(int first, int stride, int ngroups_, int heads_, int nq_)
-      : ngroups(ngroups_), heads(heads_), nq(nq_) {
+  int ngroups, heads, nq, nt;
+  __device__ __forceinline__ ItemIter(int first, int stride, int ngroups_, int heads_, int nq_, int nt_)
+      : ngroups(ngroups_), heads(heads_), nq(nq_), nt(nt_) {
     g = first % ngroups;
     const int bh = first / ngroups;
     h = bh % heads;
@@ -148,7 +166,7 @@ struct ItemIter {
     dh = dbh % heads;
     db = dbh / heads;
   }
-  __device__ __forceinline__ Item get() const { return Item{g, h, b, min(NT, nq - g * NT)}; }
+  __device__ __forceinline__ Item get() const { return Item{g, h, b, min(nt, nq - g * nt)}; }
   __device__ __forceinline__ void next() {
     g += dg;
     int carry = 0;
@@ -191,7 +209,7 @@ constexpr float kRescaleThreshold = 8.f;  // log2 units: P <= 2^8, safe in bf16 
 // the points of a step where a warp can be held up, [slot][step][point].
 #ifdef PCD_ATTN_TRACE
 constexpr int TRACE_STEPS = 96, TRACE_PTS = 12;
-__device__ unsigned long long g_trace[NT * TRACE_STEPS * TRACE_PTS];
+__device__ unsigned long long g_trace[MAX_NT * TRACE_STEPS * TRACE_PTS];
 #define PCD_TRACE(pt)                                                                                  \
   do {                                                                                                 \
     if (blockIdx.x == 0 && quarter == 0 && lane == 0 && trace_step < TRACE_STEPS)                     \
@@ -210,12 +228,20 @@ __device__ unsigned long long g_trace[NT * TRACE_STEPS * TRACE_PTS];
 //   * the tail scores join the row maximum, exponentials and row sum of the LAST full step, their P goes to eight extra
 //     P columns, and the PV issuer appends one K = 16 product with the V_tail tile (rows beyond len_kv are zero-filled by
 //     TMA, the matching P entries are zero).
-template <int TOKEN, int TAIL>
-__global__ void __launch_bounds__(512, 1)
+template <int TOKEN, int TAIL, int WIDE>
+__global__ void __launch_bounds__(Geo<WIDE>::THREADS, 1)
 attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                      int len_q, int len_kv, float scale_log2, int nq, int ngroups, int heads, int n_items,
                      const float* __restrict__ rope) {
+  using G = Geo<WIDE>;
+  static_assert(!(WIDE && (TAIL || TOKEN)), "the wide geometry has neither the tail-key form nor the token ring");
+  constexpr int NT = G::NT, BKV = G::BKV, KV_TILE = G::KV_TILE, KSK = G::KSK, KSV = G::KSV, TILE_BYTES = G::TILE_BYTES;
+  constexpr int B_Q_FULL = G::B_Q_FULL, B_Q_EMPTY = G::B_Q_EMPTY, B_Q_ROT = G::B_Q_ROT, B_K_FULL = G::B_K_FULL,
+                B_K_EMPTY = G::B_K_EMPTY, B_K_ROT = G::B_K_ROT, B_V_FULL = G::B_V_FULL, B_V_EMPTY = G::B_V_EMPTY,
+                B_S_FULL = G::B_S_FULL, B_S_FREE = G::B_S_FREE, B_P_READY = G::B_P_READY, B_PV_DONE = G::B_PV_DONE,
+                B_O_FREE = G::B_O_FREE, B_TOK = G::B_TOK, B_T_FULL = G::B_T_FULL, B_T_FREE = G::B_T_FREE,
+                B_COUNT = G::B_COUNT;
   extern __shared__ unsigned char smem_raw[];
   uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   pin(smem);
@@ -235,7 +261,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int last_valid = TAIL ? BKV : len_kv - (num_kv - 1) * BKV;      // keys in the last KV tile (1..64)
   const int tail = TAIL ? len_kv - num_kv * BKV : 0;                    // keys handled outside the steps (TAIL)
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  ItemIter items((int)blockIdx.x, (int)gridDim.x, ngroups, heads, nq);  // every role walks its own copy
+  ItemIter items((int)blockIdx.x, (int)gridDim.x, ngroups, heads, nq, NT);  // every role walks its own copy
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ);
@@ -286,7 +312,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (elect_one()) {
         int kst = 0, vst = 0;
         uint32_t kph = 1, vph = 1;  // "empty" barriers: the first pass over a ring does not block
-        uint32_t qcnt[NT] = {0, 0, 0};
+        uint32_t qcnt[NT] = {};
         for (int k = 0; k < my_items; ++k, items.next()) {
           const Item it = items.get();
 #pragma unroll
@@ -334,7 +360,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (rope != nullptr) {
         int kst = 0;
         uint32_t kph = 0;
-        uint32_t qcnt[NT] = {0, 0, 0};
+        uint32_t qcnt[NT] = {};
         for (int k = 0; k < my_items; ++k, items.next()) {
           const Item it = items.get();
 #pragma unroll
@@ -376,9 +402,9 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int kbar = rope != nullptr ? B_K_ROT : B_K_FULL;
         int kst = 0;
         uint32_t kph = 0;
-        uint32_t qcnt[NT] = {0, 0, 0};
-        uint32_t su[NT] = {0, 0, 0};  // S products issued per slot
-        uint32_t nq_items[NT] = {0, 0, 0};  // items the slot took part in (TAIL: parity of O_FREE)
+        uint32_t qcnt[NT] = {};
+        uint32_t su[NT] = {};  // S products issued per slot
+        uint32_t nq_items[NT] = {};  // items the slot took part in (TAIL: parity of O_FREE)
         constexpr uint32_t idesc_tail = idesc_bf16_f32(BQ, 16, 0);
         for (int k = 0; k < my_items; ++k, items.next()) {
           const Item it = items.get();
@@ -404,7 +430,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 bar_wait(bar(B_S_FREE + s), (su[s] & 1) ^ 1);  // previous S of the slot sits in registers
                 ++su[s];
                 tcgen05_fence_after();
-                const uint32_t s_tmem = tmem_base + s_col(s);
+                const uint32_t s_tmem = tmem_base + G::s_col(s);
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(s_tmem, adesc[s] + 2 * kk, bdesc + 2 * kk, idesc, kk != 0);
                 commit(bar(B_S_FULL + s));
@@ -425,7 +451,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                   if (nq_items[s] > 0) bar_wait(bar(B_O_FREE + s), (nq_items[s] - 1) & 1);
                   ++nq_items[s];
                   tcgen05_fence_after();
-                  const uint32_t t_tmem = tmem_base + o_col<TAIL>(s);
+                  const uint32_t t_tmem = tmem_base + G::template o_col<TAIL>(s);
 #pragma unroll
                   for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(t_tmem, adesc[s] + 2 * kk, tdesc + 2 * kk, idesc_tail, kk != 0);
                   commit(bar(B_T_FULL + s));
@@ -452,8 +478,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int nks_last = (last_valid + 15) >> 4;
         int vst = 0;
         uint32_t vph = 0;
-        uint32_t pu[NT] = {0, 0, 0};   // PV products issued per slot
-        uint32_t ni[NT] = {0, 0, 0};   // items the slot took part in
+        uint32_t pu[NT] = {};   // PV products issued per slot
+        uint32_t ni[NT] = {};   // items the slot took part in
         for (int k = 0; k < my_items; ++k, items.next()) {
           const Item it = items.get();
           for (int j = 0; j < num_kv; ++j) {
@@ -478,7 +504,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 ++pu[s];
                 if (TAIL && j == 0) bar_wait(bar(B_T_FREE + s), ni[s] & 1);  // S_tail has left the O columns
                 tcgen05_fence_after();
-                const uint32_t o_tmem = tmem_base + o_col<TAIL>(s), p_tmem = tmem_base + p_col<TAIL>(s);
+                const uint32_t o_tmem = tmem_base + G::template o_col<TAIL>(s), p_tmem = tmem_base + G::template p_col<TAIL>(s);
                 for (int kk = 0; kk < nks; ++kk)
                   umma_bf16_ts(o_tmem, p_tmem + kk * 8, smem_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0);
                 if (TAIL && lastj) umma_bf16_ts(o_tmem, p_tmem + 32, tdesc, idesc_pv, 1);
@@ -505,7 +531,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else {
-    setmaxnreg_inc<152>();
+    setmaxnreg_inc<G::SOFTMAX_REGS>();
     // --------------------------- softmax: thread = query row ----------------------------
     const int slot = (warp - 4) >> 2, quarter = warp & 3;
     uint32_t tm = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -559,8 +585,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         bar_wait(b_sfull, u & 1);
         PCD_TRACE(1);  // S_j has arrived
         tcgen05_fence_after();
-        tmem_ld_32x32b_x32(tm + s_col(slot), r);
-        tmem_ld_32x32b_x32(tm + s_col(slot) + 32, r + 32);
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(tm + G::s_col(slot) + c * 32, r + c * 32);
         tmem_ld_wait();
         PCD_TRACE(2);  // S_j in registers
         tcgen05_fence_before();
@@ -572,8 +598,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           ++nis;
           tcgen05_fence_after();
           uint32_t tr[TAIL ? TAIL : 1];
-          if (TAIL == 4) tmem_ld_32x32b_x4(tm + o_col<TAIL>(slot), tr);
-          if (TAIL == 16) tmem_ld_32x32b_x16(tm + o_col<TAIL>(slot), tr);
+          if (TAIL == 4) tmem_ld_32x32b_x4(tm + G::template o_col<TAIL>(slot), tr);
+          if (TAIL == 16) tmem_ld_32x32b_x16(tm + G::template o_col<TAIL>(slot), tr);
           tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
@@ -624,11 +650,11 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint32_t o[32];
-              tmem_ld_32x32b_x32(tm + o_col<TAIL>(slot) + h * 32, o);
+              tmem_ld_32x32b_x32(tm + G::template o_col<TAIL>(slot) + h * 32, o);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x32b_x32(tm + o_col<TAIL>(slot) + h * 32, o);
+              tmem_st_32x32b_x32(tm + G::template o_col<TAIL>(slot) + h * 32, o);
             }
             tmem_st_wait();
             l_run *= alpha;
@@ -660,7 +686,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               pk[i >> 1] = pack_bf16x2(p0, p1);
               pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
             }
-            tmem_st_32x32b_x8(tm + p_col<TAIL>(slot) + c * 8, pk);
+            tmem_st_32x32b_x8(tm + G::template p_col<TAIL>(slot) + c * 8, pk);
           }
           if (TOKEN && c == 2) {
             // pass the token on one group early: the next warp's wake-up overlaps the last 16 exponentials
@@ -685,7 +711,7 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             pk[i >> 1] = pack_bf16x2(p0, p1);
             pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
           }
-          tmem_st_32x32b_x8(tm + p_col<TAIL>(slot) + 32, pk);
+          tmem_st_32x32b_x8(tm + G::template p_col<TAIL>(slot) + 32, pk);
         }
         PCD_TRACE(6);  // exponentials issued
         tmem_st_wait();
@@ -713,8 +739,8 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       PCD_TRACE(9);   // last PV complete
       tcgen05_fence_after();
       uint32_t o[HD];
-      tmem_ld_32x32b_x32(tm + o_col<TAIL>(slot), o);
-      tmem_ld_32x32b_x32(tm + o_col<TAIL>(slot) + 32, o + 32);
+      tmem_ld_32x32b_x32(tm + G::template o_col<TAIL>(slot), o);
+      tmem_ld_32x32b_x32(tm + G::template o_col<TAIL>(slot) + 32, o + 32);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
@@ -770,51 +796,58 @@ attn_bf16_tc8_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 #ifdef PCD_ATTN_TRACE
 extern "C" __attribute__((visibility("default"))) int pcd_attn_trace_read(unsigned long long* dst, int n) {
-  const int total = a8::NT * a8::TRACE_STEPS * a8::TRACE_PTS;
+  const int total = a8::MAX_NT * a8::TRACE_STEPS * a8::TRACE_PTS;
   return cudaMemcpyFromSymbol(dst, a8::g_trace, sizeof(unsigned long long) * (n < total ? n : total)) == cudaSuccess ? total : -1;
 }
 #endif
 
-template <int TOKEN, int TAIL>
+template <int TOKEN, int TAIL, int WIDE>
 static int launch_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
                       cudaStream_t st) {
-  auto kern = a8::attn_bf16_tc8_kernel<TOKEN, TAIL>;
+  using G = a8::Geo<WIDE>;
+  auto kern = a8::attn_bf16_tc8_kernel<TOKEN, TAIL, WIDE>;
   // the attribute is per device: set it on every launch (cheap) rather than caching a per-process flag
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a8::SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
   if (e != cudaSuccess) {
-    set_error("attention_bf16: kernel attribute setup (%d B smem): %s", a8::SMEM_BYTES, cudaGetErrorString(e));
+    set_error("attention_bf16: kernel attribute setup (%d B smem): %s", G::SMEM_BYTES, cudaGetErrorString(e));
     return PCD_ERR_CUDA;
   }
   const int nq = ceil_div(len_q, a8::BQ);
-  const int ngroups = ceil_div(nq, a8::NT);
+  const int ngroups = ceil_div(nq, G::NT);
   const int64_t n_items64 = (int64_t)ngroups * heads * batch;
   if (n_items64 > 0x7fffffff) {
     set_error("attention_bf16: too many (query group, head, sequence) items");
     return PCD_ERR_INVALID;
   }
   const int n_items = (int)n_items64;
-  const int grid = min(n_items, num_sms());  // one CTA per SM: 210 KB shared memory, all 512 TMEM columns
-  kern<<<grid, 512, a8::SMEM_BYTES, st>>>(tq, tk, tv, to, len_q, len_kv, scale_log2, nq, ngroups, heads,
-                                          n_items, rope);
+  const int grid = min(n_items, num_sms());  // one CTA per SM: ~200 KB shared memory, all 512 TMEM columns
+  kern<<<grid, G::THREADS, G::SMEM_BYTES, st>>>(tq, tk, tv, to, len_q, len_kv, scale_log2, nq, ngroups, heads,
+                                                n_items, rope);
   PCD_CHECK_LAUNCH("attention_bf16");
   return PCD_OK;
 }
 
+// rows of a K / V tensor-map box (= keys per step) of a mode
+int attn_tc8_kv_rows(int mode) { return mode == 3 ? a8::Geo<1>::BKV : a8::Geo<0>::BKV; }
+
 // mode: 0 = free-running softmax warps, short tails ride on the last step (default); 1 = MUFU hand-off ring;
-// 2 = like 0 but a short tail stays an ordinary masked KV step (A/B measurements)
+// 2 = like 0 but a short tail stays an ordinary masked KV step (A/B measurements); 3 = wide geometry (two slots,
+// 128-key steps; tk / tv must be built with 128-row boxes, attn_tc8_kv_rows)
 int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
                     int mode, cudaStream_t st) {
+  constexpr int BKV = a8::Geo<0>::BKV;
   const bool no_tail = mode == 2;
-  if (mode == 1) return launch_tc8<1, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  if (mode == 3) return launch_tc8<0, 0, 1>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  if (mode == 1) return launch_tc8<1, 0, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
   // a short tail (0..16 keys beyond the last full KV tile: every registered sequence length has 1 or 2, the 77 text
-  // tokens of the perceiver 13) rides on the last
-  // step; tail == 0 takes the same kernel because its step loop has no masking code at all (344 vs 360 us at L = 1024)
-  const int tail = len_kv % a8::BKV;
-  if (len_kv >= a8::BKV && tail <= 4 && !no_tail)
-    return launch_tc8<0, 4>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
-  if (len_kv >= a8::BKV && tail <= a8::MAX_TAIL && !no_tail)
-    return launch_tc8<0, 16>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
-  return launch_tc8<0, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  // tokens of the perceiver 13) rides on the last step; tail == 0 takes the same kernel because its step loop has no
+  // masking code at all (344 vs 360 us at L = 1024)
+  const int tail = len_kv % BKV;
+  if (len_kv >= BKV && tail <= 4 && !no_tail)
+    return launch_tc8<0, 4, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  if (len_kv >= BKV && tail <= a8::MAX_TAIL && !no_tail)
+    return launch_tc8<0, 16, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
+  return launch_tc8<0, 0, 0>(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, st);
 }
 
 }  // namespace pcd

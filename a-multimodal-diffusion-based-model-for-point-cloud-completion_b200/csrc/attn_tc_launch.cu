@@ -9,7 +9,8 @@ int launch_attn_tc5(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensor
                     int64_t o_ls, int batch, int heads, int len_q, int len_kv, float scale_log2, int poly,
                     cudaStream_t st);  // attn_tc5.cu
 int launch_attn_tc8(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, int batch, int heads, int len_q, int len_kv, float scale_log2, const float* rope,
-                    int mode, cudaStream_t st);  // attn_tc8.cu (mode: 0 default, 1 MUFU token ring, 2 tail keys as a KV step)
+                    int mode, cudaStream_t st);  // attn_tc8.cu (mode: 0 default, 1 MUFU token ring, 2 tail keys as a KV step, 3 wide)
+int attn_tc8_kv_rows(int mode);                   // keys per K / V tensor-map box of a mode
 int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const float* coords, int batch, int heads,
                      int len, cudaStream_t st);  // attn_simt.cu
 
@@ -30,7 +31,9 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
     const int64_t nq = (len_q + 127) / 128, grouped_items = ((nq + 2) / 3) * heads * batch;
     variant = (rope != nullptr || grouped_items >= num_sms()) ? PCD_ATTN_GROUPED : PCD_ATTN_PAIRED;
   }
-  const bool grouped = variant == PCD_ATTN_GROUPED || variant == PCD_ATTN_GROUPED_TOKEN || variant == PCD_ATTN_GROUPED_STEPTAIL;
+  const bool grouped = variant == PCD_ATTN_GROUPED || variant == PCD_ATTN_GROUPED_TOKEN ||
+                       variant == PCD_ATTN_GROUPED_STEPTAIL || variant == PCD_ATTN_GROUPED_WIDE;
+  const int mode = variant == PCD_ATTN_GROUPED_TOKEN ? 1 : (variant == PCD_ATTN_GROUPED_STEPTAIL ? 2 : (variant == PCD_ATTN_GROUPED_WIDE ? 3 : 0));
   if (!grouped && variant != PCD_ATTN_PAIRED &&
       variant != PCD_ATTN_PAIRED_POLY4 && variant != PCD_ATTN_PAIRED_POLY2) {
     set_error("attention(bf16): unknown kernel variant %d", variant);
@@ -39,16 +42,16 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_operand_map(&tq, q, batch, heads, len_q, 128)) != PCD_OK) return rc;
-  if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, 64)) != PCD_OK) return rc;
-  if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, 64)) != PCD_OK) return rc;
+  const int kv_rows = grouped ? attn_tc8_kv_rows(mode) : 64;
+  if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
+  if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
   if (grouped) {
     // the output through the same kind of map: [batch, len_q, heads, 64] at the caller's strides, 32-row boxes
     CUtensorMap to;
     const pcd_attn_operand oo = {out, o_bs, o_ls, 64};
     if ((rc = make_operand_map(&to, &oo, batch, heads, len_q, 32)) != PCD_OK) return rc;
-    return launch_attn_tc8(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope,
-                           variant == PCD_ATTN_GROUPED_TOKEN ? 1 : (variant == PCD_ATTN_GROUPED_STEPTAIL ? 2 : 0), st);
+    return launch_attn_tc8(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, mode, st);
   }
   if (rope != nullptr) {
     set_error("attention(bf16): the paired kernel takes pre-rotated operands (pcd_rope_bf16); use PCD_ATTN_GROUPED");

@@ -183,6 +183,7 @@ typedef struct {
  *                 0..16 keys beyond the last full 64-key tile (every registered sequence length) ride on the last full
  *                 step instead of taking a step of their own;
  *  GROUPED_STEPTAIL the same kernel with such a tail as an ordinary (masked) KV step: A/B of the tail path;
+ *  GROUPED_WIDE   the same kernel in its second geometry: two query tiles per CTA, 128-key steps;
  *  GROUPED_TOKEN  the same kernel with a per-scheduler MUFU token (one of the three warps exponentiates at a time);
  *                 measured slower than GROUPED, kept for A/B runs;
  *  PAIRED         round-1 kernel: two CTAs per SM, one query tile each, softmax software-pipelined over KV tiles
@@ -192,6 +193,7 @@ typedef enum {
   PCD_ATTN_GROUPED = 8,
   PCD_ATTN_GROUPED_TOKEN = 9,
   PCD_ATTN_GROUPED_STEPTAIL = 10,
+  PCD_ATTN_GROUPED_WIDE = 11,
   PCD_ATTN_PAIRED = 5,
   PCD_ATTN_PAIRED_POLY4 = 6,
   PCD_ATTN_PAIRED_POLY2 = 7

@@ -175,7 +175,7 @@ def test_gemm_layernorm_folded_tails(M, N, K, gelu):
     same(plain, got)
 
 
-@pytest.mark.parametrize("variant", [0, 8, 9, 5])
+@pytest.mark.parametrize("variant", [0, 8, 11, 9, 5])
 @pytest.mark.parametrize("B,H,L", [(3, 2, 1026), (2, 8, 130), (5, 2, 70), (1, 1, 1)])
 def test_self_attention_bf16_tiles(variant, B, H, L):
     qkv = bf(det.normal((B, L, H * 192), 9041, std=1.5))

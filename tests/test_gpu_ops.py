@@ -265,7 +265,7 @@ def test_self_attention_lengths(dtype, tol, L):
     assert rel(got.float(), want) < tol, describe(got.float(), want, f"L={L} {dtype}")
 
 
-@pytest.mark.parametrize("variant", [8, 10, 9, 7, 6, 5])
+@pytest.mark.parametrize("variant", [8, 11, 10, 9, 7, 6, 5])
 @pytest.mark.parametrize("B,heads,L,std", [(2, 2, 1, 1.5), (2, 2, 63, 1.5), (3, 2, 64, 1.5), (2, 3, 65, 1.5),
                                            (2, 3, 66, 1.5), (2, 3, 68, 2.5),  # 1 full KV tile + a 2- / 4-key tail
                                            (2, 3, 69, 1.5), (3, 2, 196, 1.5),  # 5-key tail (16-column form); 3 x 64 + 4 keys
@@ -316,14 +316,14 @@ def test_attention_bf16_random_lengths(seed):
         v = torch.randn(B, lkv, H * 64, generator=rng).to(DEV).bfloat16()
         w = torch.einsum("bthc,bshc->bhts", q.float().view(B, lq, H, 64), k.float().view(B, lkv, H, 64)) / 8.0
         want = torch.einsum("bhts,bshc->bthc", torch.softmax(w, -1), v.float().view(B, lkv, H, 64)).reshape(B, lq, H * 64)
-        for variant in (0, 8):
+        for variant in (0, 8, 11):
             got = ops.attention_views(q, k, v, H, 64 ** -0.25, 64 ** -0.25, variant=variant)
             torch.cuda.synchronize()
             assert torch.isfinite(got.float()).all(), (B, H, lq, lkv, variant)
             assert rel(got.float(), want) < 1e-2, describe(got.float(), want, f"B{B} H{H} Lq{lq} Lkv{lkv} v{variant}")
 
 
-@pytest.mark.parametrize("variant", [8, 10, 9, 5])
+@pytest.mark.parametrize("variant", [8, 11, 10, 9, 5])
 @pytest.mark.parametrize("late", [1, 5, 16])
 def test_attention_rereferences_rows_when_later_tiles_dominate(variant, late):
     """Online softmax with a lazily updated reference point: keys from tile `late` on are scaled so that their logits
