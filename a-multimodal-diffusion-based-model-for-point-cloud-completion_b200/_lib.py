@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PCD_B200_LIB: A/B timing of two builds of the library in one process tree (tools/ab.sh); never a fallback
 LIB_PATH = os.environ.get("PCD_B200_LIB") or os.path.join(HERE, "libpcd_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PCD_F32, PCD_BF16 = 0, 1
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2
 EPI_RESIDUAL_STATS, EPI_LN_BIAS, EPI_LN_BIAS_GELU = 3, 4, 5
@@ -96,6 +96,9 @@ _SIGS = {
                                 C.c_float, vp, C.c_int, C.c_int, vp]),
     "pcd_attention_hd32": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
                                      C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, vp]),
+    "pcd_attention_hd32_bf16": (C.c_int, [C.POINTER(AttnOperand), C.POINTER(AttnOperand), C.POINTER(AttnOperand), vp,
+                                          C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                          C.c_int, vp]),
     "pcd_rope_bf16": (C.c_int, [C.POINTER(AttnOperand), vp, C.c_int, C.c_int, C.c_int, vp]),
     "pcd_farthest_point_sample": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     "pcd_nearest_points": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),

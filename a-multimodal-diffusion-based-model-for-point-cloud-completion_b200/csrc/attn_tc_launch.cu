@@ -14,9 +14,13 @@ int attn_tc8_kv_rows(int mode);                   // keys per K / V tensor-map b
 int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const float* coords, int batch, int heads,
                      int len, cudaStream_t st);  // attn_simt.cu
 
-// element (c, h, l, b) of an operand: 64 contiguous head dims, then heads, rows, sequences at their strides
-static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batch, int heads, int len, int box_rows) {
-  uint64_t dims[4] = {64, (uint64_t)heads, (uint64_t)len, (uint64_t)batch};
+// element (c, h, l, b) of an operand: head_dim contiguous head dims, then heads, rows, sequences at their strides.
+// The box is always 64 columns wide (the kernels' tile): with head_dim = 32 its columns 32..63 lie outside the tensor, so
+// TMA loads fill them with zeros and TMA stores drop them -- 32-wide heads run on the 64-wide kernel without any padded
+// copy in memory (q . k is unchanged by zero columns, the upper half of P V is zero and never written).
+static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batch, int heads, int len, int box_rows,
+                            int head_dim = 64) {
+  uint64_t dims[4] = {(uint64_t)head_dim, (uint64_t)heads, (uint64_t)len, (uint64_t)batch};
   uint64_t strides[3] = {(uint64_t)op->head_stride * 2, (uint64_t)op->row_stride * 2, (uint64_t)op->batch_stride * 2};
   uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   return encode_tmap_bf16(m, op->ptr, 4, dims, strides, box);
@@ -24,7 +28,12 @@ static int make_operand_map(CUtensorMap* m, const pcd_attn_operand* op, int batc
 
 int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v, uint16_t* out,
                           int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q, int len_kv, float q_scale,
-                          float k_scale, const float* rope, int variant, cudaStream_t st) {
+                          float k_scale, const float* rope, int variant, int head_dim, cudaStream_t st) {
+  if (head_dim != 64 && head_dim != 32) {
+    set_error("attention(bf16): head dim %d (64 or 32)", head_dim);
+    return PCD_ERR_INVALID;
+  }
+  if (head_dim == 32 && (variant == PCD_ATTN_DEFAULT || rope != nullptr)) variant = PCD_ATTN_GROUPED;  // TMA-store epilogue
   if (variant == PCD_ATTN_DEFAULT) {
     // three query tiles per CTA need enough (group, head, sequence) items to occupy every SM; small problems keep
     // the finer-grained paired kernel (one query tile per CTA, two CTAs per SM)
@@ -41,16 +50,20 @@ int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, 
   }
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = make_operand_map(&tq, q, batch, heads, len_q, 128)) != PCD_OK) return rc;
+  if (head_dim == 32 && !grouped) {
+    set_error("attention(bf16): 32-wide heads need a grouped kernel variant (its output leaves through TMA)");
+    return PCD_ERR_UNSUPPORTED;
+  }
+  if ((rc = make_operand_map(&tq, q, batch, heads, len_q, 128, head_dim)) != PCD_OK) return rc;
   const int kv_rows = grouped ? attn_tc8_kv_rows(mode) : 64;
-  if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
-  if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, kv_rows)) != PCD_OK) return rc;
+  if ((rc = make_operand_map(&tk, k, batch, heads, len_kv, kv_rows, head_dim)) != PCD_OK) return rc;
+  if ((rc = make_operand_map(&tv, v, batch, heads, len_kv, kv_rows, head_dim)) != PCD_OK) return rc;
   const float scale_log2 = q_scale * k_scale * 1.4426950408889634f;
   if (grouped) {
     // the output through the same kind of map: [batch, len_q, heads, 64] at the caller's strides, 32-row boxes
     CUtensorMap to;
-    const pcd_attn_operand oo = {out, o_bs, o_ls, 64};
-    if ((rc = make_operand_map(&to, &oo, batch, heads, len_q, 32)) != PCD_OK) return rc;
+    const pcd_attn_operand oo = {out, o_bs, o_ls, head_dim};
+    if ((rc = make_operand_map(&to, &oo, batch, heads, len_q, 32, head_dim)) != PCD_OK) return rc;
     return launch_attn_tc8(tq, tk, tv, to, batch, heads, len_q, len_kv, scale_log2, rope, mode, st);
   }
   if (rope != nullptr) {

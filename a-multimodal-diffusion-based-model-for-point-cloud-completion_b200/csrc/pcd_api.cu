@@ -94,13 +94,14 @@ int launch_rope_bf16(uint16_t* x, int64_t bs, int64_t ls, int64_t hs, const floa
                      int len, cudaStream_t st);
 int launch_attention_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
                           uint16_t* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
-                          int len_kv, float q_scale, float k_scale, const float* rope, int variant, cudaStream_t st);
+                          int len_kv, float q_scale, float k_scale, const float* rope, int variant, int head_dim,
+                          cudaStream_t st);
 
 }  // namespace pcd
 
 using namespace pcd;
 
-extern "C" int pcd_abi_version(void) { return 3; }
+extern "C" int pcd_abi_version(void) { return 4; }
 extern "C" unsigned long long pcd_launch_count(void) { return g_launch_count; }
 extern "C" const char* pcd_last_error(void) { return g_err; }
 
@@ -145,7 +146,7 @@ extern "C" int pcd_attention(const pcd_attn_operand* q, const pcd_attn_operand* 
     PCD_CHECK_ARG(operand_ok(q, 8, 2) && operand_ok(k, 8, 2) && operand_ok(v, 8, 2), "attention(bf16): operands must be 16-byte aligned with strides %% 8 == 0");
     PCD_CHECK_ARG(o_ls % 8 == 0 && o_bs % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "attention(bf16): output must be 16-byte aligned with strides %% 8 == 0");
     return launch_attention_bf16(q, k, v, (uint16_t*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale,
-                                 rope_coords, variant, st);
+                                 rope_coords, variant, 64, st);
   }
   PCD_CHECK_ARG(false, "attention: unknown precision %d", precision);
 }
@@ -160,6 +161,19 @@ extern "C" int pcd_attention_hd32(const pcd_attn_operand* q, const pcd_attn_oper
   PCD_CHECK_ARG(operand_ok(q, 4, 4) && operand_ok(k, 4, 4) && operand_ok(v, 4, 4), "attention_hd32: operands must be 16-byte aligned with strides %% 4 == 0");
   return launch_attention_f32(q, k, v, out, out_batch_stride, out_row_stride, batch, heads, len_q, len_kv, q_scale, k_scale,
                               nullptr, 32, (cudaStream_t)stream);
+}
+
+extern "C" int pcd_attention_hd32_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
+                                       void* out, int64_t o_bs, int64_t o_ls, int batch, int heads, int len_q,
+                                       int len_kv, float q_scale, float k_scale, int variant, void* stream) {
+  PCD_CHECK_ARG(out != nullptr, "attention_hd32_bf16: null argument");
+  PCD_CHECK_ARG(batch > 0 && heads > 0 && len_q > 0 && len_kv > 0, "attention_hd32_bf16: empty problem");
+  PCD_CHECK_ARG(batch <= 65535 && heads <= 65535, "attention_hd32_bf16: batch/heads exceed grid limits");
+  PCD_CHECK_ARG(q_scale > 0.f && k_scale > 0.f, "attention_hd32_bf16: scales must be positive");
+  PCD_CHECK_ARG(operand_ok(q, 8, 2) && operand_ok(k, 8, 2) && operand_ok(v, 8, 2), "attention_hd32_bf16: operands must be 16-byte aligned with strides %% 8 == 0");
+  PCD_CHECK_ARG(o_ls % 8 == 0 && o_bs % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "attention_hd32_bf16: output must be 16-byte aligned with strides %% 8 == 0");
+  return launch_attention_bf16(q, k, v, (uint16_t*)out, o_bs, o_ls, batch, heads, len_q, len_kv, q_scale, k_scale, nullptr,
+                               variant, 32, (cudaStream_t)stream);
 }
 
 extern "C" int pcd_rope_bf16(const pcd_attn_operand* x, const float* coords, int batch, int heads, int len,

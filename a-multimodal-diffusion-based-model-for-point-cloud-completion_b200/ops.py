@@ -283,17 +283,26 @@ def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int, variant: int 
 
 
 def attention_views(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, q_scale: float,
-                    k_scale: float, variant: int = 0) -> torch.Tensor:
-    """softmax((q_scale q) (k_scale k)^T) v per 64-wide head over strided views: q [B, Lq, H*64], k / v [B, Lkv, H*64]
-    (any batch / row strides, unit last stride; e.g. column blocks of one fused projection output)."""
+                    k_scale: float, variant: int = 0, head_dim: int = 64) -> torch.Tensor:
+    """softmax((q_scale q) (k_scale k)^T) v per head over strided views: q [B, Lq, H*head_dim], k / v [B, Lkv, H*head_dim]
+    (any batch / row strides, unit last stride; e.g. column blocks of one fused projection output).  head_dim 64, or 32
+    in bf16 (TwoStream's heads: the 64-wide tensor-core kernel over tensor maps that zero-fill the missing columns)."""
     B, Lq, W = q.shape
     Lkv = k.shape[1]
-    assert W == heads * 64 and k.shape == v.shape == (B, Lkv, W) and q.dtype == k.dtype == v.dtype
+    assert W == heads * head_dim and k.shape == v.shape == (B, Lkv, W) and q.dtype == k.dtype == v.dtype
     for t in (q, k, v):
         assert t.stride(2) == 1
     out = torch.empty(B, Lq, W, device=q.device, dtype=q.dtype)
-    opnd = lambda t: _operand(t, 0, t.stride(0), t.stride(1), 64)
-    return attention_packed(opnd(q), opnd(k), opnd(v), out, B, heads, Lq, Lkv, q_scale, k_scale, None, variant)
+    opnd = lambda t: _operand(t, 0, t.stride(0), t.stride(1), head_dim)
+    if head_dim == 64:
+        return attention_packed(opnd(q), opnd(k), opnd(v), out, B, heads, Lq, Lkv, q_scale, k_scale, None, variant)
+    assert head_dim == 32 and q.dtype == torch.bfloat16, "32-wide heads: bf16 here, fp32 through attention_hd32"
+    require_cuda(q, k, v)
+    qo, ko, vo = opnd(q), opnd(k), opnd(v)
+    check(_lib.load().pcd_attention_hd32_bf16(C.byref(qo), C.byref(ko), C.byref(vo), ptr(out), out.stride(0), out.stride(1),
+                                              B, heads, Lq, Lkv, float(q_scale), float(k_scale), int(variant), stream_ptr()),
+          "attention_hd32_bf16")
+    return out
 
 
 def rotary_attention(qkv: torch.Tensor, coords: torch.Tensor, heads: int) -> torch.Tensor:

@@ -276,69 +276,51 @@ class TwoStreamDenoiser(nn.Module):
                           out_dtype=torch.float32 if (out_fp32 or residual is not None) else torch.bfloat16)
 
     # ---- bf16 mode: 32-wide heads on the 64-wide tensor-core attention kernel -------------------------------
-    # Each head's 32 output rows of Wq / Wk / Wv are followed by 32 zero rows (zero bias), so the projection GEMM
-    # writes q, k, v directly in a [.., H, 64] layout whose upper halves are exact zeros: q.k is unchanged, the upper
-    # half of every output head is zero, and the output projection gets matching zero columns.  The padding doubles
-    # the (small) projection and the MMA work but not the exponentials, which bound the attention kernel; the
-    # alternative -- fp32 CUDA-core attention -- was 85 % of the model's time.
-    def _padded(self, tag: str, owner, mats, biases, cols: bool = False):
-        """bf16 weight (+ fp32 bias) with every 32-row (or, cols=True, 32-column) head group zero-padded to 64; several
-        matrices are stacked on the output axis (one fused projection).  Cached per parameter versions."""
+    # q, k, v stay in their compact [.., H, 32] layout: the attention kernel's 64-column tiles are loaded through tensor
+    # maps whose boxes hang over the 32-column heads, so TMA fills the upper half of every tile with zeros (q.k is
+    # unchanged, the upper half of every output head is zero and is dropped by the TMA store).  Round 1 zero-padded the
+    # projection weights instead, which doubled the projections' output traffic and the attention's input traffic.
+    def _stacked(self, tag: str, owner, mats, biases):
+        """bf16 weight (+ fp32 bias) of several projections stacked on the output axis (one fused GEMM).  Cached per
+        parameter versions."""
         key = (tuple(m._version for m in mats) + tuple(m.data_ptr() for m in mats)
                + tuple(-1 if x is None else x._version for x in biases))
         hit = self._bf16.get((tag, id(owner)))
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
-        if cols:
-            (m,) = mats
-            w = torch.zeros(m.shape[0], m.shape[1] // 32, 64, device=m.device)
-            w[..., :32] = m.detach().view(m.shape[0], -1, 32)
-            w, b = w.view(m.shape[0], -1), biases[0]
-        else:
-            w = torch.cat([m.detach() for m in mats], dim=0)
-            K = w.shape[1]
-            wp = torch.zeros(w.shape[0] // 32, 64, K, device=w.device)
-            wp[:, :32] = w.view(-1, 32, K)
-            w = wp.view(-1, K)
-            if any(x is not None for x in biases):
-                bb = torch.cat([(x.detach().float() if x is not None else torch.zeros(m.shape[0], device=w.device))
-                                for x, m in zip(biases, mats)])
-                b = torch.zeros(bb.shape[0] // 32, 64, device=w.device)
-                b[:, :32] = bb.view(-1, 32)
-                b = b.view(-1)
-            else:
-                b = None
-        w = w.to(torch.bfloat16).contiguous()
+        w = torch.cat([m.detach() for m in mats], dim=0).to(torch.bfloat16).contiguous()
+        b = None
+        if any(x is not None for x in biases):
+            b = torch.cat([(x.detach().float() if x is not None else torch.zeros(m.shape[0], device=w.device))
+                           for x, m in zip(biases, mats)]).contiguous()
         self._bf16[(tag, id(owner))] = (key, w, b)
         return w, b
 
     def _attention_tc(self, q_in, kv_in, B, heads, owner, wq, wk, wv, bq, bk, bv, wo, bo, residual):
-        """bf16 path of both attention flavours: fused zero-padded projections -> tensor-core attention -> padded
-        output projection with the residual in its epilogue."""
-        P = heads * 64
+        """bf16 path of both attention flavours: fused projections -> tensor-core attention over the compact 32-wide
+        heads -> output projection with the residual in its epilogue."""
+        P = heads * 32
         s = 32.0 ** -0.25
         if q_in is kv_in:
-            w, b = self._padded("qkv", owner, (wq, wk, wv), (bq, bk, bv))
+            w, b = self._stacked("qkv", owner, (wq, wk, wv), (bq, bk, bv))
             qkv = self._proj(q_in, w, b, out_fp32=False).view(B, -1, 3 * P)
             q, k, v = qkv[..., :P], qkv[..., P:2 * P], qkv[..., 2 * P:]
         else:
-            w, b = self._padded("q", owner, (wq,), (bq,))
+            w, b = self._stacked("q", owner, (wq,), (bq,))
             q = self._proj(q_in, w, b, out_fp32=False).view(B, -1, P)
-            w, b = self._padded("kv", owner, (wk, wv), (bk, bv))
+            w, b = self._stacked("kv", owner, (wk, wv), (bk, bv))
             kv = self._proj(kv_in, w, b, out_fp32=False).view(B, -1, 2 * P)
             k, v = kv[..., :P], kv[..., P:]
-        a = ops.attention_views(q, k, v, heads, s, s).view(-1, P)
-        w, _ = self._padded("o", owner, (wo,), (bo,), cols=True)
-        return self._proj(a, w, bo, residual=residual)
+        a = ops.attention_views(q, k, v, heads, s, s, head_dim=32).view(-1, P)
+        return self._proj(a, self._wb(wo), bo, residual=residual)
 
     # ---- bf16 mode, >= 512 rows per stream: LayerNorm folded into the projections (DESIGN 3.3) ----------------
     # Every LayerNorm of the backbone feeds a projection, so with W' = bf16(gamma o W), s = rowsum(W'), c = W beta + b
     #   LN(x) W^T + b = rstd (x W'^T - mu s) + c
     # is evaluated by the projection's epilogue from the bf16 copy of the stream and its row statistics, which the
     # residual projections (out_proj / fc2) emit next to the updated fp32 stream: no LayerNorm or cast kernels.
-    def _folded(self, tag: str, owner, norm: nn.LayerNorm, mats, biases, pad: bool):
-        """(W', colsum, const) of LN(norm) followed by the stacked projections ``mats``; pad=True additionally
-        zero-pads every 32-row head group to 64 rows (tensor-core attention layout)."""
+    def _folded(self, tag: str, owner, norm: nn.LayerNorm, mats, biases):
+        """(W', colsum, const) of LN(norm) followed by the stacked projections ``mats``."""
         params = tuple(mats) + tuple(x for x in biases if x is not None) + (norm.weight, norm.bias)
         key = tuple(x._version for x in params) + tuple(x.data_ptr() for x in params)
         hit = self._bf16.get((tag, id(owner)))
@@ -347,15 +329,7 @@ class TwoStreamDenoiser(nn.Module):
         w = torch.cat([m.detach().float() for m in mats], dim=0)
         b = torch.cat([(x.detach().float() if x is not None else torch.zeros(m.shape[0], device=w.device))
                        for x, m in zip(biases, mats)])
-        wf, colsum, const = fold_layernorm_into_linear(w, b, norm.weight.detach(), norm.bias.detach())
-        if pad:
-            K = wf.shape[1]
-            wp = torch.zeros(wf.shape[0] // 32, 64, K, device=wf.device, dtype=wf.dtype)
-            wp[:, :32] = wf.view(-1, 32, K)
-            cp, kp = torch.zeros(wf.shape[0] // 32, 64, device=wf.device), torch.zeros(wf.shape[0] // 32, 64, device=wf.device)
-            cp[:, :32], kp[:, :32] = colsum.view(-1, 32), const.view(-1, 32)
-            wf, colsum, const = wp.view(-1, K).contiguous(), cp.view(-1).contiguous(), kp.view(-1).contiguous()
-        out = (wf, colsum, const)
+        out = fold_layernorm_into_linear(w, b, norm.weight.detach(), norm.bias.detach())
         self._bf16[(tag, id(owner))] = (key, out)
         return out
 
@@ -363,26 +337,25 @@ class TwoStreamDenoiser(nn.Module):
         """``stream`` (fp32, updated IN PLACE) += proj(attention(LN_q(q stream), LN_kv(kv stream))); q_src / kv_src are
         (bf16 copy, row statistics) pairs.  Returns the new (bf16 copy, statistics) of ``stream``."""
         heads = self.denoiser_backbone.num_heads
-        P = heads * 64
+        P = heads * 32
         s = 32.0 ** -0.25
         wq, wk, wv = attn.wq, attn.wk, attn.wv
         if q_src is kv_src:
-            w, cs, c = self._folded("f_qkv", attn, q_norm, (wq.weight, wk.weight, wv.weight), (wq.bias, wk.bias, wv.bias), True)
+            w, cs, c = self._folded("f_qkv", attn, q_norm, (wq.weight, wk.weight, wv.weight), (wq.bias, wk.bias, wv.bias))
             qkv = ops.linear_layernorm_folded(q_src[0], q_src[1], w, cs, c, eps=LN_EPS).view(B, -1, 3 * P)
             q, k, v = qkv[..., :P], qkv[..., P:2 * P], qkv[..., 2 * P:]
         else:
-            w, cs, c = self._folded("f_q", attn, q_norm, (wq.weight,), (wq.bias,), True)
+            w, cs, c = self._folded("f_q", attn, q_norm, (wq.weight,), (wq.bias,))
             q = ops.linear_layernorm_folded(q_src[0], q_src[1], w, cs, c, eps=LN_EPS).view(B, -1, P)
-            w, cs, c = self._folded("f_kv", attn, kv_norm, (wk.weight, wv.weight), (wk.bias, wv.bias), True)
+            w, cs, c = self._folded("f_kv", attn, kv_norm, (wk.weight, wv.weight), (wk.bias, wv.bias))
             kv = ops.linear_layernorm_folded(kv_src[0], kv_src[1], w, cs, c, eps=LN_EPS).view(B, -1, 2 * P)
             k, v = kv[..., :P], kv[..., P:]
-        a = ops.attention_views(q, k, v, heads, s, s).view(-1, P)
-        wo, _ = self._padded("o", attn, (attn.proj.weight,), (attn.proj.bias,), cols=True)
-        return ops.linear_residual_stats(a, wo, attn.proj.bias.detach().float(), stream)
+        a = ops.attention_views(q, k, v, heads, s, s, head_dim=32).view(-1, P)
+        return ops.linear_residual_stats(a, self._wb(attn.proj.weight), attn.proj.bias.detach().float(), stream)
 
     def _mlp_fold(self, src, norm: nn.LayerNorm, mlp: _Mlp, stream: torch.Tensor):
         """``stream`` += fc2(gelu(fc1(LN(stream)))) in place; returns its new (bf16 copy, statistics)."""
-        w, cs, c = self._folded("f_fc1", mlp, norm, (mlp.fc1.weight,), (mlp.fc1.bias,), False)
+        w, cs, c = self._folded("f_fc1", mlp, norm, (mlp.fc1.weight,), (mlp.fc1.bias,))
         hid = ops.linear_layernorm_folded(src[0], src[1], w, cs, c, eps=LN_EPS, gelu=True)
         return ops.linear_residual_stats(hid, self._wb(mlp.fc2.weight), mlp.fc2.bias.detach().float(), stream)
 

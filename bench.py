@@ -470,7 +470,7 @@ def run_twostream(args):
         "roofline": {"kernel": "whole step (backbone projections + attention)", "bound": "tensor", "achieved": tf,
                      "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": tf / pk["tf_sustained"], "traffic": None,
                      "peak_source": pk["source"] + ", sustained",
-                     "note": "useful FLOP only (the zero-padded halves of the 32-wide heads are not counted)"},
+                     "note": "useful FLOP only (the zero-filled upper halves of the 32-wide head tiles are not counted)"},
         "clocks": clk}))
 
 

@@ -222,6 +222,15 @@ PCD_API int pcd_attention_hd32(const pcd_attn_operand* q, const pcd_attn_operand
                                float* out, int64_t out_batch_stride, int64_t out_row_stride, int batch, int heads,
                                int len_q, int len_kv, float q_scale, float k_scale, void* stream);
 
+/* The same product on tensor cores (bf16 operands [.., H, 32], bf16 out [.., H, 32]): the grouped 64-wide kernel with
+ * tensor maps whose 64-column boxes hang over the 32-column heads -- TMA zero-fills the missing columns on load and
+ * drops them on store, so no zero-padded copy of q / k / v exists in memory.  `variant`: a grouped pcd_attn_variant or
+ * PCD_ATTN_DEFAULT. */
+PCD_API int pcd_attention_hd32_bf16(const pcd_attn_operand* q, const pcd_attn_operand* k, const pcd_attn_operand* v,
+                            void* out, int64_t out_batch_stride, int64_t out_row_stride,
+                            int batch, int heads, int len_q, int len_kv,
+                            float q_scale, float k_scale, int variant, void* stream);
+
 /* Stand-alone form of the rotation (apply_rotary_pos_emb, rotaryencoderpcd.py:6-27; fp32 arithmetic): rotate head
  * dims 0..5 of a bf16 q or k operand IN PLACE with theta = pi * coords[b, l, :].  pcd_attention does this inside the
  * kernel; this entry exists for callers that want rotated projections for something else (and as the test yardstick

@@ -202,6 +202,15 @@ def test_rotary_attention_tiles(dtype):
     same(plain, got)
 
 
+@pytest.mark.parametrize("Lq,Lkv", [(131, 77), (643, 643), (1, 64)])
+def test_attention_hd32_bf16_tiles(Lq, Lkv):
+    """32-wide heads through 64-column TMA boxes: the store must drop the out-of-tensor half of every row."""
+    B, H = 3, 4
+    q, k, v = (bf(det.normal((B, n, H * 32), 9075 + i)) for i, n in enumerate((Lq, Lkv, Lkv)))
+    plain, got, _ = run_both(lambda q, k, v: ops.attention_views(q, k, v, H, 0.42, 0.42, head_dim=32), (q, k, v))
+    same(plain, got)
+
+
 def test_attention_hd32_tiles():
     B, H, Lq, Lkv = 2, 4, 131, 77
     q, k, v = (det.normal((B, n, H * 32), 9070 + i).to(DEV) for i, n in enumerate((Lq, Lkv, Lkv)))

@@ -300,6 +300,31 @@ def test_attention_bf16_variants_vs_torch(variant, B, heads, L, std):
     assert float(per) < 1e-2, float(per)
 
 
+@pytest.mark.parametrize("variant", [0, 8, 10, 11])
+@pytest.mark.parametrize("B,H,Lq,Lkv", [(3, 8, 643, 643), (2, 8, 1024, 643), (2, 8, 643, 1024), (4, 2, 70, 5), (1, 1, 1, 64),
+                                        (64, 8, 257, 129)])
+def test_attention_hd32_bf16(variant, B, H, Lq, Lkv):
+    """32-wide heads (TwoStream CrossAttention, reference models/modules.py:17-63) on the 64-wide tensor-core kernel:
+    compact [.., H, 32] operands, the missing 32 columns of every tile zero-filled by TMA, output written compactly.
+    Against an fp32 torch evaluation of the same bf16 inputs; operands are column blocks of one fused buffer."""
+    gen = torch.Generator(device="cpu").manual_seed(5000 + Lq + Lkv)
+    D = H * 32
+    qb = (torch.randn(B, Lq, D, generator=gen) * 1.4).to(DEV).bfloat16()
+    kvb = (torch.randn(B, Lkv, 2 * D, generator=gen) * 1.4).to(DEV).bfloat16()
+    q, k, v = qb, kvb[..., :D], kvb[..., D:]
+    s = 32.0 ** -0.25
+    w = torch.einsum("bthc,bshc->bhts", q.float().view(B, Lq, H, 32), k.float().reshape(B, Lkv, H, 32)) * (s * s)
+    want = torch.einsum("bhts,bshc->bthc", torch.softmax(w, -1), v.float().reshape(B, Lkv, H, 32)).reshape(B, Lq, D)
+    got = ops.attention_views(q, k, v, H, s, s, variant=variant, head_dim=32)
+    torch.cuda.synchronize()
+    assert got.shape == (B, Lq, D) and torch.isfinite(got.float()).all()
+    assert rel(got.float(), want) < 1e-2, describe(got.float(), want, f"hd32 v{variant} B{B} H{H} Lq{Lq} Lkv{Lkv}")
+    per = ((got.float() - want).flatten(1).norm(dim=1) / want.flatten(1).norm(dim=1)).max()
+    assert float(per) < 1e-2, float(per)
+    with pytest.raises(RuntimeError):
+        ops.attention_views(q, k, v, H, s, s, variant=5, head_dim=32)   # the paired kernel stores from registers
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_attention_bf16_random_lengths(seed):
     """The dispatcher over random (len_q, len_kv, sequences, heads): every tail length 0..63 class (tail-key forms for

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(P._lib.EXPORTED_SYMBOLS), declared ^ set(P._lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pcd_abi_version() == P._lib.ABI_VERSION == 3
+    assert lib.pcd_abi_version() == P._lib.ABI_VERSION == 4
 
 
 def test_product_never_imports_the_oracle():
