@@ -540,10 +540,13 @@ class TwoStreamDenoiser(nn.Module):
             xs = self._mlp(xs, blk.write.norm_x2, blk.write.mlp)
         return z, xs
 
-    def _blocks_folded(self, z: torch.Tensor, xs: torch.Tensor, S: int):
+    def _blocks_folded(self, z: torch.Tensor, xs: torch.Tensor, S: int, xsrc=None):
         """The same blocks with every LayerNorm folded into the projection that consumes it; z and xs (fp32 [rows, d])
-        are updated in place, ``zs`` / ``xsrc`` carry the (bf16 copy, row statistics) of either stream."""
-        zs, xsrc = ops.cast_rowstats(z), ops.cast_rowstats(xs)
+        are updated in place, ``zs`` / ``xsrc`` carry the (bf16 copy, row statistics) of either stream (the x stream's
+        first pair normally comes out of the token-assembly kernel)."""
+        zs = ops.cast_rowstats(z)
+        if xsrc is None:
+            xsrc = ops.cast_rowstats(xs)
         for blk in self.denoiser_backbone.blocks:
             zs = self._attend_fold(zs, blk.read.norm_z1, xsrc, blk.read.norm_x, S, blk.read.attn, z)
             zs = self._mlp_fold(zs, blk.read.norm_z2, blk.read.mlp, z)
@@ -562,10 +565,23 @@ class TwoStreamDenoiser(nn.Module):
         d, n_cond = self.latent_dim, cond.shape[1]
         n_lat = bb.num_z + n_cond + 1
 
-        # x stream: input_proj + ln_pre (modules.py:223-224); K = 3 -> CUDA-core GEMM
-        pts = x.float().permute(0, 2, 1).contiguous().view(S * self.num_points, -1)
-        xs = self._lin_k3(pts, bb.input_proj)
-        xs = self._ln(xs, bb.ln_pre, act=False)
+        fold = (self.fold_layernorm and self.compute_dtype == torch.bfloat16 and d % 256 == 0
+                and min(S * n_lat, S * self.num_points) >= 512)
+        # x stream: input_proj + ln_pre (modules.py:223-224) in the token-assembly kernel (reads x in its NCL layout,
+        # weights in registers; on the folded path it also emits the bf16 copy + row statistics of the stream)
+        xsrc = None
+        if d <= 512 and d % 4 == 0 and x.shape[1] in (3, 6):
+            r = ops.embed_tokens(x.float().contiguous(), bb.input_proj.weight.detach().float().contiguous(),
+                                 bb.input_proj.bias.detach().float(), None, None, bb.ln_pre.weight.detach(),
+                                 bb.ln_pre.bias.detach(), eps=LN_EPS, with_stats=fold)
+            if fold:
+                xs, xsrc = r[0].view(S * self.num_points, d), (r[1].view(S * self.num_points, d), r[2])
+            else:
+                xs = r.view(S * self.num_points, d)
+        else:
+            pts = x.float().permute(0, 2, 1).contiguous().view(S * self.num_points, -1)
+            xs = self._lin_k3(pts, bb.input_proj)
+            xs = self._ln(xs, bb.ln_pre, act=False)
 
         # latent stream with self-conditioning (modules.py:226-229)
         z = torch.empty(S, n_lat, d, device=dev)
@@ -579,12 +595,13 @@ class TwoStreamDenoiser(nn.Module):
         prev = self._lin(hid, bb.latent_mlp.fc2, residual=prev)
         z = ops.add(z, self._ln(prev, bb.ln_latent, act=False))
 
-        fold = (self.fold_layernorm and self.compute_dtype == torch.bfloat16 and d % 256 == 0
-                and min(z.shape[0], xs.shape[0]) >= 512)
-        z, xs = (self._blocks_folded if fold else self._blocks_plain)(z, xs, S)
+        z, xs = self._blocks_folded(z, xs, S, xsrc) if fold else self._blocks_plain(z, xs, S)
 
-        out = ops.linear(self._ln(xs, bb.ln_post, act=False), bb.output_proj.weight.detach(), bb.output_proj.bias.detach())
-        return out.view(S, self.num_points, -1).permute(0, 2, 1).contiguous(), z.view(S, n_lat, d)
+        # ln_post + output_proj + the permute back to [S, C_out, N] (modules.py:240-243) in one kernel
+        out = ops.output_proj(xs.view(S, self.num_points, d), 0, bb.ln_post.weight.detach(), bb.ln_post.bias.detach(),
+                              bb.output_proj.weight.detach().float().contiguous(), bb.output_proj.bias.detach().float(),
+                              eps=LN_EPS)
+        return out, z.view(S, n_lat, d)
 
     @torch.no_grad()
     def forward(self, x, t, class_labels=None, viewpoints=None, partial_pcd=None, depth_maps=None, prev_latent=None):
